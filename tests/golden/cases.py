@@ -1,0 +1,106 @@
+"""Golden-vector case list shared by the generator (reference side) and the tests.
+
+Each case is plain data: a network *spec* (see oracle/ntk_oracle.py docstring),
+input shapes and RNG seeds.  Inputs are regenerated from the seeds with
+`numpy.random.default_rng(seed).standard_normal(shape)`, so the
+committed fixture only needs the reference outputs.
+"""
+import numpy as np
+
+SQ2 = 2 ** 0.5
+RELU = ('abrelu', 0., 1., False)
+
+
+def conv(k=(3, 3), s=(1, 1), pad='SAME', W=SQ2, b=0.):
+  return ('conv', tuple(k), tuple(s), pad, W, b)
+
+
+def pool(w=(2, 2), s=(2, 2), pad='VALID', ne=False):
+  return ('avgpool', tuple(w), tuple(s), pad, ne)
+
+
+def myrtle(depth, tail='flatten'):
+  f = {5: [2, 1, 1], 7: [2, 2, 2], 10: [3, 3, 3]}[depth]
+  layers = [conv(), RELU] * f[0] + [pool()] + [conv(), RELU] * f[1] + [pool()] + [conv(), RELU] * f[2]
+  layers += ([pool()] * 3 + [('flatten',)]) if tail == 'flatten' else [('gap',)]
+  layers += [('dense', SQ2, 0.)]
+  return ('serial', layers)
+
+
+def fcn(depth=3, W=2., b=0.05):
+  layers = []
+  for _ in range(depth):
+    layers += [('dense', W, b), RELU]
+  return ('serial', layers + [('dense', W, b)])
+
+
+def wrn_block(stride, channel_mismatch, act=RELU):
+  """README.md:192-222 WideResnetBlock: pre-activation residual block."""
+  main = ('serial', [act, conv(s=(stride, stride), W=1., b=0.1), act, conv(W=1., b=0.1)])
+  shortcut = ('identity',) if not channel_mismatch else conv(s=(stride, stride), W=1., b=0.1)
+  return ('serial', [('fanout', 2), ('parallel', [main, shortcut]), ('faninsum',)])
+
+
+def wrn(act=RELU):
+  return ('serial', [conv(W=1., b=0.1),
+                     wrn_block(1, True, act), wrn_block(1, False, act),
+                     wrn_block(2, True, act), wrn_block(1, False, act),
+                     ('gap',), ('dense', 1., 0.1)])
+
+
+# name -> (spec, x1_shape, x2_shape_or_None, get)
+CASES = {
+    'fcn3': (fcn(3), (6, 784), (5, 784), ('nngp', 'ntk')),
+    'fcn3_sym': (fcn(3), (7, 784), None, ('nngp', 'ntk')),
+    'fcn1_nngp': (fcn(1), (4, 32), (3, 32), ('nngp',)),
+    'myrtle5': (myrtle(5), (2, 32, 32, 3), (2, 32, 32, 3), ('nngp', 'ntk')),
+    'myrtle5_gap': (myrtle(5, 'gap'), (2, 32, 32, 3), (1, 32, 32, 3), ('nngp', 'ntk')),
+    'myrtle7': (myrtle(7), (2, 32, 32, 3), (1, 32, 32, 3), ('nngp', 'ntk')),
+    'myrtle10': (myrtle(10), (2, 32, 32, 3), (2, 32, 32, 3), ('nngp', 'ntk')),
+    'myrtle10_sym': (myrtle(10), (2, 32, 32, 3), None, ('nngp', 'ntk')),
+    'myrtle10_16px': (('serial', [conv(), RELU] * 3 + [pool()] + [conv(), RELU] * 3 + [pool()] +
+                       [conv(), RELU] * 3 + [('gap',), ('dense', SQ2, 0.)]),
+                      (3, 16, 16, 3), (4, 16, 16, 3), ('nngp', 'ntk')),
+    'conv_pool_stride': (('serial', [conv(W=1.3, b=0.2), RELU, pool(), conv(s=(2, 2), W=1.1, b=0.1),
+                                     RELU, ('gap',), ('dense', 1.2, 0.3)]),
+                         (3, 8, 8, 3), (4, 8, 8, 3), ('nngp', 'ntk')),
+    'conv_flatten_bias': (('serial', [conv(W=1.5, b=0.3), RELU, conv(W=1.2, b=0.1), RELU,
+                                      ('flatten',), ('dense', 1., 0.5)]),
+                          (3, 6, 5, 2), (2, 6, 5, 2), ('nngp', 'ntk')),
+    'erf_valid': (('serial', [conv(W=1.2, b=0.1), ('erf', 1., 1., 0.),
+                              conv(k=(2, 3), pad='VALID', W=1.1, b=0.2), ('erf', 0.8, 1.3, 0.2),
+                              ('flatten',), ('dense', 1., 0.1)]),
+                  (3, 6, 5, 2), (4, 6, 5, 2), ('nngp', 'ntk')),
+    'erf_pool_same': (('serial', [conv(W=1.2, b=0.1), ('erf', 1., 1., 0.),
+                                  pool((2, 2), (1, 1), 'SAME', False), conv(W=1., b=0.),
+                                  ('erf', 1., 0.7, 0.), ('gap',), ('dense', 1., 0.)]),
+                      (2, 6, 6, 3), (3, 6, 6, 3), ('nngp', 'ntk')),
+    'circular': (('serial', [conv(pad='CIRCULAR', W=1.3, b=0.1), RELU,
+                             pool((2, 2), (2, 2), 'CIRCULAR', False),
+                             conv(k=(3, 2), pad='CIRCULAR'), RELU, ('gap',), ('dense', 1., 0.)]),
+                 (2, 8, 6, 3), (3, 8, 6, 3), ('nngp', 'ntk')),
+    'pool_norm_edges': (('serial', [conv(), RELU, pool((3, 3), (2, 2), 'SAME', True), conv(), RELU,
+                                    ('gap',), ('dense', 1., 0.)]),
+                        (2, 7, 7, 2), (2, 7, 7, 2), ('nngp', 'ntk')),
+    'leaky_abs': (('serial', [conv(W=1.1, b=0.2), ('abrelu', 0.2, 1., False), conv(),
+                              ('abrelu', -1., 1., False), ('gap',), ('dense', 1., 0.1)]),
+                  (3, 5, 5, 2), (2, 5, 5, 2), ('nngp', 'ntk')),
+    'relu_stabilize': (('serial', [conv(W=1.1, b=0.2), ('abrelu', 0., 1., True), conv(),
+                                   ('abrelu', 0., 1., True), ('gap',), ('dense', 1., 0.1)]),
+                       (3, 5, 5, 2), (2, 5, 5, 2), ('nngp', 'ntk')),
+    'wrn_relu': (wrn(RELU), (3, 8, 8, 3), (2, 8, 8, 3), ('nngp', 'ntk')),
+    'wrn_erf': (wrn(('erf', 1., 1., 0.)), (2, 8, 8, 3), (3, 8, 8, 3), ('nngp', 'ntk')),
+    'wrn_relu_sym': (wrn(RELU), (3, 8, 8, 3), None, ('nngp', 'ntk')),
+    # Full `Kernel` outputs (get=None) with spatial axes: layout / is_reversed contract (F4).
+    'kernel_conv_relu': (('serial', [conv(W=1.2, b=0.1), RELU]), (2, 4, 3, 2), (3, 4, 3, 2), None),
+    'kernel_conv2_pool': (('serial', [conv(W=1.2, b=0.1), RELU, conv(k=(3, 2)), RELU, pool((2, 1), (2, 1))]),
+                          (2, 4, 4, 2), None, None),
+}
+
+
+def make_inputs(name):
+  _, s1, s2, _ = CASES[name]
+  idx = list(CASES).index(name)  # seeds are derived from the (append-only) case order
+  x1 = np.random.default_rng(1000 + 2 * idx).standard_normal(s1).astype(np.float32)
+  x2 = None if s2 is None else np.random.default_rng(1001 + 2 * idx).standard_normal(s2).astype(np.float32)
+  return x1, x2

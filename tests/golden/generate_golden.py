@@ -1,0 +1,83 @@
+"""Generates tests/golden/golden.npz by running the REFERENCE's own stax code.
+
+Run in the build container only:  python tests/golden/generate_golden.py
+
+The reference (/root/reference, unmodified, read-only) is executed in float64 on
+the NumPy jax shim (oracle/jax_shim, see its README for what is substituted).
+For every case in cases.py the reference network is assembled from the spec with
+the reference's public layer constructors and `kernel_fn(x1, x2, get)` is
+evaluated; outputs are stored under '<case>/<field>'.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+import cases  # noqa: E402
+import ref_loader  # noqa: E402
+
+
+def build(spec, stax):
+  kind = spec[0]
+  if kind == 'serial':
+    return stax.serial(*[build(s, stax) for s in spec[1]])
+  if kind == 'parallel':
+    return stax.parallel(*[build(s, stax) for s in spec[1]])
+  if kind == 'fanout':
+    return stax.FanOut(spec[1])
+  if kind == 'faninsum':
+    return stax.FanInSum()
+  if kind == 'identity':
+    return stax.Identity()
+  if kind == 'dense':
+    return stax.Dense(1, W_std=spec[1], b_std=spec[2])
+  if kind == 'conv':
+    return stax.Conv(1, spec[1], strides=spec[2], padding=spec[3], W_std=spec[4], b_std=spec[5])
+  if kind == 'abrelu':
+    return stax.ABRelu(spec[1], spec[2], do_stabilize=spec[3])
+  if kind == 'erf':
+    return stax.Erf(spec[1], spec[2], spec[3])
+  if kind == 'avgpool':
+    return stax.AvgPool(spec[1], strides=spec[2], padding=spec[3], normalize_edges=spec[4])
+  if kind == 'gap':
+    return stax.GlobalAvgPool()
+  if kind == 'flatten':
+    return stax.Flatten()
+  raise ValueError(kind)
+
+
+def main():
+  warnings.simplefilter('ignore')
+  stax = ref_loader.load_reference_stax()
+  out = {}
+  for name, (spec, _, _, get) in cases.CASES.items():
+    x1, x2 = cases.make_inputs(name)
+    _, _, kernel_fn = build(spec, stax)
+    import jax.numpy as jnp   # the shim: immutable float64 arrays
+    x1d = jnp.asarray(x1, np.float64)
+    x2d = None if x2 is None else jnp.asarray(x2, np.float64)
+    res = kernel_fn(x1d, x2d, get)
+    if get is None:
+      for f in ('nngp', 'ntk', 'cov1', 'cov2'):
+        v = getattr(res, f)
+        if v is not None:
+          out[f'{name}/{f}'] = np.asarray(v, np.float64)
+      out[f'{name}/is_reversed'] = np.asarray(bool(res.is_reversed))
+      out[f'{name}/is_gaussian'] = np.asarray(bool(res.is_gaussian))
+      out[f'{name}/shape1'] = np.asarray(res.shape1)
+      out[f'{name}/shape2'] = np.asarray(res.shape2)
+    else:
+      for f in get:
+        out[f'{name}/{f}'] = np.asarray(getattr(res, f), np.float64)
+    print(name, {k.split('/')[1]: v.shape for k, v in out.items() if k.startswith(name + '/')})
+  path = os.path.join(HERE, 'golden.npz')
+  np.savez_compressed(path, **out)
+  print('wrote', path, os.path.getsize(path), 'bytes')
+
+
+if __name__ == '__main__':
+  main()
