@@ -1,0 +1,182 @@
+/*
+ * ntk_b200.h — C-ABI of the B200-native analytic NNGP/NTK kernel path.
+ *
+ * Drop-in boundary for google/neural-tangents' `stax` `kernel_fn(x1, x2, get)`
+ * and the `nt.batch` Gram tiling.  The reference has no FFI of its own (it is
+ * pure Python on JAX/XLA); every entry point below cites the reference
+ * interface it replaces (paths relative to /root/reference/neural_tangents/).
+ * INTEGRATION.md shows the reference-side binding (ctypes today, an XLA-FFI
+ * handler over the same symbols when jaxlib headers are available).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes only; no C++/torch/JAX types.
+ *  - Every function returns 0 on success or a negative NTK_E* code and never
+ *    throws; `ntk_last_error()` returns a thread-local message.
+ *  - dtype: NTK_F32 or NTK_F64 is both the storage and the arithmetic type
+ *    (`_src/stax/requirements.py:794`: float32 unless jax_enable_x64).
+ *  - Spatial tensors use the canonical zipped layout [n1, n2, h, h', w, w']
+ *    (`_src/utils/kernel.py:32-36` with is_reversed == False); the Python
+ *    front end presents the reference's per-Conv axis reversal lazily.
+ *  - There is NO CPU fallback: every compute entry point needs a CUDA device.
+ */
+#ifndef NTK_B200_H_
+#define NTK_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NTK_B200_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------ */
+#define NTK_OK 0
+#define NTK_EINVAL (-1)        /* bad argument / malformed program            */
+#define NTK_ECUDA (-2)         /* CUDA runtime error (see ntk_last_error)     */
+#define NTK_ENOMEM (-3)        /* workspace too small / allocation failed     */
+#define NTK_ENOTGAUSSIAN (-4)  /* activation on a non-Gaussian input
+                                  (`_src/stax/elementwise.py:1267-1270`)     */
+#define NTK_EUNSUPPORTED (-5)  /* valid in the reference, outside this path   */
+#define NTK_ESHAPE (-6)        /* FanInSum shape mismatch
+                                  (`_src/stax/branching.py:71-75`)           */
+
+/* ---- dtypes ------------------------------------------------------------ */
+#define NTK_F32 0
+#define NTK_F64 1
+
+/* ---- op kinds (one per in-scope reference layer rule) -------------------- */
+enum {
+  NTK_OP_DENSE = 1,    /* `_src/stax/linear.py:899-926`   f[0]=W_std^2 f[1]=b_std^2 (i[0]=has_bias)      */
+  NTK_OP_CONV = 2,     /* `_src/stax/linear.py:1321-1424` i = {kh,kw,sh,sw,padding,has_bias}
+                                                          f[0]=W_std^2 f[1]=b_std^2                      */
+  NTK_OP_ABRELU = 3,   /* `_src/stax/elementwise.py:423-477` f[0]=a f[1]=b, i[0]=do_stabilize           */
+  NTK_OP_ERF = 4,      /* `_src/stax/elementwise.py:67-112`  f[0]=a f[1]=b f[2]=c                        */
+  NTK_OP_AVGPOOL = 5,  /* `_src/stax/linear.py:1631-1664,3499-3572`
+                                                          i = {wh,ww,sh,sw,padding,normalize_edges}      */
+  NTK_OP_GAP = 6,      /* `_src/stax/linear.py:1771-1801`                                               */
+  NTK_OP_FLATTEN = 7,  /* `_src/stax/linear.py:1865-1899`                                               */
+  NTK_OP_FANINSUM = 8, /* `_src/stax/branching.py:55-117`  dst = src + src2                              */
+  NTK_OP_IDENTITY = 9  /* `_src/stax/linear.py:107-119`    dst = src (FanOut is expressed by slot reuse) */
+};
+
+/* padding modes (`_src/stax/linear.py:54-69`) */
+#define NTK_PAD_VALID 0
+#define NTK_PAD_SAME 1
+#define NTK_PAD_CIRCULAR 2
+
+/*
+ * One layer application in slot (SSA-like) form: dst = op(src [, src2]).
+ * `serial` (`_src/stax/combinators.py:40-68`) becomes consecutive ops;
+ * `FanOut`/`parallel`/`FanInSum` (`_src/stax/branching.py:36-117`,
+ * `_src/stax/combinators.py:166-198`) become slot reuse + NTK_OP_FANINSUM.
+ * Slot 0 holds the input kernel (built from x1/x2 or supplied by the caller).
+ */
+typedef struct ntk_op {
+  int32_t kind;
+  int32_t src;
+  int32_t src2; /* -1 unless NTK_OP_FANINSUM */
+  int32_t dst;
+  int32_t i[6];
+  double f[4];
+} ntk_op_t;
+
+/* A kernel state crossing the ABI (Kernel-in / Kernel-out composition,
+ * `_src/stax/requirements.py:935-937,1039-1044`; fields of
+ * `_src/utils/kernel.py:124-145`).  Pointers are HOST pointers for the *_host
+ * entry points and DEVICE pointers for the *_device ones.  Spatial tensors are
+ * [n1,n2,H,H,W,W] (nngp, ntk) and [n,H,H,W,W] (cov); H == W == 0 means the
+ * spatial axes have been pooled away ([n1,n2] and [n]). */
+typedef struct ntk_state {
+  void* nngp;
+  void* ntk;  /* NULL when ntk_mode != NTK_NTK_TENSOR */
+  void* cov1;
+  void* cov2; /* NULL <=> x2 is None (cov2 == cov1) */
+  int32_t n1, n2;
+  int32_t H, W;
+  int32_t ntk_mode;    /* NTK_NTK_* below */
+  int32_t is_gaussian; /* `_src/utils/kernel.py:131` */
+} ntk_state_t;
+
+#define NTK_NTK_NONE 0   /* ntk not requested (`requirements.py:943`)         */
+#define NTK_NTK_ZERO 1   /* the 0-d zero of `requirements.py:807`             */
+#define NTK_NTK_TENSOR 2
+
+/* flags for the gram entry points */
+#define NTK_FLAG_NTK 1u          /* compute ntk as well as nngp                */
+#define NTK_FLAG_NO_FUSION 2u    /* force the one-kernel-per-layer path        */
+#define NTK_FLAG_WANT_COV 4u     /* also return cov1 / cov2                    */
+
+typedef struct ntk_program ntk_program_t;
+typedef struct ntk_context ntk_context_t;
+
+/* ---- library ------------------------------------------------------------ */
+int ntk_abi_version(void);
+const char* ntk_last_error(void);
+int ntk_device_count(int* count);
+
+/* ---- programs (replace the closure tree built by `stax.serial(...)`) ---- */
+int ntk_program_create(const ntk_op_t* ops, int32_t n_ops, int32_t n_slots, int32_t out_slot,
+                       ntk_program_t** out);
+void ntk_program_destroy(ntk_program_t* prog);
+
+/* Output geometry of `prog` for inputs of spatial size H x W (0,0 for [N,d]
+ * inputs): replaces the `eval_shape` walk of `requirements.py:833-879`.     */
+int ntk_program_output_shape(const ntk_program_t* prog, int32_t H, int32_t W,
+                             int32_t in_is_gaussian, int32_t* out_H, int32_t* out_W,
+                             int32_t* out_is_gaussian);
+
+/* ---- contexts: one per (host thread, GPU) -------------------------------
+ * Own a stream, a device workspace and pinned staging buffers; replace the
+ * PjRt client/executable cache behind `jit`/`pmap` in `_src/batching.py:689-787`. */
+int ntk_context_create(int32_t device, size_t workspace_bytes, ntk_context_t** out);
+void ntk_context_destroy(ntk_context_t* ctx);
+int ntk_context_synchronize(ntk_context_t* ctx);
+/* cudaStream_t of the context as an opaque pointer (for event timing by the host). */
+void* ntk_context_stream(ntk_context_t* ctx);
+/* Number of CUDA kernels this context has launched so far (bench `gpu_launches`). */
+int64_t ntk_context_launch_count(const ntk_context_t* ctx);
+
+/* ---- the hot path --------------------------------------------------------
+ * kernel_fn(x1, x2, get) on raw inputs (`requirements.py:939-953`):
+ *   x1: [n1, H, W, C] (or [n1, C] with H == W == 0), x2 likewise or NULL (== x1).
+ * Results: nngp/ntk [n1, n2] row-major with leading dimension `ld` (elements),
+ * or [n1, n2, Ho, Ho, Wo, Wo] when the program keeps spatial axes (then `ld`
+ * is ignored).  cov1/cov2 ([n1..], [n2..]) only with NTK_FLAG_WANT_COV.
+ * The call tiles the n1 x n2 pair grid internally to fit the workspace
+ * (the role of `nt.batch`'s serial loop, `batching.py:314-502`).
+ */
+
+/* HOST buffers in, HOST buffers out; copies run on the context stream and the
+ * call returns after the results have landed. */
+int ntk_gram_host(ntk_context_t* ctx, const ntk_program_t* prog, int32_t dtype, const void* x1,
+                  int32_t n1, const void* x2, int32_t n2, int32_t H, int32_t W, int32_t C,
+                  uint32_t flags, void* nngp, void* ntk, int64_t ld, void* cov1, void* cov2);
+
+/* DEVICE buffers in/out, asynchronous on the context stream. */
+int ntk_gram_device(ntk_context_t* ctx, const ntk_program_t* prog, int32_t dtype, const void* x1,
+                    int32_t n1, const void* x2, int32_t n2, int32_t H, int32_t W, int32_t C,
+                    uint32_t flags, void* nngp, void* ntk, int64_t ld, void* cov1, void* cov2);
+
+/* Kernel-in / Kernel-out: apply `prog` to a caller-supplied kernel state
+ * (`requirements.py:935-937`).  `out` pointers must be preallocated to the
+ * geometry reported by ntk_program_output_shape.  HOST pointers. */
+int ntk_apply_host(ntk_context_t* ctx, const ntk_program_t* prog, int32_t dtype,
+                   const ntk_state_t* in, ntk_state_t* out);
+
+/* Workspace (bytes) one tile of t1 x t2 pairs needs; lets callers size
+ * contexts (`README.md:387-396` documents the reference's batch-size limits). */
+int ntk_workspace_bytes(const ntk_program_t* prog, int32_t dtype, int32_t t1, int32_t t2, int32_t H,
+                        int32_t W, int32_t C, uint32_t flags, size_t* bytes);
+
+/* ---- device memory helpers (so a host language needs no CUDA binding) ---- */
+int ntk_device_malloc(int32_t device, size_t bytes, void** ptr);
+int ntk_device_free(int32_t device, void* ptr);
+int ntk_memcpy_h2d(ntk_context_t* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int ntk_memcpy_d2h(ntk_context_t* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTK_B200_H_ */

@@ -1,0 +1,277 @@
+"""ctypes binding of libntk_b200.so (the C-ABI declared in include/ntk_b200.h).
+
+Fails loudly: if the shared library is missing or no CUDA device is usable,
+every compute entry point raises — there is no CPU or PyTorch fallback.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libntk_b200.so')
+
+NTK_F32, NTK_F64 = 0, 1
+OP_DENSE, OP_CONV, OP_ABRELU, OP_ERF, OP_AVGPOOL, OP_GAP, OP_FLATTEN, OP_FANINSUM, OP_IDENTITY = range(1, 10)
+PAD = {'VALID': 0, 'SAME': 1, 'CIRCULAR': 2}
+NTK_NONE, NTK_ZERO, NTK_TENSOR = 0, 1, 2
+FLAG_NTK, FLAG_NO_FUSION, FLAG_WANT_COV = 1, 2, 4
+
+E_INVAL, E_CUDA, E_NOMEM, E_NOTGAUSSIAN, E_UNSUPPORTED, E_SHAPE = -1, -2, -3, -4, -5, -6
+
+# every symbol include/ntk_b200.h declares (checked by tests/test_abi.py)
+EXPORTED_SYMBOLS = (
+    'ntk_abi_version', 'ntk_last_error', 'ntk_device_count', 'ntk_program_create',
+    'ntk_program_destroy', 'ntk_program_output_shape', 'ntk_context_create', 'ntk_context_destroy',
+    'ntk_context_synchronize', 'ntk_context_stream', 'ntk_context_launch_count', 'ntk_gram_host',
+    'ntk_gram_device', 'ntk_apply_host', 'ntk_workspace_bytes', 'ntk_device_malloc',
+    'ntk_device_free', 'ntk_memcpy_h2d', 'ntk_memcpy_d2h')
+
+
+class NtkOp(ctypes.Structure):
+  _fields_ = [('kind', ctypes.c_int32), ('src', ctypes.c_int32), ('src2', ctypes.c_int32),
+              ('dst', ctypes.c_int32), ('i', ctypes.c_int32 * 6), ('f', ctypes.c_double * 4)]
+
+
+class NtkState(ctypes.Structure):
+  _fields_ = [('nngp', ctypes.c_void_p), ('ntk', ctypes.c_void_p), ('cov1', ctypes.c_void_p),
+              ('cov2', ctypes.c_void_p), ('n1', ctypes.c_int32), ('n2', ctypes.c_int32),
+              ('H', ctypes.c_int32), ('W', ctypes.c_int32), ('ntk_mode', ctypes.c_int32),
+              ('is_gaussian', ctypes.c_int32)]
+
+
+class NtkError(RuntimeError):
+  def __init__(self, code, msg):
+    super().__init__(f'ntk_b200 error {code}: {msg}')
+    self.code = code
+    self.msg = msg
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+  """Loads the shared library (once).  Raises if it has not been built."""
+  global _lib
+  with _lock:
+    if _lib is not None:
+      return _lib
+    if not os.path.exists(LIB_PATH):
+      raise ImportError(
+          f'{LIB_PATH} not found: build the CUDA library first '
+          '(`python -c "import __graft_entry__ as g; g.build()"` or `make -C neural-tangents_b200/csrc`). '
+          'neural_tangents_b200 has no CPU fallback.')
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, u32, sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_size_t
+    P = ctypes.POINTER
+    lib.ntk_abi_version.restype = ctypes.c_int
+    lib.ntk_last_error.restype = ctypes.c_char_p
+    lib.ntk_device_count.argtypes = [P(ctypes.c_int)]
+    lib.ntk_program_create.argtypes = [P(NtkOp), i32, i32, i32, P(vp)]
+    lib.ntk_program_destroy.argtypes = [vp]
+    lib.ntk_program_destroy.restype = None
+    lib.ntk_program_output_shape.argtypes = [vp, i32, i32, i32, P(i32), P(i32), P(i32)]
+    lib.ntk_context_create.argtypes = [i32, sz, P(vp)]
+    lib.ntk_context_destroy.argtypes = [vp]
+    lib.ntk_context_destroy.restype = None
+    lib.ntk_context_synchronize.argtypes = [vp]
+    lib.ntk_context_stream.argtypes = [vp]
+    lib.ntk_context_stream.restype = vp
+    lib.ntk_context_launch_count.argtypes = [vp]
+    lib.ntk_context_launch_count.restype = i64
+    gram_args = [vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, u32, vp, vp, i64, vp, vp]
+    lib.ntk_gram_host.argtypes = gram_args
+    lib.ntk_gram_device.argtypes = gram_args
+    lib.ntk_apply_host.argtypes = [vp, vp, i32, P(NtkState), P(NtkState)]
+    lib.ntk_workspace_bytes.argtypes = [vp, i32, i32, i32, i32, i32, i32, u32, P(sz)]
+    lib.ntk_device_malloc.argtypes = [i32, sz, P(vp)]
+    lib.ntk_device_free.argtypes = [i32, vp]
+    lib.ntk_memcpy_h2d.argtypes = [vp, vp, vp, sz]
+    lib.ntk_memcpy_d2h.argtypes = [vp, vp, vp, sz]
+    _lib = lib
+    return lib
+
+
+def check(status):
+  if status != 0:
+    msg = load().ntk_last_error().decode('utf-8', 'replace')
+    if status in (E_NOTGAUSSIAN, E_SHAPE, E_INVAL):
+      raise ValueError(msg)
+    if status == E_UNSUPPORTED:
+      raise NotImplementedError(msg)
+    if status == E_NOMEM:
+      raise MemoryError(msg)
+    raise NtkError(status, msg)
+
+
+def dtype_code(dtype):
+  dtype = np.dtype(dtype)
+  if dtype == np.float32:
+    return NTK_F32
+  if dtype == np.float64:
+    return NTK_F64
+  raise TypeError(f'unsupported dtype {dtype}')
+
+
+class Program:
+  """Owns an `ntk_program_t`."""
+
+  def __init__(self, ops, n_slots, out_slot):
+    lib = load()
+    arr = (NtkOp * max(len(ops), 1))()
+    for k, (kind, src, src2, dst, ints, floats) in enumerate(ops):
+      o = arr[k]
+      o.kind, o.src, o.src2, o.dst = kind, src, src2, dst
+      for t in range(6):
+        o.i[t] = int(ints[t]) if t < len(ints) else 0
+      for t in range(4):
+        o.f[t] = float(floats[t]) if t < len(floats) else 0.0
+    self._h = ctypes.c_void_p()
+    check(lib.ntk_program_create(arr, len(ops), n_slots, out_slot, ctypes.byref(self._h)))
+    self._lib = lib
+
+  @property
+  def handle(self):
+    return self._h
+
+  def output_shape(self, H, W, in_is_gaussian=False):
+    oh, ow, og = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    check(self._lib.ntk_program_output_shape(self._h, H, W, int(in_is_gaussian), ctypes.byref(oh), ctypes.byref(ow),
+                                              ctypes.byref(og)))
+    return oh.value, ow.value, bool(og.value)
+
+  def __del__(self):
+    try:
+      if self._h:
+        self._lib.ntk_program_destroy(self._h)
+    except Exception:
+      pass
+
+
+class Context:
+  """Owns an `ntk_context_t` (one per host thread x GPU)."""
+
+  def __init__(self, device=0, workspace_bytes=0):
+    lib = load()
+    self._h = ctypes.c_void_p()
+    check(lib.ntk_context_create(device, workspace_bytes, ctypes.byref(self._h)))
+    self._lib = lib
+    self.device = device
+
+  @property
+  def handle(self):
+    return self._h
+
+  def synchronize(self):
+    check(self._lib.ntk_context_synchronize(self._h))
+
+  @property
+  def stream(self):
+    return self._lib.ntk_context_stream(self._h)
+
+  @property
+  def launch_count(self):
+    return int(self._lib.ntk_context_launch_count(self._h))
+
+  def close(self):
+    if self._h:
+      self._lib.ntk_context_destroy(self._h)
+      self._h = ctypes.c_void_p()
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
+
+
+_contexts = {}
+_ctx_lock = threading.Lock()
+_tls = threading.local()
+
+
+class device_scope:
+  """`with device_scope(d):` routes this thread's kernel_fn calls to GPU `d`."""
+
+  def __init__(self, device):
+    self.device = device
+
+  def __enter__(self):
+    self.prev = getattr(_tls, 'device', None)
+    _tls.device = self.device
+
+  def __exit__(self, *exc):
+    _tls.device = self.prev
+
+
+def device_count():
+  n = ctypes.c_int(0)
+  check(load().ntk_device_count(ctypes.byref(n)))
+  return n.value
+
+
+def get_context(device=None):
+  """Per-(thread, device) cached context."""
+  from ._config import config
+  if device is None:
+    device = getattr(_tls, 'device', None)
+  if device is None:
+    device = config.device
+  key = (threading.get_ident(), device)
+  with _ctx_lock:
+    ctx = _contexts.get(key)
+    if ctx is None:
+      ctx = Context(device, config.workspace_bytes)
+      _contexts[key] = ctx
+    return ctx
+
+
+def _ptr(a):
+  return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def gram_host(ctx, prog, x1, x2, H, W, C, flags, out_h, out_w, want_ntk, want_cov, device_ptrs=False):
+  """kernel_fn on raw inputs; returns dict of numpy arrays in canonical layout."""
+  lib = load()
+  dt = dtype_code(x1.dtype)
+  n1 = x1.shape[0]
+  n2 = n1 if x2 is None else x2.shape[0]
+  sp = (out_h, out_h, out_w, out_w) if out_h > 0 else ()
+  nngp = np.empty((n1, n2) + sp, x1.dtype)
+  ntk = np.empty((n1, n2) + sp, x1.dtype) if want_ntk else None
+  cov1 = np.empty((n1,) + sp, x1.dtype) if want_cov else None
+  cov2 = np.empty((n2,) + sp, x1.dtype) if (want_cov and x2 is not None) else None
+  f = flags | (FLAG_NTK if want_ntk else 0) | (FLAG_WANT_COV if want_cov else 0)
+  check(lib.ntk_gram_host(ctx.handle, prog.handle, dt, _ptr(x1), n1, _ptr(x2), n2, H, W, C, f,
+                          _ptr(nngp), _ptr(ntk), n2, _ptr(cov1), _ptr(cov2)))
+  return dict(nngp=nngp, ntk=ntk, cov1=cov1, cov2=cov2)
+
+
+def gram_device(ctx, prog, dtype, x1_ptr, n1, x2_ptr, n2, H, W, C, flags, nngp_ptr, ntk_ptr, ld):
+  """Device-pointer entry (asynchronous on the context stream); pointers are ints."""
+  lib = load()
+  f = flags | (FLAG_NTK if ntk_ptr else 0)
+  check(lib.ntk_gram_device(ctx.handle, prog.handle, dtype_code(dtype), x1_ptr, n1, x2_ptr, n2, H, W,
+                            C, f, nngp_ptr, ntk_ptr, ld, None, None))
+
+
+def apply_host(ctx, prog, dtype, nngp, ntk, cov1, cov2, H, W, ntk_mode, is_gaussian, out_h, out_w):
+  """Kernel-in / Kernel-out on canonical-layout numpy arrays."""
+  lib = load()
+  dt = dtype_code(dtype)
+  n1, n2 = nngp.shape[0], nngp.shape[1]
+  sp = (out_h, out_h, out_w, out_w) if out_h > 0 else ()
+  o_nngp = np.empty((n1, n2) + sp, dtype)
+  o_ntk = np.empty((n1, n2) + sp, dtype) if ntk_mode != NTK_NONE else None
+  o_cov1 = np.empty((n1,) + sp, dtype)
+  o_cov2 = np.empty((n2,) + sp, dtype) if cov2 is not None else None
+  sin = NtkState(_ptr(nngp), _ptr(ntk) if ntk_mode == NTK_TENSOR else None, _ptr(cov1), _ptr(cov2),
+                 n1, n2, H, W, ntk_mode, int(is_gaussian))
+  sout = NtkState(_ptr(o_nngp), _ptr(o_ntk), _ptr(o_cov1), _ptr(o_cov2), n1, n2, out_h, out_w, 0, 0)
+  check(lib.ntk_apply_host(ctx.handle, prog.handle, dt, ctypes.byref(sin), ctypes.byref(sout)))
+  if sout.ntk_mode == NTK_ZERO and o_ntk is not None:
+    o_ntk = np.zeros((), dtype)
+  return dict(nngp=o_nngp, ntk=o_ntk, cov1=o_cov1, cov2=o_cov2, ntk_mode=sout.ntk_mode,
+              is_gaussian=bool(sout.is_gaussian))

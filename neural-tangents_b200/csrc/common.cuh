@@ -1,0 +1,131 @@
+// Shared host/device helpers for the ntk_b200 library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ntk_b200.h"
+
+namespace ntk {
+
+// ---- thread-local error string ------------------------------------------------
+inline std::string& last_error() {
+  thread_local std::string e;
+  return e;
+}
+
+inline int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return code;
+}
+
+#define NTK_CUDA(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return ::ntk::fail(NTK_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,           \
+                         cudaGetErrorString(_e));                                          \
+  } while (0)
+
+#define NTK_TRY(expr)          \
+  do {                         \
+    int _s = (expr);           \
+    if (_s != NTK_OK) return _s; \
+  } while (0)
+
+// ---- padding arithmetic (lax.padtype_to_pads) ----------
+struct AxisGeom {
+  int out;  // output size
+  int lo;   // low-side padding
+};
+
+inline AxisGeom axis_geom(int n, int k, int s, int padding) {
+  AxisGeom g;
+  if (padding == NTK_PAD_VALID) {
+    g.out = n >= k ? (n - k) / s + 1 : 0;
+    g.lo = 0;
+  } else {  // SAME and CIRCULAR share the SAME geometry (linear.py:3158-3165)
+    g.out = (n + s - 1) / s;
+    int tot = (g.out - 1) * s + k - n;
+    if (tot < 0) tot = 0;
+    g.lo = tot / 2;
+  }
+  return g;
+}
+
+// ---- stream-ordered bump/free-list arena over one device workspace -------------
+// All kernels of a context run on one stream, so a block can be handed out
+// again as soon as the host frees it.  In `dry` mode nothing is backed by memory
+// and `peak` reports the workspace a real run with identical calls would need.
+class Arena {
+ public:
+  void reset(char* base, size_t cap, bool dry) {
+    base_ = dry ? reinterpret_cast<char*>(uintptr_t(1) << 40) : base;
+    cap_ = dry ? (size_t(1) << 60) : cap;
+    dry_ = dry;
+    peak_ = 0;
+    free_.clear();
+    used_.clear();
+    free_[0] = cap_;
+  }
+  void* alloc(size_t bytes) {
+    bytes = (bytes + 255) & ~size_t(255);
+    if (bytes == 0) bytes = 256;
+    for (auto it = free_.begin(); it != free_.end(); ++it) {
+      if (it->second >= bytes) {
+        size_t off = it->first, sz = it->second;
+        free_.erase(it);
+        if (sz > bytes) free_[off + bytes] = sz - bytes;
+        used_[off] = bytes;
+        if (off + bytes > peak_) peak_ = off + bytes;
+        return base_ + off;
+      }
+    }
+    return nullptr;
+  }
+  void release(void* p) {
+    if (!p) return;
+    size_t off = static_cast<char*>(p) - base_;
+    auto u = used_.find(off);
+    if (u == used_.end()) return;
+    size_t sz = u->second;
+    used_.erase(u);
+    auto nx = free_.lower_bound(off);
+    if (nx != free_.end() && off + sz == nx->first) {
+      sz += nx->second;
+      nx = free_.erase(nx);
+    }
+    if (nx != free_.begin()) {
+      auto pv = std::prev(nx);
+      if (pv->first + pv->second == off) {
+        pv->second += sz;
+        return;
+      }
+    }
+    free_[off] = sz;
+  }
+  size_t peak() const { return peak_; }
+  bool dry() const { return dry_; }
+
+ private:
+  char* base_ = nullptr;
+  size_t cap_ = 0, peak_ = 0;
+  bool dry_ = false;
+  std::map<size_t, size_t> free_, used_;
+};
+
+constexpr int kNumSMs = 148;  // B200
+
+}  // namespace ntk

@@ -1,0 +1,968 @@
+// Program interpreter + C-ABI entry points of libntk_b200.so.
+//
+// A program is the slot form of a `stax` layer tree (include/ntk_b200.h).  The
+// executor tiles the n1 x n2 pair grid (the job of nt.batch's serial loop,
+// _src/batching.py:314-502), builds the input kernel of each tile
+// (_src/stax/requirements.py:641-830), runs the layer rules on the GPU and
+// scatters the tile into the result matrices.  There is no CPU path.
+#include <algorithm>
+#include <memory>
+
+#include "common.cuh"
+#include "generic_kernels.cuh"
+#include "fused_kernels.cuh"
+
+using namespace ntk;
+
+// ------------------------------------------------------------------------------
+struct ntk_program {
+  std::vector<ntk_op_t> ops;
+  int n_slots = 0;
+  int out_slot = 0;
+  std::vector<int> last_use;  // per slot: index of the last op reading it (or n_ops if output)
+  FusedPlan fused;            // fast-path plan (fused_kernels.cuh); empty if not matched
+};
+
+struct ntk_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  char* ws = nullptr;
+  size_t ws_bytes = 0;
+  int64_t launches = 0;
+  Arena arena;
+  // grow-only device IO buffers for the *_host entry points
+  void* io[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t io_bytes[6] = {0, 0, 0, 0, 0, 0};
+};
+
+namespace {
+
+struct Buf {
+  void* p = nullptr;
+  int refs = 0;
+};
+
+struct TState {
+  Buf* nngp = nullptr;
+  Buf* ntk = nullptr;
+  Buf* cov1 = nullptr;
+  Buf* cov2 = nullptr;
+  int H = 0, W = 0;
+  int ntk_mode = NTK_NTK_NONE;
+  bool gaussian = false;
+  bool valid = false;
+};
+
+// Execution environment of one tile (or one dry run).
+struct Env {
+  ntk_context* ctx = nullptr;  // nullptr in dry runs
+  Arena* arena = nullptr;
+  cudaStream_t stream = nullptr;
+  bool dry = false;
+  int64_t launches = 0;
+  std::vector<std::unique_ptr<Buf>> bufs;
+
+  Buf* alloc(size_t bytes, int* status) {
+    void* p = arena->alloc(bytes);
+    if (!p) {
+      *status = fail(NTK_ENOMEM, "workspace exhausted allocating %zu bytes", bytes);
+      return nullptr;
+    }
+    bufs.emplace_back(new Buf());
+    bufs.back()->p = p;
+    bufs.back()->refs = 1;
+    return bufs.back().get();
+  }
+  void unref(Buf*& b) {
+    if (b && --b->refs == 0) {
+      arena->release(b->p);
+      b->p = nullptr;
+    }
+    b = nullptr;
+  }
+  void release(TState& s) {
+    unref(s.nngp);
+    unref(s.ntk);
+    unref(s.cov1);
+    unref(s.cov2);
+    s.valid = false;
+  }
+};
+
+#define LAUNCH(env, kernel, grid, block, smem, ...)                                   \
+  do {                                                                                \
+    (env).launches++;                                                                 \
+    if (!(env).dry) {                                                                 \
+      kernel<<<(grid), (block), (smem), (env).stream>>>(__VA_ARGS__);                 \
+      NTK_CUDA(cudaGetLastError());                                                   \
+    }                                                                                 \
+  } while (0)
+
+inline long long per_of(int H, int W) { return H > 0 ? (long long)H * H * W * W : 1; }
+
+template <typename T>
+int copy_buf(Env& env, Buf* src, size_t bytes, Buf** out) {
+  int st = NTK_OK;
+  Buf* b = env.alloc(bytes, &st);
+  if (!b) return st;
+  if (!env.dry) NTK_CUDA(cudaMemcpyAsync(b->p, src->p, bytes, cudaMemcpyDeviceToDevice, env.stream));
+  env.launches++;
+  *out = b;
+  return NTK_OK;
+}
+
+// Make `b` exclusively owned (copy-on-write) so an in-place kernel may run on it.
+template <typename T>
+int make_unique_buf(Env& env, Buf*& b, size_t bytes) {
+  if (!b || b->refs == 1) return NTK_OK;
+  Buf* nb = nullptr;
+  NTK_TRY(copy_buf<T>(env, b, bytes, &nb));
+  env.unref(b);
+  b = nb;
+  return NTK_OK;
+}
+
+// ---- layer rules on a tile --------------------------------------------------------
+template <typename T>
+int op_conv(Env& env, const ntk_op_t& op, const TState& in, TState& out, int t1, int t2) {
+  if (in.H <= 0) return fail(NTK_EINVAL, "Conv needs spatial inputs");
+  const int kh = op.i[0], kw = op.i[1], sh = op.i[2], sw = op.i[3], pad = op.i[4];
+  AxisGeom gh = axis_geom(in.H, kh, sh, pad), gw = axis_geom(in.W, kw, sw, pad);
+  if (gh.out <= 0 || gw.out <= 0) return fail(NTK_EINVAL, "Conv output would be empty");
+  ConvGeom g{in.H, in.W, gh.out, gw.out, kh, kw, sh, sw, gh.lo, gw.lo, pad == NTK_PAD_CIRCULAR};
+  const T scale = (T)(op.f[0] / (double)(kh * kw));
+  const T shift = (T)(op.i[5] ? op.f[1] : 0.0);
+  const long long per_o = per_of(g.Ho, g.Wo);
+  int st = NTK_OK;
+  auto run = [&](Buf* src, Buf* addend, long long P, T sc, T shf, Buf** dst) -> int {
+    Buf* o = env.alloc((size_t)(P * per_o) * sizeof(T), &st);
+    if (!o) return st;
+    LAUNCH(env, k_conv<T>, grid_for(P * per_o), kThreads, 0, (const T*)src->p,
+           addend ? (const T*)addend->p : (const T*)nullptr, (T*)o->p, P, g, sc, shf);
+    *dst = o;
+    return NTK_OK;
+  };
+  const long long P = (long long)t1 * t2;
+  NTK_TRY(run(in.nngp, nullptr, P, scale, shift, &out.nngp));
+  out.ntk_mode = in.ntk_mode;
+  if (in.ntk_mode == NTK_NTK_TENSOR) {
+    NTK_TRY(run(in.ntk, out.nngp, P, scale, (T)0, &out.ntk));  // linear.py:1396-1398
+  } else if (in.ntk_mode == NTK_NTK_ZERO) {
+    NTK_TRY(copy_buf<T>(env, out.nngp, (size_t)(P * per_o) * sizeof(T), &out.ntk));
+    out.ntk_mode = NTK_NTK_TENSOR;
+  }
+  NTK_TRY(run(in.cov1, nullptr, t1, scale, shift, &out.cov1));
+  NTK_TRY(run(in.cov2, nullptr, t2, scale, shift, &out.cov2));
+  out.H = g.Ho;
+  out.W = g.Wo;
+  out.gaussian = true;
+  out.valid = true;
+  return NTK_OK;
+}
+
+template <typename T>
+int op_pool(Env& env, const ntk_op_t& op, const TState& in, TState& out, int t1, int t2) {
+  if (in.H <= 0) return fail(NTK_EINVAL, "AvgPool needs spatial inputs");
+  const int wh = op.i[0], ww = op.i[1], sh = op.i[2], sw = op.i[3], pad = op.i[4];
+  AxisGeom gh = axis_geom(in.H, wh, sh, pad), gw = axis_geom(in.W, ww, sw, pad);
+  if (gh.out <= 0 || gw.out <= 0) return fail(NTK_EINVAL, "AvgPool output would be empty");
+  PoolGeom g{in.H, in.W, gh.out, gw.out, wh, ww, sh, sw, gh.lo, gw.lo, pad == NTK_PAD_CIRCULAR,
+             (op.i[5] && pad == NTK_PAD_SAME) ? 1 : 0};
+  const long long per_o = per_of(g.Ho, g.Wo);
+  int st = NTK_OK;
+  auto run = [&](Buf* src, long long P, Buf** dst) -> int {
+    Buf* o = env.alloc((size_t)(P * per_o) * sizeof(T), &st);
+    if (!o) return st;
+    LAUNCH(env, k_pool<T>, grid_for(P * per_o), kThreads, 0, (const T*)src->p, (T*)o->p, P, g);
+    *dst = o;
+    return NTK_OK;
+  };
+  const long long P = (long long)t1 * t2;
+  NTK_TRY(run(in.nngp, P, &out.nngp));
+  out.ntk_mode = in.ntk_mode;
+  if (in.ntk_mode == NTK_NTK_TENSOR) NTK_TRY(run(in.ntk, P, &out.ntk));
+  NTK_TRY(run(in.cov1, t1, &out.cov1));
+  NTK_TRY(run(in.cov2, t2, &out.cov2));
+  out.H = g.Ho;
+  out.W = g.Wo;
+  out.gaussian = in.gaussian;
+  out.valid = true;
+  return NTK_OK;
+}
+
+template <typename T>
+int op_reduce(Env& env, const ntk_op_t& op, const TState& in, TState& out, int t1, int t2) {
+  const bool flatten = op.kind == NTK_OP_FLATTEN;
+  if (in.H <= 0) {
+    if (!flatten) return fail(NTK_EINVAL, "GlobalAvgPool needs spatial inputs");
+    out = in;  // Flatten of [N,d] is the identity (shares buffers)
+    for (Buf* b : {out.nngp, out.ntk, out.cov1, out.cov2})
+      if (b) b->refs++;
+    out.gaussian = false;
+    return NTK_OK;
+  }
+  int st = NTK_OK;
+  auto run = [&](Buf* src, long long P, Buf** dst) -> int {
+    Buf* o = env.alloc((size_t)P * sizeof(T), &st);
+    if (!o) return st;
+    int grid = (int)std::min<long long>(P, (long long)kNumSMs * 16);
+    if (flatten)
+      LAUNCH(env, (k_reduce_spatial<T, true>), grid, kThreads, 0, (const T*)src->p, (T*)o->p, P,
+             in.H, in.W);
+    else
+      LAUNCH(env, (k_reduce_spatial<T, false>), grid, kThreads, 0, (const T*)src->p, (T*)o->p, P,
+             in.H, in.W);
+    *dst = o;
+    return NTK_OK;
+  };
+  const long long P = (long long)t1 * t2;
+  NTK_TRY(run(in.nngp, P, &out.nngp));
+  out.ntk_mode = in.ntk_mode;
+  if (in.ntk_mode == NTK_NTK_TENSOR) NTK_TRY(run(in.ntk, P, &out.ntk));
+  NTK_TRY(run(in.cov1, t1, &out.cov1));
+  NTK_TRY(run(in.cov2, t2, &out.cov2));
+  out.H = out.W = 0;
+  out.gaussian = flatten ? false : in.gaussian;
+  out.valid = true;
+  return NTK_OK;
+}
+
+// Moves (steal == true) or shares the buffers of `in` into `out`, then makes them
+// exclusively owned so in-place kernels can run.
+template <typename T>
+int take_for_inplace(Env& env, TState& in, TState& out, bool steal, int t1, int t2) {
+  out = in;
+  if (steal) {
+    in.nngp = in.ntk = in.cov1 = in.cov2 = nullptr;
+    in.valid = false;
+  } else {
+    for (Buf* b : {out.nngp, out.ntk, out.cov1, out.cov2})
+      if (b) b->refs++;
+  }
+  const long long per = per_of(out.H, out.W);
+  const long long P = (long long)t1 * t2;
+  NTK_TRY(make_unique_buf<T>(env, out.nngp, (size_t)(P * per) * sizeof(T)));
+  NTK_TRY(make_unique_buf<T>(env, out.ntk, (size_t)(P * per) * sizeof(T)));
+  NTK_TRY(make_unique_buf<T>(env, out.cov1, (size_t)(t1 * per) * sizeof(T)));
+  NTK_TRY(make_unique_buf<T>(env, out.cov2, (size_t)(t2 * per) * sizeof(T)));
+  return NTK_OK;
+}
+
+template <typename T>
+int op_act(Env& env, const ntk_op_t& op, TState& in, TState& out, bool steal, int t1, int t2) {
+  if (!in.gaussian)
+    return fail(NTK_ENOTGAUSSIAN,
+                "The input to the activation function must be Gaussian, i.e. a random affine "
+                "transform is required before the activation function.");
+  NTK_TRY((take_for_inplace<T>(env, in, out, steal, t1, t2)));
+  const int H = out.H > 0 ? out.H : 1, W = out.W > 0 ? out.W : 1;
+  const long long per = per_of(out.H, out.W);
+  const long long P = (long long)t1 * t2;
+  int st = NTK_OK;
+  Buf* q1 = env.alloc((size_t)t1 * H * W * sizeof(T), &st);
+  if (!q1) return st;
+  Buf* q2 = env.alloc((size_t)t2 * H * W * sizeof(T), &st);
+  if (!q2) return st;
+  LAUNCH(env, k_diag<T>, grid_for((long long)t1 * H * W), kThreads, 0, (const T*)out.cov1->p,
+         (T*)q1->p, (long long)t1, H, W);
+  LAUNCH(env, k_diag<T>, grid_for((long long)t2 * H * W), kThreads, 0, (const T*)out.cov2->p,
+         (T*)q2->p, (long long)t2, H, W);
+  ActParams ap{op.kind, op.f[0], op.f[1], op.f[2]};
+  Buf* stab = nullptr;
+  if (op.kind == NTK_OP_ABRELU && op.i[0]) {  // do_stabilize: elementwise.py:430-436
+    stab = env.alloc(256, &st);
+    if (!stab) return st;
+    if (!env.dry) NTK_CUDA(cudaMemsetAsync(stab->p, 0, 256, env.stream));
+    LAUNCH(env, k_absmax<T>, grid_for(P * per), kThreads, 0, (const T*)out.nngp->p, P * per,
+           (T*)stab->p);
+  }
+  const T* sp = stab ? (const T*)stab->p : (const T*)nullptr;
+  T* tt = out.ntk_mode == NTK_NTK_TENSOR ? (T*)out.ntk->p : (T*)nullptr;
+  LAUNCH(env, k_act<T>, grid_for(P * per), kThreads, 0, (T*)out.nngp->p, tt, (const T*)q1->p,
+         (const T*)q2->p, P, PairMap{t2, 0}, H, W, ap, sp);
+  LAUNCH(env, k_act<T>, grid_for(t1 * per), kThreads, 0, (T*)out.cov1->p, (T*)nullptr,
+         (const T*)q1->p, (const T*)q1->p, (long long)t1, PairMap{1, 1}, H, W, ap, sp);
+  LAUNCH(env, k_act<T>, grid_for(t2 * per), kThreads, 0, (T*)out.cov2->p, (T*)nullptr,
+         (const T*)q2->p, (const T*)q2->p, (long long)t2, PairMap{1, 1}, H, W, ap, sp);
+  env.unref(q1);
+  env.unref(q2);
+  if (stab) env.unref(stab);
+  out.gaussian = false;
+  out.valid = true;
+  return NTK_OK;
+}
+
+template <typename T>
+int op_dense(Env& env, const ntk_op_t& op, TState& in, TState& out, bool steal, int t1, int t2) {
+  NTK_TRY((take_for_inplace<T>(env, in, out, steal, t1, t2)));
+  const long long per = per_of(out.H, out.W);
+  const long long P = (long long)t1 * t2;
+  const T w2 = (T)op.f[0], b2 = (T)(op.i[0] ? op.f[1] : 0.0);
+  int st = NTK_OK;
+  int t_zero = 0;
+  if (out.ntk_mode == NTK_NTK_ZERO) {
+    out.ntk = env.alloc((size_t)(P * per) * sizeof(T), &st);
+    if (!out.ntk) return st;
+    out.ntk_mode = NTK_NTK_TENSOR;
+    t_zero = 1;
+  }
+  T* tt = out.ntk_mode == NTK_NTK_TENSOR ? (T*)out.ntk->p : (T*)nullptr;
+  LAUNCH(env, k_dense<T>, grid_for(P * per), kThreads, 0, (T*)out.nngp->p, tt, P * per, w2, b2,
+         t_zero);
+  LAUNCH(env, k_dense<T>, grid_for(t1 * per), kThreads, 0, (T*)out.cov1->p, (T*)nullptr, t1 * per,
+         w2, b2, 0);
+  LAUNCH(env, k_dense<T>, grid_for(t2 * per), kThreads, 0, (T*)out.cov2->p, (T*)nullptr, t2 * per,
+         w2, b2, 0);
+  out.gaussian = true;
+  out.valid = true;
+  return NTK_OK;
+}
+
+template <typename T>
+int op_faninsum(Env& env, const TState& a, const TState& b, TState& out, int t1, int t2) {
+  if (a.H != b.H || a.W != b.W)
+    return fail(NTK_ESHAPE, "All shapes should be equal in `FanInSum`, got %dx%d and %dx%d", a.H,
+                a.W, b.H, b.W);
+  if (!(a.gaussian && b.gaussian))
+    return fail(NTK_EUNSUPPORTED,
+                "`FanInSum` is only implemented for the case where all input layers are "
+                "guaranteed to be mean-zero Gaussian (is_gaussian == True).");
+  const long long per = per_of(a.H, a.W);
+  const long long P = (long long)t1 * t2;
+  int st = NTK_OK;
+  auto add = [&](Buf* x, Buf* y, long long n, Buf** dst) -> int {
+    Buf* o = env.alloc((size_t)n * sizeof(T), &st);
+    if (!o) return st;
+    LAUNCH(env, k_add<T>, grid_for(n), kThreads, 0, (const T*)x->p, (const T*)y->p, (T*)o->p, n);
+    *dst = o;
+    return NTK_OK;
+  };
+  NTK_TRY(add(a.nngp, b.nngp, P * per, &out.nngp));
+  NTK_TRY(add(a.cov1, b.cov1, t1 * per, &out.cov1));
+  NTK_TRY(add(a.cov2, b.cov2, t2 * per, &out.cov2));
+  if (a.ntk_mode == NTK_NTK_TENSOR && b.ntk_mode == NTK_NTK_TENSOR) {
+    NTK_TRY(add(a.ntk, b.ntk, P * per, &out.ntk));
+    out.ntk_mode = NTK_NTK_TENSOR;
+  } else if (a.ntk_mode == NTK_NTK_TENSOR || b.ntk_mode == NTK_NTK_TENSOR) {
+    out.ntk = a.ntk_mode == NTK_NTK_TENSOR ? a.ntk : b.ntk;
+    out.ntk->refs++;
+    out.ntk_mode = NTK_NTK_TENSOR;
+  } else {
+    out.ntk_mode = a.ntk_mode;
+  }
+  out.H = a.H;
+  out.W = a.W;
+  out.gaussian = true;
+  out.valid = true;
+  return NTK_OK;
+}
+
+// Runs ops [first, n_ops) of the program on slots; slot `ops[first].src` etc. must be valid.
+template <typename T>
+int run_ops(Env& env, const ntk_program& prog, std::vector<TState>& slots, int first, int t1,
+            int t2) {
+  const int n_ops = (int)prog.ops.size();
+  for (int k = first; k < n_ops; ++k) {
+    const ntk_op_t& op = prog.ops[k];
+    TState& in = slots[op.src];
+    if (!in.valid) return fail(NTK_EINVAL, "op %d reads empty slot %d", k, op.src);
+    TState out;
+    const bool steal = prog.last_use[op.src] == k;
+    switch (op.kind) {
+      case NTK_OP_CONV:
+        NTK_TRY(op_conv<T>(env, op, in, out, t1, t2));
+        break;
+      case NTK_OP_AVGPOOL:
+        NTK_TRY(op_pool<T>(env, op, in, out, t1, t2));
+        break;
+      case NTK_OP_GAP:
+      case NTK_OP_FLATTEN:
+        NTK_TRY(op_reduce<T>(env, op, in, out, t1, t2));
+        out.valid = true;
+        break;
+      case NTK_OP_ABRELU:
+      case NTK_OP_ERF:
+        NTK_TRY(op_act<T>(env, op, in, out, steal, t1, t2));
+        break;
+      case NTK_OP_DENSE:
+        NTK_TRY(op_dense<T>(env, op, in, out, steal, t1, t2));
+        break;
+      case NTK_OP_FANINSUM: {
+        TState& in2 = slots[op.src2];
+        if (!in2.valid) return fail(NTK_EINVAL, "op %d reads empty slot %d", k, op.src2);
+        NTK_TRY(op_faninsum<T>(env, in, in2, out, t1, t2));
+        break;
+      }
+      case NTK_OP_IDENTITY:
+        out = in;
+        for (Buf* b : {out.nngp, out.ntk, out.cov1, out.cov2})
+          if (b) b->refs++;
+        break;
+      default:
+        return fail(NTK_EINVAL, "unknown op kind %d", op.kind);
+    }
+    // retire dead inputs, then publish the result
+    if (prog.last_use[op.src] == k && slots[op.src].valid) env.release(slots[op.src]);
+    if (op.src2 >= 0 && prog.last_use[op.src2] == k && slots[op.src2].valid)
+      env.release(slots[op.src2]);
+    if (slots[op.dst].valid) env.release(slots[op.dst]);
+    slots[op.dst] = out;
+  }
+  return NTK_OK;
+}
+
+// Builds the input kernel of a tile: requirements.py:641-830.
+template <typename T>
+int build_input_state(Env& env, const T* x1, int t1, const T* x2, int t2, int H, int W, int C,
+                      bool want_ntk, TState& s) {
+  const long long P = (long long)t1 * t2;
+  int st = NTK_OK;
+  const T inv_c = (T)(1.0 / (double)C);
+  if (H > 0) {
+    const long long per = per_of(H, W);
+    s.nngp = env.alloc((size_t)(P * per) * sizeof(T), &st);
+    if (!s.nngp) return st;
+    s.cov1 = env.alloc((size_t)(t1 * per) * sizeof(T), &st);
+    if (!s.cov1) return st;
+    s.cov2 = env.alloc((size_t)(t2 * per) * sizeof(T), &st);
+    if (!s.cov2) return st;
+    LAUNCH(env, k_input_cov<T>, grid_for(P * per), kThreads, 0, x1, x2, (T*)s.nngp->p, P,
+           PairMap{t2, 0}, H, W, C, inv_c);
+    LAUNCH(env, k_input_cov<T>, grid_for(t1 * per), kThreads, 0, x1, x1, (T*)s.cov1->p,
+           (long long)t1, PairMap{1, 1}, H, W, C, inv_c);
+    LAUNCH(env, k_input_cov<T>, grid_for(t2 * per), kThreads, 0, x2, x2, (T*)s.cov2->p,
+           (long long)t2, PairMap{1, 1}, H, W, C, inv_c);
+  } else {
+    s.nngp = env.alloc((size_t)P * sizeof(T), &st);
+    if (!s.nngp) return st;
+    s.cov1 = env.alloc((size_t)t1 * sizeof(T), &st);
+    if (!s.cov1) return st;
+    s.cov2 = env.alloc((size_t)t2 * sizeof(T), &st);
+    if (!s.cov2) return st;
+    NTK_TRY((fcn_input_gram<T>(env.dry, env.stream, &env.launches, x1, t1, x2, t2, C,
+                               (T*)s.nngp->p)));
+    LAUNCH(env, k_rowdot<T>, grid_for((long long)t1 * 32), kThreads, 0, x1, x1, (T*)s.cov1->p,
+           (long long)t1, PairMap{1, 1}, C, inv_c);
+    LAUNCH(env, k_rowdot<T>, grid_for((long long)t2 * 32), kThreads, 0, x2, x2, (T*)s.cov2->p,
+           (long long)t2, PairMap{1, 1}, C, inv_c);
+  }
+  s.H = H;
+  s.W = W;
+  s.ntk_mode = want_ntk ? NTK_NTK_ZERO : NTK_NTK_NONE;
+  s.gaussian = false;
+  s.valid = true;
+  return NTK_OK;
+}
+
+struct OutPtrs {
+  void* nngp;
+  void* ntk;
+  void* cov1;
+  void* cov2;
+  long long ld;
+};
+
+template <typename T>
+int scatter_tile(Env& env, const TState& s, int t1, int t2, int r0, int c0, int n2, const OutPtrs& o) {
+  const long long per = per_of(s.H, s.W);
+  const long long ld = s.H > 0 ? n2 : o.ld;
+  const long long P = (long long)t1 * t2;
+  if (o.nngp)
+    LAUNCH(env, k_scatter<T>, grid_for(P * per), kThreads, 0, (const T*)s.nngp->p, (T*)o.nngp, t1,
+           t2, per, ld, r0, c0);
+  if (o.ntk) {
+    if (s.ntk_mode == NTK_NTK_TENSOR) {
+      LAUNCH(env, k_scatter<T>, grid_for(P * per), kThreads, 0, (const T*)s.ntk->p, (T*)o.ntk, t1,
+             t2, per, ld, r0, c0);
+    } else {
+      // the 0-d zero of requirements.py:807 never met a Dense/Conv: materialise zeros.
+      int st = NTK_OK;
+      Buf* z = env.alloc((size_t)(P * per) * sizeof(T), &st);
+      if (!z) return st;
+      LAUNCH(env, k_fill<T>, grid_for(P * per), kThreads, 0, (T*)z->p, P * per, (T)0);
+      LAUNCH(env, k_scatter<T>, grid_for(P * per), kThreads, 0, (const T*)z->p, (T*)o.ntk, t1, t2,
+             per, ld, r0, c0);
+      env.unref(z);
+    }
+  }
+  if (o.cov1 && c0 == 0)
+    LAUNCH(env, k_scatter<T>, grid_for(t1 * per), kThreads, 0, (const T*)s.cov1->p, (T*)o.cov1, t1,
+           1, per, 1LL, r0, 0);
+  if (o.cov2 && r0 == 0)
+    LAUNCH(env, k_scatter<T>, grid_for(t2 * per), kThreads, 0, (const T*)s.cov2->p, (T*)o.cov2, t2,
+           1, per, 1LL, c0, 0);
+  return NTK_OK;
+}
+
+// One tile through the general per-layer path.
+template <typename T>
+int run_tile_generic(Env& env, const ntk_program& prog, const T* x1, int t1, const T* x2, int t2,
+                     int H, int W, int C, bool want_ntk, int r0, int c0, int n2,
+                     const OutPtrs& out) {
+  std::vector<TState> slots(prog.n_slots);
+  NTK_TRY(build_input_state<T>(env, x1, t1, x2, t2, H, W, C, want_ntk, slots[0]));
+  NTK_TRY(run_ops<T>(env, prog, slots, 0, t1, t2));
+  TState& fin = slots[prog.out_slot];
+  if (!fin.valid) return fail(NTK_EINVAL, "program left its output slot empty");
+  NTK_TRY(scatter_tile<T>(env, fin, t1, t2, r0, c0, n2, out));
+  for (auto& s : slots)
+    if (s.valid) env.release(s);
+  return NTK_OK;
+}
+
+template <typename T>
+int dry_peak_generic(const ntk_program& prog, int t1, int t2, int H, int W, int C, bool want_ntk,
+                     size_t* peak) {
+  Arena a;
+  a.reset(nullptr, 0, true);
+  Env env;
+  env.arena = &a;
+  env.dry = true;
+  OutPtrs o{(void*)1, want_ntk ? (void*)1 : nullptr, nullptr, nullptr, t2};
+  int st = run_tile_generic<T>(env, prog, (const T*)nullptr, t1, (const T*)nullptr, t2, H, W, C,
+                               want_ntk, 0, 0, t2, o);
+  *peak = a.peak();
+  return st;
+}
+
+template <typename T>
+int choose_tile(const ntk_program& prog, size_t ws, int n1, int n2, int H, int W, int C,
+                bool want_ntk, int* t1o, int* t2o) {
+  auto fits = [&](int a, int b, bool* ok) -> int {
+    size_t peak = 0;
+    int st = dry_peak_generic<T>(prog, a, b, H, W, C, want_ntk, &peak);
+    if (st != NTK_OK) return st;
+    *ok = peak <= ws;
+    return NTK_OK;
+  };
+  bool ok = false;
+  NTK_TRY(fits(1, 1, &ok));
+  if (!ok) return fail(NTK_ENOMEM, "workspace (%zu bytes) cannot hold a single pair", ws);
+  int t1 = 1, t2 = 1;
+  // grow alternately while it fits
+  for (;;) {
+    bool grew = false;
+    if (t2 < n2) {
+      int c = std::min(n2, t2 * 2);
+      NTK_TRY(fits(t1, c, &ok));
+      if (ok) {
+        t2 = c;
+        grew = true;
+      }
+    }
+    if (t1 < n1) {
+      int c = std::min(n1, t1 * 2);
+      NTK_TRY(fits(c, t2, &ok));
+      if (ok) {
+        t1 = c;
+        grew = true;
+      }
+    }
+    if (!grew) break;
+    if ((long long)t1 * t2 >= (1LL << 22)) break;
+  }
+  *t1o = t1;
+  *t2o = t2;
+  return NTK_OK;
+}
+
+int validate_program(ntk_program& p) {
+  const int n = (int)p.ops.size();
+  if (p.n_slots < 1 || p.out_slot < 0 || p.out_slot >= p.n_slots)
+    return fail(NTK_EINVAL, "bad slot configuration");
+  p.last_use.assign(p.n_slots, -1);
+  for (int k = 0; k < n; ++k) {
+    const ntk_op_t& op = p.ops[k];
+    if (op.src < 0 || op.src >= p.n_slots || op.dst < 0 || op.dst >= p.n_slots)
+      return fail(NTK_EINVAL, "op %d: slot out of range", k);
+    if (op.kind == NTK_OP_FANINSUM && (op.src2 < 0 || op.src2 >= p.n_slots))
+      return fail(NTK_EINVAL, "op %d: FanInSum needs src2", k);
+    p.last_use[op.src] = k;
+    if (op.kind == NTK_OP_FANINSUM) p.last_use[op.src2] = k;
+    switch (op.kind) {
+      case NTK_OP_CONV:
+      case NTK_OP_AVGPOOL:
+        if (op.i[0] < 1 || op.i[1] < 1 || op.i[2] < 1 || op.i[3] < 1 || op.i[4] < 0 || op.i[4] > 2)
+          return fail(NTK_EINVAL, "op %d: bad window/stride/padding", k);
+        break;
+      case NTK_OP_DENSE:
+      case NTK_OP_ABRELU:
+      case NTK_OP_ERF:
+      case NTK_OP_GAP:
+      case NTK_OP_FLATTEN:
+      case NTK_OP_FANINSUM:
+      case NTK_OP_IDENTITY:
+        break;
+      default:
+        return fail(NTK_EINVAL, "op %d: unknown kind %d", k, op.kind);
+    }
+  }
+  p.last_use[p.out_slot] = n;  // never retired by an op
+  return NTK_OK;
+}
+
+int ensure_io(ntk_context* ctx, int which, size_t bytes) {
+  if (ctx->io_bytes[which] >= bytes) return NTK_OK;
+  if (ctx->io[which]) NTK_CUDA(cudaFree(ctx->io[which]));
+  ctx->io[which] = nullptr;
+  ctx->io_bytes[which] = 0;
+  size_t want = std::max(bytes, (size_t)1 << 20);
+  NTK_CUDA(cudaMalloc(&ctx->io[which], want));
+  ctx->io_bytes[which] = want;
+  return NTK_OK;
+}
+
+template <typename T>
+int gram_device_t(ntk_context* ctx, const ntk_program* prog, const T* x1, int n1, const T* x2,
+                  int n2, int H, int W, int C, uint32_t flags, const OutPtrs& out) {
+  const bool want_ntk = (flags & NTK_FLAG_NTK) != 0;
+  const bool symmetric = x2 == nullptr;
+  if (symmetric) {
+    x2 = x1;
+    n2 = n1;
+  }
+  NTK_CUDA(cudaSetDevice(ctx->device));
+  Env env;
+  env.ctx = ctx;
+  env.arena = &ctx->arena;
+  env.stream = ctx->stream;
+
+  // Fast path: fused diagonal-marching kernels (fused_kernels.cuh).
+  if (!(flags & NTK_FLAG_NO_FUSION) && prog->fused.ok && H > 0 &&
+      fused_supported<T>(prog->fused, H, W, C) && !out.cov1 && !out.cov2) {
+    ctx->arena.reset(ctx->ws, ctx->ws_bytes, false);
+    int st = fused_gram<T>(prog->fused, ctx->arena, ctx->stream, &env.launches, x1, n1, x2, n2,
+                           symmetric, H, W, C, want_ntk, (T*)out.nngp, (T*)out.ntk, out.ld);
+    ctx->launches += env.launches;
+    return st;
+  }
+
+  int t1 = 0, t2 = 0;
+  NTK_TRY(choose_tile<T>(*prog, ctx->ws_bytes, n1, n2, H, W, C, want_ntk, &t1, &t2));
+  const size_t row = (size_t)(H > 0 ? (size_t)H * W * C : (size_t)C);
+  for (int r0 = 0; r0 < n1; r0 += t1) {
+    const int a = std::min(t1, n1 - r0);
+    for (int c0 = 0; c0 < n2; c0 += t2) {
+      const int b = std::min(t2, n2 - c0);
+      ctx->arena.reset(ctx->ws, ctx->ws_bytes, false);
+      env.bufs.clear();
+      int st = run_tile_generic<T>(env, *prog, x1 + (size_t)r0 * row, a, x2 + (size_t)c0 * row, b,
+                                   H, W, C, want_ntk, r0, c0, n2, out);
+      if (st != NTK_OK) {
+        ctx->launches += env.launches;
+        return st;
+      }
+    }
+  }
+  ctx->launches += env.launches;
+  return NTK_OK;
+}
+
+}  // namespace
+
+template <typename T>
+static int apply_host_t(ntk_context* ctx, const ntk_program* prog, const ntk_state_t* in,
+                        ntk_state_t* out) {
+  const int t1 = in->n1, t2 = in->n2;
+  const long long per_i = per_of(in->H, in->W);
+  const long long P = (long long)t1 * t2;
+  ctx->arena.reset(ctx->ws, ctx->ws_bytes, false);
+  Env env;
+  env.ctx = ctx;
+  env.arena = &ctx->arena;
+  env.stream = ctx->stream;
+  std::vector<TState> slots(prog->n_slots);
+  TState& s = slots[0];
+  int st = NTK_OK;
+  auto up = [&](const void* host, long long n, Buf** dst) -> int {
+    Buf* b = env.alloc((size_t)n * sizeof(T), &st);
+    if (!b) return st;
+    NTK_CUDA(cudaMemcpyAsync(b->p, host, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *dst = b;
+    return NTK_OK;
+  };
+  NTK_TRY(up(in->nngp, P * per_i, &s.nngp));
+  NTK_TRY(up(in->cov1, t1 * per_i, &s.cov1));
+  NTK_TRY(up(in->cov2 ? in->cov2 : in->cov1, t2 * per_i, &s.cov2));
+  s.ntk_mode = in->ntk_mode;
+  if (in->ntk_mode == NTK_NTK_TENSOR) NTK_TRY(up(in->ntk, P * per_i, &s.ntk));
+  s.H = in->H;
+  s.W = in->W;
+  s.gaussian = in->is_gaussian != 0;
+  s.valid = true;
+  NTK_TRY(run_ops<T>(env, *prog, slots, 0, t1, t2));
+  TState& f = slots[prog->out_slot];
+  if (!f.valid) return fail(NTK_EINVAL, "program left its output slot empty");
+  const long long per_o = per_of(f.H, f.W);
+  auto down = [&](void* host, Buf* b, long long n) -> int {
+    if (host && b)
+      NTK_CUDA(cudaMemcpyAsync(host, b->p, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    return NTK_OK;
+  };
+  NTK_TRY(down(out->nngp, f.nngp, P * per_o));
+  if (f.ntk_mode == NTK_NTK_TENSOR) NTK_TRY(down(out->ntk, f.ntk, P * per_o));
+  NTK_TRY(down(out->cov1, f.cov1, t1 * per_o));
+  if (in->cov2) NTK_TRY(down(out->cov2, f.cov2, t2 * per_o));
+  out->n1 = t1;
+  out->n2 = t2;
+  out->H = f.H;
+  out->W = f.W;
+  out->ntk_mode = f.ntk_mode;
+  out->is_gaussian = f.gaussian ? 1 : 0;
+  NTK_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->launches += env.launches;
+  return NTK_OK;
+}
+
+
+// =================================== C ABI ===================================
+extern "C" {
+
+int ntk_abi_version(void) { return NTK_B200_ABI_VERSION; }
+
+const char* ntk_last_error(void) { return last_error().c_str(); }
+
+int ntk_device_count(int* count) {
+  if (!count) return fail(NTK_EINVAL, "count is NULL");
+  NTK_CUDA(cudaGetDeviceCount(count));
+  return NTK_OK;
+}
+
+int ntk_program_create(const ntk_op_t* ops, int32_t n_ops, int32_t n_slots, int32_t out_slot,
+                       ntk_program_t** out) {
+  if (!out || (n_ops > 0 && !ops) || n_ops < 0) return fail(NTK_EINVAL, "bad arguments");
+  std::unique_ptr<ntk_program> p(new ntk_program());
+  p->ops.assign(ops, ops + n_ops);
+  p->n_slots = n_slots;
+  p->out_slot = out_slot;
+  NTK_TRY(validate_program(*p));
+  p->fused = plan_fused(p->ops, p->n_slots, p->out_slot);
+  *out = p.release();
+  return NTK_OK;
+}
+
+void ntk_program_destroy(ntk_program_t* prog) { delete prog; }
+
+int ntk_program_output_shape(const ntk_program_t* prog, int32_t H, int32_t W,
+                             int32_t in_is_gaussian, int32_t* out_H, int32_t* out_W,
+                             int32_t* out_is_gaussian) {
+  if (!prog) return fail(NTK_EINVAL, "prog is NULL");
+  struct S {
+    int H, W;
+    bool g, valid;
+  };
+  std::vector<S> slots(prog->n_slots, S{0, 0, false, false});
+  slots[0] = S{H, W, in_is_gaussian != 0, true};
+  for (size_t k = 0; k < prog->ops.size(); ++k) {
+    const ntk_op_t& op = prog->ops[k];
+    S in = slots[op.src];
+    if (!in.valid) return fail(NTK_EINVAL, "op %zu reads empty slot", k);
+    S o = in;
+    switch (op.kind) {
+      case NTK_OP_CONV:
+      case NTK_OP_AVGPOOL: {
+        if (in.H <= 0) return fail(NTK_EINVAL, "spatial op on non-spatial input");
+        AxisGeom gh = axis_geom(in.H, op.i[0], op.i[2], op.i[4]);
+        AxisGeom gw = axis_geom(in.W, op.i[1], op.i[3], op.i[4]);
+        if (gh.out <= 0 || gw.out <= 0) return fail(NTK_EINVAL, "empty output");
+        o.H = gh.out;
+        o.W = gw.out;
+        if (op.kind == NTK_OP_CONV) o.g = true;
+        break;
+      }
+      case NTK_OP_DENSE:
+        o.g = true;
+        break;
+      case NTK_OP_ABRELU:
+      case NTK_OP_ERF:
+        if (!in.g) return fail(NTK_ENOTGAUSSIAN, "The input to the activation function must be Gaussian");
+        o.g = false;
+        break;
+      case NTK_OP_GAP:
+        if (in.H <= 0) return fail(NTK_EINVAL, "GlobalAvgPool needs spatial inputs");
+        o.H = o.W = 0;
+        break;
+      case NTK_OP_FLATTEN:
+        o.H = o.W = 0;
+        o.g = false;
+        break;
+      case NTK_OP_FANINSUM: {
+        S b = slots[op.src2];
+        if (b.H != in.H || b.W != in.W) return fail(NTK_ESHAPE, "All shapes should be equal in `FanInSum`");
+        if (!(in.g && b.g)) return fail(NTK_EUNSUPPORTED, "`FanInSum` needs Gaussian inputs");
+        o.g = true;
+        break;
+      }
+      default:
+        break;
+    }
+    slots[op.dst] = o;
+  }
+  S f = slots[prog->out_slot];
+  if (out_H) *out_H = f.H;
+  if (out_W) *out_W = f.W;
+  if (out_is_gaussian) *out_is_gaussian = f.g ? 1 : 0;
+  return NTK_OK;
+}
+
+int ntk_context_create(int32_t device, size_t workspace_bytes, ntk_context_t** out) {
+  if (!out) return fail(NTK_EINVAL, "out is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(NTK_ECUDA, "no CUDA device available (%s); ntk_b200 has no CPU fallback",
+                cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(NTK_EINVAL, "device %d out of range [0,%d)", device, n);
+  NTK_CUDA(cudaSetDevice(device));
+  std::unique_ptr<ntk_context> c(new ntk_context());
+  c->device = device;
+  NTK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  if (workspace_bytes == 0) {
+    size_t free_b = 0, total_b = 0;
+    NTK_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    workspace_bytes = std::min<size_t>((size_t)(free_b * 0.5), (size_t)48 << 30);
+  }
+  NTK_CUDA(cudaMalloc((void**)&c->ws, workspace_bytes));
+  c->ws_bytes = workspace_bytes;
+  NTK_TRY(fused_configure_device());
+  *out = c.release();
+  return NTK_OK;
+}
+
+void ntk_context_destroy(ntk_context_t* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int k = 0; k < 6; ++k)
+    if (ctx->io[k]) cudaFree(ctx->io[k]);
+  if (ctx->ws) cudaFree(ctx->ws);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int ntk_context_synchronize(ntk_context_t* ctx) {
+  if (!ctx) return fail(NTK_EINVAL, "ctx is NULL");
+  NTK_CUDA(cudaSetDevice(ctx->device));
+  NTK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NTK_OK;
+}
+
+void* ntk_context_stream(ntk_context_t* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int64_t ntk_context_launch_count(const ntk_context_t* ctx) { return ctx ? ctx->launches : 0; }
+
+int ntk_gram_device(ntk_context_t* ctx, const ntk_program_t* prog, int32_t dtype, const void* x1,
+                    int32_t n1, const void* x2, int32_t n2, int32_t H, int32_t W, int32_t C,
+                    uint32_t flags, void* nngp, void* ntk, int64_t ld, void* cov1, void* cov2) {
+  if (!ctx || !prog || !x1 || n1 <= 0 || C <= 0 || (x2 && n2 <= 0))
+    return fail(NTK_EINVAL, "bad arguments");
+  if ((H > 0) != (W > 0) || H < 0) return fail(NTK_EINVAL, "bad spatial shape");
+  if ((flags & NTK_FLAG_NTK) && !ntk) return fail(NTK_EINVAL, "NTK requested but ntk is NULL");
+  OutPtrs o{nngp, (flags & NTK_FLAG_NTK) ? ntk : nullptr,
+            (flags & NTK_FLAG_WANT_COV) ? cov1 : nullptr,
+            (flags & NTK_FLAG_WANT_COV) ? cov2 : nullptr, ld};
+  if (dtype == NTK_F32)
+    return gram_device_t<float>(ctx, prog, (const float*)x1, n1, (const float*)x2, n2, H, W, C,
+                                flags, o);
+  if (dtype == NTK_F64)
+    return gram_device_t<double>(ctx, prog, (const double*)x1, n1, (const double*)x2, n2, H, W, C,
+                                 flags, o);
+  return fail(NTK_EINVAL, "unknown dtype %d", dtype);
+}
+
+int ntk_gram_host(ntk_context_t* ctx, const ntk_program_t* prog, int32_t dtype, const void* x1,
+                  int32_t n1, const void* x2, int32_t n2, int32_t H, int32_t W, int32_t C,
+                  uint32_t flags, void* nngp, void* ntk, int64_t ld, void* cov1, void* cov2) {
+  if (!ctx || !prog || !x1 || n1 <= 0 || C <= 0) return fail(NTK_EINVAL, "bad arguments");
+  if (dtype != NTK_F32 && dtype != NTK_F64) return fail(NTK_EINVAL, "unknown dtype %d", dtype);
+  NTK_CUDA(cudaSetDevice(ctx->device));
+  const size_t sz = dtype == NTK_F32 ? 4 : 8;
+  const size_t row = (size_t)(H > 0 ? (size_t)H * W * C : (size_t)C);
+  const int m2 = x2 ? n2 : n1;
+  int oh = 0, ow = 0, og = 0;
+  NTK_TRY(ntk_program_output_shape(prog, H, W, 0, &oh, &ow, &og));
+  const size_t per = (size_t)per_of(oh, ow);
+  const size_t ldd = oh > 0 ? (size_t)m2 : (size_t)m2;  // device results are dense [n1, m2]
+  const bool want_ntk = (flags & NTK_FLAG_NTK) != 0;
+  const bool want_cov = (flags & NTK_FLAG_WANT_COV) != 0;
+  NTK_TRY(ensure_io(ctx, 0, (size_t)n1 * row * sz));
+  if (x2) NTK_TRY(ensure_io(ctx, 1, (size_t)n2 * row * sz));
+  NTK_TRY(ensure_io(ctx, 2, (size_t)n1 * ldd * per * sz));
+  if (want_ntk) NTK_TRY(ensure_io(ctx, 3, (size_t)n1 * ldd * per * sz));
+  if (want_cov) {
+    NTK_TRY(ensure_io(ctx, 4, (size_t)n1 * per * sz));
+    if (x2) NTK_TRY(ensure_io(ctx, 5, (size_t)n2 * per * sz));
+  }
+  NTK_CUDA(cudaMemcpyAsync(ctx->io[0], x1, (size_t)n1 * row * sz, cudaMemcpyHostToDevice, ctx->stream));
+  if (x2)
+    NTK_CUDA(cudaMemcpyAsync(ctx->io[1], x2, (size_t)n2 * row * sz, cudaMemcpyHostToDevice, ctx->stream));
+  NTK_TRY(ntk_gram_device(ctx, prog, dtype, ctx->io[0], n1, x2 ? ctx->io[1] : nullptr, n2, H, W, C,
+                          flags, ctx->io[2], want_ntk ? ctx->io[3] : nullptr, (int64_t)ldd,
+                          want_cov ? ctx->io[4] : nullptr, (want_cov && x2) ? ctx->io[5] : nullptr));
+  auto d2h = [&](void* dst, const void* src) -> int {
+    if (oh > 0 || (size_t)ld == ldd) {
+      NTK_CUDA(cudaMemcpyAsync(dst, src, (size_t)n1 * ldd * per * sz, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+      NTK_CUDA(cudaMemcpy2DAsync(dst, (size_t)ld * sz, src, ldd * sz, (size_t)m2 * sz, (size_t)n1,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return NTK_OK;
+  };
+  if (nngp) NTK_TRY(d2h(nngp, ctx->io[2]));
+  if (want_ntk && ntk) NTK_TRY(d2h(ntk, ctx->io[3]));
+  if (want_cov && cov1)
+    NTK_CUDA(cudaMemcpyAsync(cov1, ctx->io[4], (size_t)n1 * per * sz, cudaMemcpyDeviceToHost, ctx->stream));
+  if (want_cov && cov2 && x2)
+    NTK_CUDA(cudaMemcpyAsync(cov2, ctx->io[5], (size_t)n2 * per * sz, cudaMemcpyDeviceToHost, ctx->stream));
+  NTK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NTK_OK;
+}
+
+int ntk_apply_host(ntk_context_t* ctx, const ntk_program_t* prog, int32_t dtype,
+                   const ntk_state_t* in, ntk_state_t* out) {
+  if (!ctx || !prog || !in || !out || !in->nngp || !in->cov1 || in->n1 <= 0 || in->n2 <= 0)
+    return fail(NTK_EINVAL, "bad arguments");
+  NTK_CUDA(cudaSetDevice(ctx->device));
+  if (dtype == NTK_F32) return apply_host_t<float>(ctx, prog, in, out);
+  if (dtype == NTK_F64) return apply_host_t<double>(ctx, prog, in, out);
+  return fail(NTK_EINVAL, "unknown dtype %d", dtype);
+}
+
+int ntk_workspace_bytes(const ntk_program_t* prog, int32_t dtype, int32_t t1, int32_t t2, int32_t H,
+                        int32_t W, int32_t C, uint32_t flags, size_t* bytes) {
+  if (!prog || !bytes || t1 <= 0 || t2 <= 0) return fail(NTK_EINVAL, "bad arguments");
+  const bool want_ntk = (flags & NTK_FLAG_NTK) != 0;
+  if (dtype == NTK_F32) return dry_peak_generic<float>(*prog, t1, t2, H, W, C, want_ntk, bytes);
+  if (dtype == NTK_F64) return dry_peak_generic<double>(*prog, t1, t2, H, W, C, want_ntk, bytes);
+  return fail(NTK_EINVAL, "unknown dtype %d", dtype);
+}
+
+int ntk_device_malloc(int32_t device, size_t bytes, void** ptr) {
+  if (!ptr) return fail(NTK_EINVAL, "ptr is NULL");
+  NTK_CUDA(cudaSetDevice(device));
+  NTK_CUDA(cudaMalloc(ptr, bytes));
+  return NTK_OK;
+}
+
+int ntk_device_free(int32_t device, void* ptr) {
+  NTK_CUDA(cudaSetDevice(device));
+  NTK_CUDA(cudaFree(ptr));
+  return NTK_OK;
+}
+
+int ntk_memcpy_h2d(ntk_context_t* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+  if (!ctx) return fail(NTK_EINVAL, "ctx is NULL");
+  NTK_CUDA(cudaSetDevice(ctx->device));
+  NTK_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return NTK_OK;
+}
+
+int ntk_memcpy_d2h(ntk_context_t* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+  if (!ctx) return fail(NTK_EINVAL, "ctx is NULL");
+  NTK_CUDA(cudaSetDevice(ctx->device));
+  NTK_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  NTK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NTK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,411 @@
+// One-kernel-per-layer path: straightforward, coalesced, grid-stride kernels on
+// the canonical zipped layout [pair, h, h', w, w'].  This is the general path
+// (any filter/stride/padding, Erf, FanInSum, Kernel-in/Kernel-out); the fused
+// diagonal-marching kernels in fused_kernels.cuh take over for the stride-1
+// 3x3 SAME Conv+ABRelu(+AvgPool 2x2) stacks that dominate the Myrtle configs.
+//
+// Math follows SURVEY.md Appendix A; each kernel cites the reference rule.
+#pragma once
+
+#include "common.cuh"
+
+namespace ntk {
+
+template <typename T>
+struct Consts;
+template <>
+struct Consts<float> {
+  static __host__ __device__ constexpr float pi() { return 3.14159265358979323846f; }
+};
+template <>
+struct Consts<double> {
+  static __host__ __device__ constexpr double pi() { return 3.14159265358979323846; }
+};
+
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float sqrt_t(float a) { return sqrtf(a); }
+__device__ __forceinline__ double sqrt_t(double a) { return sqrt(a); }
+__device__ __forceinline__ float atan2_t(float y, float x) { return atan2f(y, x); }
+__device__ __forceinline__ double atan2_t(double y, double x) { return atan2(y, x); }
+__device__ __forceinline__ float max_t(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double max_t(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float abs_t(float a) { return fabsf(a); }
+__device__ __forceinline__ double abs_t(double a) { return fabs(a); }
+
+// Pair index -> (row sample, column sample).  `self`: pair p is (p, p) (cov1/cov2).
+struct PairMap {
+  int n2;
+  int self;
+  __device__ __forceinline__ void ij(long long p, int& i, int& j) const {
+    if (self) {
+      i = j = (int)p;
+    } else {
+      i = (int)(p / n2);
+      j = (int)(p % n2);
+    }
+  }
+};
+
+constexpr int kThreads = 256;
+
+inline int grid_for(long long n, int threads = kThreads) {
+  long long b = (n + threads - 1) / threads;
+  long long cap = (long long)kNumSMs * 32;  // grid-stride beyond this
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ---- input layer: requirements.py:542-553 (cross) / 529-539 (self) -----------
+// out[p,h,h',w,w'] = (1/C) sum_c x1[i,h,w,c] * x2[j,h',w',c]
+template <typename T>
+__global__ void k_input_cov(const T* __restrict__ x1, const T* __restrict__ x2, T* __restrict__ out,
+                            long long P, PairMap pm, int H, int W, int C, T inv_c) {
+  const long long per = (long long)H * H * W * W;
+  const long long total = P * per;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long p = idx / per;
+    int r = (int)(idx % per);
+    int w2 = r % W;
+    r /= W;
+    int w = r % W;
+    r /= W;
+    int h2 = r % H;
+    int h = r / H;
+    int i, j;
+    pm.ij(p, i, j);
+    const T* a = x1 + (((long long)i * H + h) * W + w) * C;
+    const T* b = x2 + (((long long)j * H + h2) * W + w2) * C;
+    T acc = 0;
+    for (int c = 0; c < C; ++c) acc = fma_t(a[c], b[c], acc);
+    out[idx] = acc * inv_c;
+  }
+}
+
+// FCN input ([N,d] inputs): nngp[i,j] = x1[i].x2[j]/d, one warp per output.
+// (The tensor-core split-precision GEMM in gemm_kernels.cuh replaces this for
+// large d; this kernel is the exact-accumulation fallback for tiny/odd shapes.)
+template <typename T>
+__global__ void k_rowdot(const T* __restrict__ x1, const T* __restrict__ x2, T* __restrict__ out,
+                         long long P, PairMap pm, int C, T inv_c) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long p = warp; p < P; p += nwarps) {
+    int i, j;
+    pm.ij(p, i, j);
+    const T* a = x1 + (long long)i * C;
+    const T* b = x2 + (long long)j * C;
+    T acc = 0;
+    for (int c = lane; c < C; c += 32) acc = fma_t(a[c], b[c], acc);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[p] = acc * inv_c;
+  }
+}
+
+// ---- Conv rule: linear.py:3341-3378 (diagonal-offset box filter) -------------
+// out[p,a,a',b,b'] = scale/(kh kw) * sum_{i<kh,j<kw} in~[sa+i-lo, sa'+i-lo, sb+j-lo, sb'+j-lo]
+//                    + shift (+ addend[p,a,a',b,b'])
+struct ConvGeom {
+  int Hi, Wi, Ho, Wo, kh, kw, sh, sw, loh, low, circular;
+};
+
+template <typename T>
+__global__ void k_conv(const T* __restrict__ in, const T* __restrict__ addend, T* __restrict__ out,
+                       long long P, ConvGeom g, T scale, T shift) {
+  const long long per_o = (long long)g.Ho * g.Ho * g.Wo * g.Wo;
+  const long long per_i = (long long)g.Hi * g.Hi * g.Wi * g.Wi;
+  const long long total = P * per_o;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long p = idx / per_o;
+    int r = (int)(idx % per_o);
+    int b2 = r % g.Wo;
+    r /= g.Wo;
+    int b = r % g.Wo;
+    r /= g.Wo;
+    int a2 = r % g.Ho;
+    int a = r / g.Ho;
+    const T* src = in + p * per_i;
+    T acc = 0;
+    for (int i = 0; i < g.kh; ++i) {
+      int h = g.sh * a + i - g.loh, h2 = g.sh * a2 + i - g.loh;
+      if (g.circular) {
+        h = ((h % g.Hi) + g.Hi) % g.Hi;
+        h2 = ((h2 % g.Hi) + g.Hi) % g.Hi;
+      } else if (h < 0 || h >= g.Hi || h2 < 0 || h2 >= g.Hi) {
+        continue;
+      }
+      for (int j = 0; j < g.kw; ++j) {
+        int w = g.sw * b + j - g.low, w2 = g.sw * b2 + j - g.low;
+        if (g.circular) {
+          w = ((w % g.Wi) + g.Wi) % g.Wi;
+          w2 = ((w2 % g.Wi) + g.Wi) % g.Wi;
+        } else if (w < 0 || w >= g.Wi || w2 < 0 || w2 >= g.Wi) {
+          continue;
+        }
+        acc += src[(((long long)h * g.Hi + h2) * g.Wi + w) * g.Wi + w2];
+      }
+    }
+    T v = fma_t(acc, scale, shift);
+    if (addend) v += addend[idx];
+    out[idx] = v;
+  }
+}
+
+// ---- AvgPool rule: linear.py:3499-3572 (independent offsets on both members) --
+struct PoolGeom {
+  int Hi, Wi, Ho, Wo, wh, ww, sh, sw, loh, low, circular, normalize_edges;
+};
+
+template <typename T>
+__global__ void k_pool(const T* __restrict__ in, T* __restrict__ out, long long P, PoolGeom g) {
+  const long long per_o = (long long)g.Ho * g.Ho * g.Wo * g.Wo;
+  const long long per_i = (long long)g.Hi * g.Hi * g.Wi * g.Wi;
+  const long long total = P * per_o;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long p = idx / per_o;
+    int r = (int)(idx % per_o);
+    int b2 = r % g.Wo;
+    r /= g.Wo;
+    int b = r % g.Wo;
+    r /= g.Wo;
+    int a2 = r % g.Ho;
+    int a = r / g.Ho;
+    const T* src = in + p * per_i;
+    T acc = 0;
+    int cnt_h = 0, cnt_h2 = 0, cnt_w = 0, cnt_w2 = 0;
+    for (int i = 0; i < g.wh; ++i) {
+      int h = g.sh * a + i - g.loh;
+      if (g.circular) h = ((h % g.Hi) + g.Hi) % g.Hi;
+      if (h >= 0 && h < g.Hi) ++cnt_h;
+    }
+    for (int i = 0; i < g.wh; ++i) {
+      int h = g.sh * a2 + i - g.loh;
+      if (g.circular) h = ((h % g.Hi) + g.Hi) % g.Hi;
+      if (h >= 0 && h < g.Hi) ++cnt_h2;
+    }
+    for (int i = 0; i < g.ww; ++i) {
+      int w = g.sw * b + i - g.low;
+      if (g.circular) w = ((w % g.Wi) + g.Wi) % g.Wi;
+      if (w >= 0 && w < g.Wi) ++cnt_w;
+    }
+    for (int i = 0; i < g.ww; ++i) {
+      int w = g.sw * b2 + i - g.low;
+      if (g.circular) w = ((w % g.Wi) + g.Wi) % g.Wi;
+      if (w >= 0 && w < g.Wi) ++cnt_w2;
+    }
+    for (int i = 0; i < g.wh; ++i) {
+      int h = g.sh * a + i - g.loh;
+      if (g.circular) h = ((h % g.Hi) + g.Hi) % g.Hi;
+      if (h < 0 || h >= g.Hi) continue;
+      for (int i2 = 0; i2 < g.wh; ++i2) {
+        int h2 = g.sh * a2 + i2 - g.loh;
+        if (g.circular) h2 = ((h2 % g.Hi) + g.Hi) % g.Hi;
+        if (h2 < 0 || h2 >= g.Hi) continue;
+        for (int j = 0; j < g.ww; ++j) {
+          int w = g.sw * b + j - g.low;
+          if (g.circular) w = ((w % g.Wi) + g.Wi) % g.Wi;
+          if (w < 0 || w >= g.Wi) continue;
+          const T* row = src + (((long long)h * g.Hi + h2) * g.Wi + w) * g.Wi;
+          for (int j2 = 0; j2 < g.ww; ++j2) {
+            int w2 = g.sw * b2 + j2 - g.low;
+            if (g.circular) w2 = ((w2 % g.Wi) + g.Wi) % g.Wi;
+            if (w2 < 0 || w2 >= g.Wi) continue;
+            acc += row[w2];
+          }
+        }
+      }
+    }
+    T norm = g.normalize_edges ? (T)((long long)cnt_h * cnt_h2 * cnt_w * cnt_w2)
+                               : (T)((long long)g.wh * g.wh * g.ww * g.ww);
+    out[idx] = acc / norm;
+  }
+}
+
+// ---- diagonal variances: requirements.py:1057-1074 ----------------------------
+// q[n,h,w] = cov[n,h,h,w,w]
+template <typename T>
+__global__ void k_diag(const T* __restrict__ cov, T* __restrict__ q, long long n, int H, int W) {
+  const long long total = n * H * W;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long s = idx / ((long long)H * W);
+    int r = (int)(idx % ((long long)H * W));
+    int h = r / W, w = r % W;
+    q[idx] = cov[((((long long)s * H + h) * H + h) * W + w) * W + w];
+  }
+}
+
+// ---- activations ---------------------------------------------------------------
+// ABRelu: elementwise.py:444-455;  Erf: elementwise.py:84-93 + kernel.py:426-439.
+struct ActParams {
+  int kind;       // NTK_OP_ABRELU or NTK_OP_ERF
+  double a, b, c;
+};
+
+template <typename T>
+__device__ __forceinline__ void abrelu_point(T k, T prod, T coef_s, T half_ab, T& k_out, T& dot) {
+  // s = sqrt(max(prod - k^2, 0)); theta = atan2(s, k) (pi/2 at (0,0));
+  // dot = (a^2+b^2)/2 - (a-b)^2/(2 pi) * theta;  k' = (a-b)^2/(2 pi) * s + dot * k
+  T s = sqrt_t(max_t(fma_t(-k, k, prod), (T)0));
+  T theta = (s == (T)0 && k == (T)0) ? Consts<T>::pi() / 2 : atan2_t(s, k);
+  dot = half_ab - coef_s * theta;
+  k_out = fma_t(dot, k, coef_s * s);
+}
+
+template <typename T>
+__device__ __forceinline__ void erf_point(T k, T prod, T& k_out, T& dot) {
+  // k, prod already include the b^2 input scale: prod = (1+2 q1)(1+2 q2).
+  T s = sqrt_t(max_t(fma_t((T)-4 * k, k, prod), (T)0));
+  const T f = (T)2 / Consts<T>::pi();
+  k_out = f * atan2_t((T)2 * k, s);
+  dot = (T)2 * f / s;
+}
+
+// In-place on K (and Tt when non-null).  q1/q2 are the diagonal maps of cov1/cov2
+// taken BEFORE this activation.  `stab` (device scalar, nullable) is the
+// do_stabilize factor of elementwise.py:430-436.
+template <typename T>
+__global__ void k_act(T* __restrict__ K, T* __restrict__ Tt, const T* __restrict__ q1,
+                      const T* __restrict__ q2, long long P, PairMap pm, int H, int W, ActParams ap,
+                      const T* __restrict__ stab) {
+  const long long per = (long long)H * H * W * W;
+  const long long total = P * per;
+  const T a = (T)ap.a, b = (T)ap.b;
+  const T coef_s = (a - b) * (a - b) / ((T)2 * Consts<T>::pi());
+  const T half_ab = (a * a + b * b) / (T)2;
+  const T bb = b * b, aa = a * a, cc = (T)(ap.c * ap.c);
+  T factor = (T)1;
+  if (stab) factor = max_t(*stab, (T)1e-12);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long p = idx / per;
+    int r = (int)(idx % per);
+    int w2 = r % W;
+    r /= W;
+    int w = r % W;
+    r /= W;
+    int h2 = r % H;
+    int h = r / H;
+    int i, j;
+    pm.ij(p, i, j);
+    T v1 = q1[((long long)i * H + h) * W + w];
+    T v2 = q2[((long long)j * H + h2) * W + w2];
+    T k = K[idx];
+    T ko, dot;
+    if (ap.kind == NTK_OP_ABRELU) {
+      if (stab) {
+        k /= factor;
+        v1 /= factor;
+        v2 /= factor;
+      }
+      abrelu_point<T>(k, v1 * v2, coef_s, half_ab, ko, dot);
+      if (stab) ko *= factor;
+      K[idx] = ko;
+      if (Tt) Tt[idx] *= dot;
+    } else {
+      k *= bb;
+      T prod = ((T)1 + (T)2 * bb * v1) * ((T)1 + (T)2 * bb * v2);
+      erf_point<T>(k, prod, ko, dot);
+      K[idx] = fma_t(aa, ko, cc);
+      if (Tt) Tt[idx] = aa * (bb * Tt[idx] * dot);
+    }
+  }
+}
+
+// max |x| over a tensor -> *out (out must be zeroed first); values are >= 0 so the
+// float bit pattern orders like an unsigned integer.
+template <typename T>
+__global__ void k_absmax(const T* __restrict__ x, long long n, T* __restrict__ out) {
+  T m = 0;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x)
+    m = max_t(m, abs_t(x[idx]));
+  for (int o = 16; o > 0; o >>= 1) m = max_t(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) {
+    if (sizeof(T) == 4)
+      atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint((float)m));
+    else
+      atomicMax(reinterpret_cast<unsigned long long*>(out),
+                (unsigned long long)__double_as_longlong((double)m));
+  }
+}
+
+// ---- reductions to [P]: GlobalAvgPool linear.py:1771-1801, Flatten 1865-1899 ----
+// One block per pair; fixed-order tree reduction (deterministic).
+template <typename T, bool kFlatten>
+__global__ void k_reduce_spatial(const T* __restrict__ in, T* __restrict__ out, long long P, int H,
+                                 int W) {
+  __shared__ T sm[kThreads / 32];
+  const long long per = (long long)H * H * W * W;
+  for (long long p = blockIdx.x; p < P; p += gridDim.x) {
+    const T* src = in + p * per;
+    T acc = 0;
+    if (kFlatten) {
+      for (int t = threadIdx.x; t < H * W; t += blockDim.x) {
+        int h = t / W, w = t % W;
+        acc += src[(((long long)h * H + h) * W + w) * W + w];
+      }
+    } else {
+      for (long long t = threadIdx.x; t < per; t += blockDim.x) acc += src[t];
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      T v = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : (T)0;
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (threadIdx.x == 0) out[p] = v / (T)(kFlatten ? (long long)H * W : per);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- Dense: linear.py:899-926 ----------------------------------------------------
+// K <- w2 K + b2;  T <- K_new + w2 T   (T == nullptr: skip; t_zero: T_in == 0)
+template <typename T>
+__global__ void k_dense(T* __restrict__ K, T* __restrict__ Tt, long long n, T w2, T b2, int t_zero) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    T k = fma_t(w2, K[idx], b2);
+    K[idx] = k;
+    if (Tt) Tt[idx] = t_zero ? k : fma_t(w2, Tt[idx], k);
+  }
+}
+
+// ---- FanInSum: branching.py:87-93 ---------------------------------------------------
+template <typename T>
+__global__ void k_add(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
+                      long long n) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x)
+    out[idx] = a[idx] + b[idx];
+}
+
+template <typename T>
+__global__ void k_fill(T* __restrict__ out, long long n, T v) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x)
+    out[idx] = v;
+}
+
+// ---- tile -> result matrix --------------------------------------------------------
+// src: [t1, t2, per] tile; dst: pair (r0+i, c0+j) at ((r0+i)*ld + (c0+j))*per.
+template <typename T>
+__global__ void k_scatter(const T* __restrict__ src, T* __restrict__ dst, int t1, int t2,
+                          long long per, long long ld, int r0, int c0) {
+  const long long total = (long long)t1 * t2 * per;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long p = idx / per;
+    long long e = idx % per;
+    int i = (int)(p / t2), j = (int)(p % t2);
+    dst[((long long)(r0 + i) * ld + (c0 + j)) * per + e] = src[idx];
+  }
+}
+
+}  // namespace ntk

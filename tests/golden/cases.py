@@ -98,6 +98,37 @@ CASES = {
 }
 
 
+def build(spec, stax):
+  """Assembles `spec` with the layer constructors of `stax` (the reference's module in the
+  generator, `neural_tangents_b200.stax` in the parity tests)."""
+  kind = spec[0]
+  if kind == 'serial':
+    return stax.serial(*[build(s, stax) for s in spec[1]])
+  if kind == 'parallel':
+    return stax.parallel(*[build(s, stax) for s in spec[1]])
+  if kind == 'fanout':
+    return stax.FanOut(spec[1])
+  if kind == 'faninsum':
+    return stax.FanInSum()
+  if kind == 'identity':
+    return stax.Identity()
+  if kind == 'dense':
+    return stax.Dense(1, W_std=spec[1], b_std=spec[2])
+  if kind == 'conv':
+    return stax.Conv(1, spec[1], strides=spec[2], padding=spec[3], W_std=spec[4], b_std=spec[5])
+  if kind == 'abrelu':
+    return stax.ABRelu(spec[1], spec[2], do_stabilize=spec[3])
+  if kind == 'erf':
+    return stax.Erf(spec[1], spec[2], spec[3])
+  if kind == 'avgpool':
+    return stax.AvgPool(spec[1], strides=spec[2], padding=spec[3], normalize_edges=spec[4])
+  if kind == 'gap':
+    return stax.GlobalAvgPool()
+  if kind == 'flatten':
+    return stax.Flatten()
+  raise ValueError(kind)
+
+
 def make_inputs(name):
   _, s1, s2, _ = CASES[name]
   idx = list(CASES).index(name)  # seeds are derived from the (append-only) case order

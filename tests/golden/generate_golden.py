@@ -21,33 +21,7 @@ import cases  # noqa: E402
 import ref_loader  # noqa: E402
 
 
-def build(spec, stax):
-  kind = spec[0]
-  if kind == 'serial':
-    return stax.serial(*[build(s, stax) for s in spec[1]])
-  if kind == 'parallel':
-    return stax.parallel(*[build(s, stax) for s in spec[1]])
-  if kind == 'fanout':
-    return stax.FanOut(spec[1])
-  if kind == 'faninsum':
-    return stax.FanInSum()
-  if kind == 'identity':
-    return stax.Identity()
-  if kind == 'dense':
-    return stax.Dense(1, W_std=spec[1], b_std=spec[2])
-  if kind == 'conv':
-    return stax.Conv(1, spec[1], strides=spec[2], padding=spec[3], W_std=spec[4], b_std=spec[5])
-  if kind == 'abrelu':
-    return stax.ABRelu(spec[1], spec[2], do_stabilize=spec[3])
-  if kind == 'erf':
-    return stax.Erf(spec[1], spec[2], spec[3])
-  if kind == 'avgpool':
-    return stax.AvgPool(spec[1], strides=spec[2], padding=spec[3], normalize_edges=spec[4])
-  if kind == 'gap':
-    return stax.GlobalAvgPool()
-  if kind == 'flatten':
-    return stax.Flatten()
-  raise ValueError(kind)
+build = cases.build
 
 
 def main():

@@ -1,0 +1,118 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every
+symbol include/ntk_b200.h declares, and the host-side program logic works without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+  text = open(os.path.join(ROOT, 'include', 'ntk_b200.h')).read()
+  text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+  return sorted(set(re.findall(r'\b(ntk_[a-z0-9_]+)\s*\(', text)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+  import __graft_entry__ as g
+  g.build()
+  from neural_tangents_b200 import _lib
+  return _lib
+
+
+def test_library_exports_every_declared_symbol(lib):
+  cdll = lib.load()
+  declared = _declared_symbols()
+  assert len(declared) >= 15
+  for name in declared:
+    assert hasattr(cdll, name), f'{name} declared in include/ntk_b200.h but not exported'
+  assert set(declared) == set(lib.EXPORTED_SYMBOLS)
+  assert cdll.ntk_abi_version() == 1
+
+
+def test_struct_layout_matches_header(lib):
+  # ntk_op_t: 4 + 6 int32 (40 bytes) + 4 doubles = 72 bytes; ntk_state_t: 4 ptrs + 6 int32 = 56
+  assert ctypes.sizeof(lib.NtkOp) == 72
+  assert ctypes.sizeof(lib.NtkState) == 56
+
+
+def test_program_shape_inference_without_gpu(lib):
+  import cases
+  from neural_tangents_b200 import stax
+  _, _, kf = cases.build(cases.myrtle(10), stax)
+  low = stax._lowered(stax._strip(kf._spec), False, False, True)
+  assert low.program.output_shape(32, 32) == (0, 0, True)
+  _, _, kf = cases.build(('serial', [cases.conv(), cases.RELU, cases.pool()]), stax)
+  low = stax._lowered(stax._strip(kf._spec), False, False, True)
+  assert low.program.output_shape(32, 32) == (16, 16, False)
+  assert low.out_meta.is_reversed is True
+  # WideResNet: FanOut/parallel/FanInSum lower to slot reuse + NTK_OP_FANINSUM
+  _, _, kf = cases.build(cases.wrn(), stax)
+  low = stax._lowered(stax._strip(kf._spec), False, False, True)
+  assert sum(1 for op in low.ops if op[0] == lib.OP_FANINSUM) == 4
+  assert low.program.output_shape(8, 8) == (0, 0, True)
+
+
+def test_errors_without_gpu(lib):
+  from neural_tangents_b200 import stax
+  _, _, kf = stax.serial(stax.Relu())
+  low = stax._lowered(stax._strip(kf._spec), False, False, False)
+  with pytest.raises(ValueError, match='must be Gaussian'):      # elementwise.py:1267-1270
+    low.program.output_shape(0, 0)
+  with pytest.raises(NotImplementedError):
+    stax.Dense(1, parameterization='standard')
+  with pytest.raises(NotImplementedError):
+    stax.Conv(1, (3, 3), dimension_numbers=('NCHW', 'OIHW', 'NCHW'))
+  _, _, kf = stax.serial(stax.Dense(1))
+  with pytest.raises(TypeError):                                   # requirements.py:754-758
+    kf([[1., 2.]], None, 'nngp')
+  with pytest.raises(ValueError, match='unique'):                  # utils.py:150-152
+    kf(np.ones((2, 3)), None, ('nngp', 'NNGP'))
+  with pytest.raises(ValueError, match='non-empty'):
+    kf(np.ones((2, 3)), None, ())
+  with pytest.raises(NotImplementedError):
+    kf(np.ones((2, 3)), None, 'nngp', mask_constant=0.)
+
+
+def test_no_gpu_means_loud_failure(lib):
+  """The product path has no CPU fallback."""
+  n = ctypes.c_int(0)
+  st = lib.load().ntk_device_count(ctypes.byref(n))
+  if st == 0 and n.value > 0:
+    pytest.skip('a GPU is present')
+  from neural_tangents_b200 import stax
+  _, _, kf = stax.serial(stax.Dense(1), stax.Relu(), stax.Dense(1))
+  with pytest.raises(Exception, match='no CUDA device|CUDA'):
+    kf(np.ones((2, 3), np.float32), None, 'nngp')
+
+
+def test_batch_size_arithmetic():
+  """batching.py:647-679."""
+  from neural_tangents_b200 import batching
+  assert batching._get_n_batches_and_batch_sizes(12, 8, 4, 1) == (3, 4, 2, 4)
+  assert batching._get_n_batches_and_batch_sizes(16, 8, 2, 4) == (2, 8, 4, 2)
+  with pytest.raises(ValueError, match='rows of kernel must divide'):
+    batching._get_n_batches_and_batch_sizes(10, 10, 3, 1)
+  with pytest.warns(UserWarning, match='Batch size is reduced'):
+    assert batching._get_n_batches_and_batch_sizes(8, 8, 16, 1) == (1, 8, 1, 8)
+  with pytest.raises(ValueError, match='must divide number of physical devices'):
+    batching._get_n_per_device(10, 4)
+
+
+def test_batch_stitching_with_foreign_kernel_fn():
+  """`batch` wraps any kernel_fn(x1, x2, ...) (batching.py:88-92): batched == unbatched."""
+  from neural_tangents_b200 import batching
+
+  def kernel_fn(x1, x2=None, get=None):
+    x2 = x1 if x2 is None else x2
+    return x1 @ x2.T
+
+  x1 = np.random.default_rng(0).standard_normal((12, 5))
+  x2 = np.random.default_rng(1).standard_normal((8, 5))
+  b = batching.batch(kernel_fn, batch_size=4, device_count=0)
+  np.testing.assert_allclose(b(x1, x2), kernel_fn(x1, x2), rtol=1e-13, atol=1e-14)
+  np.testing.assert_allclose(b(x1), kernel_fn(x1), rtol=1e-13, atol=1e-14)

@@ -1,0 +1,186 @@
+"""GPU parity: the CUDA path (through the Python front end and the C-ABI) against
+(1) the golden vectors generated from the reference's own code, and (2) the oracle on
+other seeded inputs.  Tolerances are north_star's: rtol 1e-4 (FP32 path vs the float64
+result) and rtol 1e-10 (FP64 path).  Exact-duplicate pairs (the diagonal of a symmetric
+Gram) get the documented looser bound (SURVEY Appendix A caveat)."""
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {False: 1e-4, True: 1e-10}
+# kappa-dot on exact duplicates carries ~sqrt(eps)/pi per Relu layer
+RTOL_DUP = {False: 2e-3, True: 2e-7}
+
+
+@pytest.fixture(scope='module')
+def nt():
+  import __graft_entry__ as g
+  g.build()
+  import neural_tangents_b200 as nt
+  yield nt
+  nt.config.update('enable_x64', False)
+  nt.config.update('disable_fusion', False)
+
+
+def _compare(v, ref, x64, symmetric):
+  assert v.shape == ref.shape
+  if symmetric and v.ndim == 2:
+    off = ~np.eye(v.shape[0], dtype=bool)
+    np.testing.assert_allclose(v[off], ref[off], rtol=RTOL[x64], atol=0)
+    np.testing.assert_allclose(np.diag(v), np.diag(ref), rtol=RTOL_DUP[x64], atol=0)
+  else:
+    np.testing.assert_allclose(v, ref, rtol=RTOL[x64], atol=RTOL[x64] * 1e-3)
+
+
+@pytest.mark.parametrize('fusion', [True, False])
+@pytest.mark.parametrize('x64', [False, True])
+@pytest.mark.parametrize('name', [n for n, c in cases.CASES.items() if c[3] is not None])
+def test_golden_matrix_outputs(nt, golden, name, x64, fusion):
+  spec, _, _, get = cases.CASES[name]
+  x1, x2 = cases.make_inputs(name)
+  nt.config.update('enable_x64', x64)
+  nt.config.update('disable_fusion', not fusion)
+  _, _, kernel_fn = cases.build(spec, nt.stax)
+  out = kernel_fn(x1, x2, get)
+  assert out._fields == tuple(get)
+  for f in get:
+    v = getattr(out, f)
+    assert v.dtype == (np.float64 if x64 else np.float32)
+    _compare(v, golden[f'{name}/{f}'], x64, x2 is None)
+
+
+@pytest.mark.parametrize('x64', [False, True])
+@pytest.mark.parametrize('name', [n for n, c in cases.CASES.items() if c[3] is None])
+def test_golden_full_kernel_layout(nt, golden, name, x64):
+  """get=None returns a `Kernel` in the reference's zipped / is_reversed layout (F4)."""
+  spec, _, _, _ = cases.CASES[name]
+  x1, x2 = cases.make_inputs(name)
+  nt.config.update('enable_x64', x64)
+  _, _, kernel_fn = cases.build(spec, nt.stax)
+  k = kernel_fn(x1, x2)
+  assert isinstance(k, nt.Kernel)
+  assert k.is_reversed == bool(golden[f'{name}/is_reversed'])
+  assert k.is_gaussian == bool(golden[f'{name}/is_gaussian'])
+  assert tuple(k.shape1) == tuple(golden[f'{name}/shape1'])
+  assert tuple(k.shape2) == tuple(golden[f'{name}/shape2'])
+  for f in ('nngp', 'ntk', 'cov1', 'cov2'):
+    key = f'{name}/{f}'
+    v = getattr(k, f)
+    if key not in golden.files:
+      assert v is None
+    else:
+      np.testing.assert_allclose(v, golden[key], rtol=RTOL[x64], atol=RTOL[x64] * 1e-3)
+
+
+@pytest.mark.parametrize('x64', [False, True])
+def test_composition_identity(nt, x64):
+  """tests/stax/stax_test.py:636-687: kernel_fn(kernel_fn(x)) == composed network."""
+  stax = nt.stax
+  nt.config.update('enable_x64', x64)
+  rng = np.random.default_rng(5)
+  x1 = rng.standard_normal((2, 4, 5, 2)).astype(np.float32)
+  x2 = rng.standard_normal((3, 4, 5, 2)).astype(np.float32)
+  a = stax.serial(stax.Conv(1, (3, 3), padding='SAME', W_std=1.2, b_std=0.1), stax.Relu())
+  b = stax.serial(stax.Conv(1, (2, 2), W_std=1.0, b_std=0.3), stax.Relu(), stax.GlobalAvgPool(),
+                  stax.Dense(1, 1.1, 0.2))
+  ab = stax.serial(a, b)
+  k_mid = a[2](x1, x2)
+  assert k_mid.is_reversed and k_mid.nngp.shape == (2, 3, 5, 5, 4, 4)
+  two = b[2](k_mid)
+  one = ab[2](x1, x2)
+  tol = 1e-12 if x64 else 1e-5
+  np.testing.assert_allclose(two.nngp, one.nngp, rtol=tol)
+  np.testing.assert_allclose(two.ntk, one.ntk, rtol=tol)
+  np.testing.assert_allclose(two.cov1, one.cov1, rtol=tol)
+  assert two.shape1 == one.shape1 == (2, 1)
+  # get on a Kernel input
+  np.testing.assert_allclose(b[2](k_mid, get='ntk'), one.ntk, rtol=tol)
+
+
+def test_oracle_parity_other_seeds(nt):
+  """CUDA vs oracle on fresh seeds and ragged block shapes (n1 != n2, odd counts)."""
+  from oracle import ntk_oracle as O
+  spec = cases.myrtle(7, 'gap')
+  x1 = np.random.default_rng(11).standard_normal((3, 32, 32, 3)).astype(np.float32)
+  x2 = np.random.default_rng(12).standard_normal((5, 32, 32, 3)).astype(np.float32)
+  ref = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'))
+  _, _, kernel_fn = cases.build(spec, nt.stax)
+  for x64 in (False, True):
+    nt.config.update('enable_x64', x64)
+    out = kernel_fn(x1, x2, ('nngp', 'ntk'))
+    np.testing.assert_allclose(out.nngp, ref[0], rtol=RTOL[x64])
+    np.testing.assert_allclose(out.ntk, ref[1], rtol=RTOL[x64])
+    only = kernel_fn(x1, x2, 'nngp')                       # nngp-only call skips the ntk work
+    np.testing.assert_allclose(only, ref[0], rtol=RTOL[x64])
+
+
+def test_symmetry_and_x2_none_equivalence(nt):
+  """kernel_fn(x, None) == kernel_fn(x, x) and is symmetric (size-independent property)."""
+  nt.config.update('enable_x64', False)
+  _, _, kernel_fn = cases.build(cases.myrtle(5), nt.stax)
+  x = np.random.default_rng(21).standard_normal((6, 32, 32, 3)).astype(np.float32)
+  a = kernel_fn(x, None, ('nngp', 'ntk'))
+  b = kernel_fn(x, x.copy(), ('nngp', 'ntk'))
+  np.testing.assert_allclose(a.nngp, b.nngp, rtol=1e-6)
+  np.testing.assert_allclose(a.ntk, b.ntk, rtol=1e-6)
+  np.testing.assert_allclose(a.nngp, a.nngp.T, rtol=1e-5)
+  np.testing.assert_allclose(a.ntk, a.ntk.T, rtol=1e-5)
+
+
+def test_batch_equals_unbatched(nt):
+  """tests/batching_test.py:160-284: batched == unbatched, incl. divisibility errors."""
+  nt.config.update('enable_x64', False)
+  _, _, kernel_fn = cases.build(cases.CASES['conv_pool_stride'][0], nt.stax)
+  x1 = np.random.default_rng(31).standard_normal((8, 8, 8, 3)).astype(np.float32)
+  x2 = np.random.default_rng(32).standard_normal((4, 8, 8, 3)).astype(np.float32)
+  full = kernel_fn(x1, x2, ('nngp', 'ntk'))
+  for bs in (2, 4):
+    b = nt.batch(kernel_fn, batch_size=bs, device_count=0)
+    out = b(x1, x2, ('nngp', 'ntk'))
+    np.testing.assert_allclose(out.nngp, full.nngp, rtol=1e-6)
+    np.testing.assert_allclose(out.ntk, full.ntk, rtol=1e-6)
+  with pytest.raises(ValueError, match='must divide batch size'):
+    nt.batch(kernel_fn, batch_size=3, device_count=0)(x1[:7], x2[:3], 'nngp')
+  # Kernel outputs through the Python block loop (cov1/cov2 stitched, cov2 None for x2=None)
+  _, _, kf_sp = cases.build(('serial', [cases.conv(), cases.RELU]), nt.stax)
+  k_full = kf_sp(x1, None)
+  k_b = nt.batch(kf_sp, batch_size=4, device_count=0)(x1, None)
+  assert k_b.cov2 is None and k_b.shape1 == k_full.shape1
+  np.testing.assert_allclose(k_b.nngp, k_full.nngp, rtol=1e-6)
+  np.testing.assert_allclose(k_b.cov1, k_full.cov1, rtol=1e-6)
+
+
+def test_internal_tiling_small_workspace(nt):
+  """The executor tiles the pair grid to fit its workspace; results do not depend on it."""
+  from neural_tangents_b200 import _lib, stax
+  nt.config.update('enable_x64', False)
+  spec = cases.CASES['conv_pool_stride'][0]
+  _, _, kernel_fn = cases.build(spec, nt.stax)
+  x1 = np.random.default_rng(41).standard_normal((7, 8, 8, 3)).astype(np.float32)
+  x2 = np.random.default_rng(42).standard_normal((5, 8, 8, 3)).astype(np.float32)
+  full = kernel_fn(x1, x2, ('nngp', 'ntk'))
+  low = stax._lowered(stax._strip(kernel_fn._spec), False, False, True)
+  small = _lib.Context(0, 2 << 20)   # 2 MiB: forces several tiles on the per-layer path
+  res = _lib.gram_host(small, low.program, x1, x2, 8, 8, 3, _lib.FLAG_NO_FUSION, 0, 0, True, False)
+  np.testing.assert_allclose(res['nngp'], full.nngp, rtol=1e-6)
+  np.testing.assert_allclose(res['ntk'], full.ntk, rtol=1e-6)
+  small.close()
+
+
+def test_reference_errors_on_gpu(nt):
+  stax = nt.stax
+  x = np.random.default_rng(0).standard_normal((2, 4, 4, 2)).astype(np.float32)
+  with pytest.raises(ValueError, match='must be Gaussian'):
+    stax.serial(stax.Relu())[2](x, None, 'nngp')
+  bad = stax.serial(stax.Conv(1, (3, 3), padding='SAME'), stax.FanOut(2),
+                    stax.parallel(stax.Relu(), stax.Identity()), stax.FanInSum())
+  with pytest.raises(NotImplementedError, match='FanInSum'):      # branching.py:77-85
+    bad[2](x, None, 'nngp')
+  mism = stax.serial(stax.Conv(1, (3, 3), padding='SAME'), stax.FanOut(2),
+                     stax.parallel(stax.Conv(1, (3, 3), padding='VALID'), stax.Identity()),
+                     stax.FanInSum())
+  with pytest.raises(ValueError, match='shapes should be equal'):  # branching.py:71-75
+    mism[2](x, None, 'nngp')
