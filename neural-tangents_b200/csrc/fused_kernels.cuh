@@ -1,29 +1,988 @@
-// Fused diagonal-marching fast path (placeholder until the kernels land).
+// Fused "diagonal-marching" kernels: the B200 fast path for stacks of
+//   [Conv 3x3 / stride 1 / SAME  ->  ABRelu] x L   (+ AvgPool 2x2/2 | GlobalAvgPool)
+// (the Myrtle configurations of BASELINE.json).  Math: SURVEY.md Appendix A,
+// reference rules `_src/stax/linear.py:3341-3378` (Conv), `_src/stax/elementwise.py:444-455`
+// (ABRelu), `_src/stax/linear.py:3499-3572` (AvgPool), `:1771-1801` (GlobalAvgPool).
+//
+// Key facts exploited
+//  * Every tap of the covariance-space conv moves BOTH members of a pixel pair by the
+//    same offset, so (dh, dw) = (h'-h, w'-w) is invariant: the [h,h',w,w'] tensor of one
+//    sample pair is a stack of independent 2-D images, each box-filtered 3x3.
+//  * "Circular shear" layout: element (h,h',w,w') lives at [ch][h][w][cw] with
+//    ch = (h'-h) mod S, cw = (w'-w) mod S.  It is dense (S^4 elements), the innermost
+//    index is contiguous, and every conv tap is a pure (h,w) shift at fixed (ch,cw).
+//    Zero padding becomes a per-link 0/1 mask (a link is cut where h' or w' wraps).
+//  * A thread owns WPT consecutive w at fixed (ch,cw): the w-direction taps are
+//    register-local (one shuffle pair per row for the block halo), the h-direction taps
+//    are a 2-row sliding window in registers while the thread group marches over h.
+//    L layers are software-pipelined with one row of lag each, so L Conv+ABRelu layers
+//    cost ZERO HBM traffic; only the pooled (16x smaller) tensor is written.
+//  * The first stage computes the input covariance K0 = x1.x2/C on the fly from the
+//    two samples held in shared memory (K = C = 3 outer product; nothing materialised).
+//
+// HBM traffic per pair for Myrtle-10/fp32: 2 x 512 KB + 2 x 32 KB written+read, vs the
+// 36.9 MB "one round trip per layer" model used for the roofline.
 #pragma once
+
+#include <type_traits>
 
 #include "common.cuh"
 #include "generic_kernels.cuh"
 
 namespace ntk {
 
-struct FusedPlan {
-  bool ok = false;
+constexpr int kMaxFusedLayers = 3;
+
+enum { IN_FROM_X = 0, IN_LOAD = 1 };
+enum { EPI_STORE = 0, EPI_POOL = 1, EPI_GAP = 2 };
+
+// Per-layer constants, already multiplied by the scale of the NEXT conv (alpha = W^2/9),
+// so the box filter itself is a plain sum.
+template <typename T>
+struct FLayer {
+  T coef;     // alpha_next * (a-b)^2 / (2 pi)
+  T half_ab;  // alpha_next * (a^2+b^2) / 2
+  T bias;     // b_std^2 of this layer's conv
 };
 
-inline FusedPlan plan_fused(const std::vector<ntk_op_t>&, int, int) { return FusedPlan(); }
-
 template <typename T>
-bool fused_supported(const FusedPlan&, int, int, int) {
-  return false;
+struct StageArgs {
+  const T* x1;    // FROM_X: [n1, S, S, C]
+  const T* x2;    // FROM_X: [n2, S, S, C]
+  const T* inK;   // LOAD: sheared [P, S, S, S, S]
+  const T* inT;
+  T* outK;        // STORE: sheared [P,S^4]; POOL: sheared [P,(S/2)^4] (pre-zeroed); GAP: [P]
+  T* outT;
+  const T* qm1;   // [n1][L][S][S][2]  (q, 1/sqrt(q)) per fused layer
+  const T* qm2;   // [n2][L][S][S][2]
+  long long P;
+  int n2;         // pair p -> (p / n2, p % n2), or (p, p) when self
+  int self;
+  T in_scale;     // FROM_X: alpha_1 / C folded into x1
+  T epi_scale;    // POOL: alpha_next/16; GAP: 1/S^4; STORE: unused (folded in coef)
+  FLayer<T> lp[kMaxFusedLayers];
+};
+
+// ---------------------------------------------------------------------------------------
+// arithmetic shared by the stage kernel and the q-map kernels (identical rounding, so a
+// duplicate pair x1[i] == x2[j] sees q1*q2 - K^2 == 0 exactly; SURVEY §7 "FP32 accuracy").
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+
+// R = P0 + mL*Pm + mR*Pp
+template <typename T>
+__device__ __forceinline__ T hsum3(T Pm, T P0, T Pp, T mL, T mR) {
+  return fma_t(mR, Pp, fma_t(mL, Pm, P0));
+}
+// C = R0 + vU*Ru + vD*Rd + bias
+template <typename T>
+__device__ __forceinline__ T vsum3(T Ru, T R0, T Rd, T vU, T vD, T bias) {
+  return add_rn(fma_t(vD, Rd, fma_t(vU, Ru, R0)), bias);
+}
+
+__device__ __forceinline__ float sqrt_fast(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rsqrt_t(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double rsqrt_t(double x) { return 1.0 / sqrt(x); }
+
+// acos(c)/sqrt(1-c^2) on [0,1], degree-8 fit (max abs error 1.0e-7 before rounding).
+__device__ __forceinline__ float acos_over_sin(float c) {
+  float g = 0.017638931050896645f;
+  g = __fmaf_rn(g, c, -0.09791343659162521f);
+  g = __fmaf_rn(g, c, 0.2531546652317047f);
+  g = __fmaf_rn(g, c, -0.42450031638145447f);
+  g = __fmaf_rn(g, c, 0.5569935441017151f);
+  g = __fmaf_rn(g, c, -0.6610828042030334f);
+  g = __fmaf_rn(g, c, 0.7848954796791077f);
+  g = __fmaf_rn(g, c, -0.9999822378158569f);
+  g = __fmaf_rn(g, c, 1.570796251296997f);
+  return g;
+}
+
+// ABRelu on one element (elementwise.py:444-455), constants pre-scaled by alpha_next.
+//   s = sqrt(max(q1 q2 - K^2, 0)); theta = atan2(s, K);
+//   kd = half_ab - coef*theta;  K' = coef*s + kd*K;  T' = kd*T
+// fp32: theta = sin(theta) * G(|cos theta|) with sin/cos from the stored 1/sqrt(q) maps:
+// one MUFU (sqrt) per element, no division, no atan2.
+__device__ __forceinline__ void act_point(float K, float Tn, float q1, float b1, float q2, float b2,
+                                          float coef, float half_ab, float& Ko, float& To) {
+  const float p = __fmul_rn(q1, q2);
+  const float rb = __fmul_rn(b1, b2);
+  const float s = sqrt_fast(fmaxf(__fsub_rn(p, __fmul_rn(K, K)), 0.f));
+  const float sn = __fmul_rn(s, rb);
+  const float c = __fmul_rn(K, rb);
+  const float th = __fmul_rn(sn, acos_over_sin(fminf(fabsf(c), 1.f)));
+  const float theta = c < 0.f ? __fsub_rn(3.14159265358979323846f, th) : th;
+  const float kd = __fmaf_rn(-coef, theta, half_ab);
+  Ko = __fmaf_rn(kd, K, __fmul_rn(coef, s));
+  To = __fmul_rn(kd, Tn);
+}
+
+__device__ __forceinline__ void act_point(double K, double Tn, double q1, double b1, double q2,
+                                          double b2, double coef, double half_ab, double& Ko,
+                                          double& To) {
+  (void)b1;
+  (void)b2;
+  const double p = __dmul_rn(q1, q2);
+  const double s = sqrt(fmax(__dsub_rn(p, __dmul_rn(K, K)), 0.0));
+  const double theta = (s == 0.0 && K == 0.0) ? 1.5707963267948966 : atan2(s, K);
+  const double kd = __fma_rn(-coef, theta, half_ab);
+  Ko = __fma_rn(kd, K, __dmul_rn(coef, s));
+  To = __dmul_rn(kd, Tn);
 }
 
 template <typename T>
-int fused_gram(const FusedPlan&, Arena&, cudaStream_t, int64_t*, const T*, int, const T*, int, bool,
-               int, int, int, bool, T*, T*, long long) {
-  return fail(NTK_EUNSUPPORTED, "fused path not built");
+struct Vec2;
+template <>
+struct Vec2<float> {
+  using type = float2;
+};
+template <>
+struct Vec2<double> {
+  using type = double2;
+};
+
+// ---------------------------------------------------------------------------------------
+// q-maps: the per-sample diagonal variances q^l[h,w] = cov^l[h,h,w,w] of every fused layer
+// (requirements.py:1057-1117) and their reciprocal square roots.  Between pools the
+// diagonal image (ch = cw = 0) evolves on its own: conv -> box filter with border-only
+// cuts; ABRelu on the diagonal is q -> (a^2+b^2)/2 q.  One CTA per sample.
+//   src_mode 0: diag0[h,w] = in_scale * sum_c x[h,w,c]^2      (FROM_X stages)
+//   src_mode 1: diag0[h,w] = selfK[n][ch=0][h][w][cw=0]        (sheared self-pair tensor)
+// ---------------------------------------------------------------------------------------
+template <typename T, int S>
+__global__ void k_qmaps(const T* __restrict__ src, int src_mode, int C, T in_scale, int L,
+                        FLayer<T> l0, FLayer<T> l1, FLayer<T> l2, T* __restrict__ qm) {
+  __shared__ T P[S * S];
+  __shared__ T R[S * S];
+  const int n = blockIdx.x;
+  const FLayer<T> lp[3] = {l0, l1, l2};
+  for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+    const int h = e / S, w = e % S;
+    T v;
+    if (src_mode == 0) {
+      const T* x = src + ((long long)n * S * S + e) * C;
+      v = mul_rn(mul_rn(x[0], in_scale), x[0]);
+      for (int c = 1; c < C; ++c) v = fma_t(mul_rn(x[c], in_scale), x[c], v);
+    } else {
+      v = src[(((long long)n * S + 0) * S + h) * S * S + (long long)w * S + 0];
+    }
+    P[e] = v;
+  }
+  __syncthreads();
+  typename Vec2<T>::type* out = reinterpret_cast<typename Vec2<T>::type*>(qm) + (long long)n * L * S * S;
+  for (int l = 0; l < L; ++l) {
+    for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+      const int h = e / S, w = e % S;
+      const T mL = w > 0 ? (T)1 : (T)0, mR = w < S - 1 ? (T)1 : (T)0;
+      R[e] = hsum3<T>(P[h * S + (w > 0 ? w - 1 : w)], P[e], P[h * S + (w < S - 1 ? w + 1 : w)], mL, mR);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+      const int h = e / S, w = e % S;
+      const T vU = h > 0 ? (T)1 : (T)0, vD = h < S - 1 ? (T)1 : (T)0;
+      const T q = vsum3<T>(R[(h > 0 ? h - 1 : h) * S + w], R[e], R[(h < S - 1 ? h + 1 : h) * S + w], vU,
+                           vD, lp[l].bias);
+      typename Vec2<T>::type o;
+      o.x = q;
+      o.y = q > (T)0 ? rsqrt_t(q) : (T)0;
+      out[(long long)l * S * S + e] = o;
+      P[e] = mul_rn(lp[l].half_ab, q);  // ABRelu on the diagonal: theta = 0
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// The stage kernel.
+//   S    spatial size (32, 16, 8);  WPT  consecutive w per thread;  L fused layers (1..3)
+//   CIN  input channels for FROM_X (x2 is padded to 4 in shared memory)
+// A *group* of TPP = S*S/WPT threads owns one sample pair and marches over its S*S rows
+// (ch-major: row r = ch*S + h).  NT threads per CTA hold NT/TPP groups.
+// ---------------------------------------------------------------------------------------
+template <int S, int WPT>
+struct StageGeom {
+  static constexpr int TPP = S * S / WPT;               // threads per plane == per group
+  static constexpr int NT = TPP < 128 ? 128 : TPP;      // threads per CTA
+  static constexpr int GROUPS = NT / TPP;
+  static constexpr int LPG = TPP < 32 ? TPP : 32;       // lanes of one group inside a warp
+  static constexpr int NWB = S / WPT;                   // w-blocks
+  static constexpr int LW = LPG / NWB;                  // cw lanes per w-block inside a warp
+  static constexpr int NR = S * S;                      // rows per pair
+};
+
+template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN>
+__global__ void __launch_bounds__(StageGeom<S, WPT>::NT)
+k_stage(const StageArgs<T> a) {
+  using G = StageGeom<S, WPT>;
+  using V2 = typename Vec2<T>::type;
+  constexpr int TPP = G::TPP, LPG = G::LPG, NWB = G::NWB, LW = G::LW, NR = G::NR;
+  constexpr int SO = S / 2;
+  constexpr int SP = S + 1;  // padded staging row
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // per-group shared memory carve-up
+  constexpr int XS1 = IN == IN_FROM_X ? S * S * CIN : 0;
+  constexpr int XS2 = IN == IN_FROM_X ? S * S * 4 : 0;
+  constexpr int QM = L * S * S * 2;
+  constexpr int STG = EPI == EPI_POOL ? 2 * (NTK ? 2 : 1) * S * SP : 0;
+  constexpr int PER_GROUP = XS1 + XS2 + 2 * QM + STG;
+  const int tid = threadIdx.x;
+  const int grp = tid / TPP, tg = tid % TPP;
+  T* sm = reinterpret_cast<T*>(smem_raw) + (size_t)grp * PER_GROUP;
+  T* x1s = sm;
+  T* x2s = x1s + XS1;
+  V2* q1m = reinterpret_cast<V2*>(x2s + XS2);
+  V2* q2m = q1m + L * S * S;
+  T* stg = reinterpret_cast<T*>(q2m + L * S * S);
+
+  const int lig = tg % LPG, wig = tg / 32;
+  const int wblk = lig / LW, cwsub = lig % LW;
+  const int cw = wig * LW + cwsub;
+  const int w0 = wblk * WPT;
+
+  long long p = (long long)blockIdx.x * G::GROUPS + grp;
+  const bool live = p < a.P;
+  if (!live) p = a.P - 1;
+  int si, sj;
+  if (a.self) {
+    si = sj = (int)p;
+  } else {
+    si = (int)(p / a.n2);
+    sj = (int)(p % a.n2);
+  }
+
+  // ---- stage the two samples and their q-maps in shared memory -------------------------
+  if (IN == IN_FROM_X) {
+    const T* g1 = a.x1 + (long long)si * S * S * CIN;
+    const T* g2 = a.x2 + (long long)sj * S * S * CIN;
+    for (int e = tg; e < S * S * CIN; e += TPP) x1s[e] = mul_rn(g1[e], a.in_scale);
+    for (int e = tg; e < S * S; e += TPP) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) x2s[e * 4 + c] = c < CIN ? g2[e * CIN + c] : (T)0;
+    }
+  }
+  {
+    const V2* g1 = reinterpret_cast<const V2*>(a.qm1) + (long long)si * L * S * S;
+    const V2* g2 = reinterpret_cast<const V2*>(a.qm2) + (long long)sj * L * S * S;
+    for (int e = tg; e < L * S * S; e += TPP) {
+      q1m[e] = g1[e];
+      q2m[e] = g2[e];
+    }
+  }
+  if (TPP > 32)
+    __syncthreads();
+  else
+    __syncwarp();
+
+  // ---- per-thread constants -------------------------------------------------------------
+  // lk[i]: link between w0+i-1 and w0+i is intact (both inside the image, w' does not wrap)
+  T lk[WPT + 1];
+#pragma unroll
+  for (int i = 0; i <= WPT; ++i) {
+    const int wl = w0 + i - 1, wr = w0 + i;
+    lk[i] = (wl >= 0 && wr <= S - 1 && ((wl + cw) % S) != S - 1) ? (T)1 : (T)0;
+  }
+
+  // sliding windows: RK[l][slot][i] = horizontally summed input row of layer l
+  T RK[L][2][WPT];
+  T RT[L][2][WPT];
+#pragma unroll
+  for (int l = 0; l < L; ++l)
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int i = 0; i < WPT; ++i) {
+        RK[l][s][i] = (T)0;
+        RT[l][s][i] = (T)0;
+      }
+
+  T gap_k = (T)0, gap_t = (T)0;
+  const T* inK = IN == IN_LOAD ? a.inK + p * (long long)NR * S * S : nullptr;
+  const T* inT = (IN == IN_LOAD && NTK) ? a.inT + p * (long long)NR * S * S : nullptr;
+
+  // next input row (software prefetch for LOAD)
+  T nK[WPT], nT[WPT];
+  auto fetch = [&](int r) {
+    if (IN == IN_LOAD) {
+      if (r < NR) {
+        const long long base = (long long)r * S * S + (long long)w0 * S + cw;
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) {
+          nK[i] = __ldg(inK + base + (long long)i * S);
+          if (NTK) nT[i] = __ldg(inT + base + (long long)i * S);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) {
+          nK[i] = (T)0;
+          nT[i] = (T)0;
+        }
+      }
+    }
+  };
+  fetch(0);
+
+  auto step = [&](const int t, auto par_c) {
+    // `par` = t & 1 as a compile-time constant: the ring slot of each layer alternates.
+    constexpr int par = decltype(par_c)::value;
+    T PK[WPT], PT[WPT];
+    // ---- input row r = t of layer 1 ----------------------------------------------------
+    {
+      const int r = t;
+      if (IN == IN_FROM_X) {
+        if (r < NR) {
+          const int ch = r / S, h = r % S;
+          const int h2 = (h + ch) % S;
+#pragma unroll
+          for (int i = 0; i < WPT; ++i) {
+            const int w = w0 + i, w2 = (w + cw) % S;
+            const T* xa = x1s + (h * S + w) * CIN;
+            const T* xb = x2s + (h2 * S + w2) * 4;
+            T acc = mul_rn(xa[0], xb[0]);
+#pragma unroll
+            for (int c = 1; c < CIN; ++c) acc = fma_t(xa[c], xb[c], acc);
+            PK[i] = acc;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < WPT; ++i) PK[i] = (T)0;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) {
+          PK[i] = nK[i];
+          PT[i] = nT[i];
+        }
+        fetch(r + 1);
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      const int r_in = t - l;  // row of layer-l input now in PK/PT
+      const int slot = (par + l) & 1;  // == r_in & 1 (compile-time)
+      const bool has_t = NTK && (l > 0 || IN == IN_LOAD);
+      if (r_in >= 0 && r_in <= NR) {  // uniform: pipeline fill / drain
+        // ---- horizontal 3-tap (register-local + one halo shuffle pair) -----------------
+        T Rk[WPT], Rt[WPT];
+        {
+          T left = (T)0, right = (T)0, leftT = (T)0, rightT = (T)0;
+          if (NWB > 1) {
+            left = __shfl_up_sync(0xffffffffu, PK[WPT - 1], LW);
+            right = __shfl_down_sync(0xffffffffu, PK[0], LW);
+            if (has_t) {
+              leftT = __shfl_up_sync(0xffffffffu, PT[WPT - 1], LW);
+              rightT = __shfl_down_sync(0xffffffffu, PT[0], LW);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < WPT; ++i) {
+            Rk[i] = hsum3<T>(i == 0 ? left : PK[i == 0 ? 0 : i - 1], PK[i],
+                             i == WPT - 1 ? right : PK[i == WPT - 1 ? i : i + 1], lk[i], lk[i + 1]);
+            if (has_t)
+              Rt[i] = hsum3<T>(i == 0 ? leftT : PT[i == 0 ? 0 : i - 1], PT[i],
+                               i == WPT - 1 ? rightT : PT[i == WPT - 1 ? i : i + 1], lk[i], lk[i + 1]);
+          }
+        }
+        // ---- vertical 3-tap: emit conv row r_out = r_in - 1 ------------------------------
+        const int r_out = r_in - 1;
+        if (r_out >= 0) {
+          const int ch = r_out / S, h = r_out % S;
+          const int h2 = (h + ch) % S;
+          const T vU = (h > 0 && h2 != 0) ? (T)1 : (T)0;
+          const T vD = (h < S - 1 && h2 != S - 1) ? (T)1 : (T)0;
+          const V2* q1r = q1m + (l * S + h) * S + w0;
+          const V2* q2r = q2m + (l * S + h2) * S;
+          const T coef = a.lp[l].coef, half_ab = a.lp[l].half_ab, bias = a.lp[l].bias;
+#pragma unroll
+          for (int i = 0; i < WPT; ++i) {
+            const T ck = vsum3<T>(RK[l][slot][i], RK[l][slot ^ 1][i], Rk[i], vU, vD, bias);
+            T ct = (T)0;
+            if (NTK) {
+              // linear.py:1396-1398 (T0 == 0 for the first layer of a FROM_X stage)
+              ct = has_t ? add_rn(fma_t(vD, Rt[i], fma_t(vU, RT[l][slot][i], RT[l][slot ^ 1][i])), ck)
+                         : ck;
+            }
+            const V2 qa = q1r[i];
+            const V2 qb = q2r[(w0 + i + cw) % S];
+            act_point(ck, ct, qa.x, qa.y, qb.x, qb.y, coef, half_ab, PK[i], PT[i]);
+          }
+        }
+        // ---- rotate the window: the new row replaces the oldest one ---------------------
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) {
+          RK[l][slot][i] = Rk[i];
+          if (has_t) RT[l][slot][i] = Rt[i];
+        }
+      } else if (r_in > NR) {  // this layer has drained: feed a zero row downstream
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) {
+          PK[i] = (T)0;
+          PT[i] = (T)0;
+        }
+      }
+    }
+    // ---- epilogue on the finished row r_fin = t - L -----------------------------------------
+    const int r_fin = t - L;
+    if (r_fin >= 0 && r_fin < NR) {
+      const int ch = r_fin / S, h = r_fin % S;
+      if (EPI == EPI_STORE) {
+        if (live) {
+          const long long base = (p * NR + r_fin) * (long long)(S * S) + (long long)w0 * S + cw;
+#pragma unroll
+          for (int i = 0; i < WPT; ++i) {
+            a.outK[base + (long long)i * S] = PK[i];
+            if (NTK) a.outT[base + (long long)i * S] = PT[i];
+          }
+        }
+      } else if (EPI == EPI_GAP) {
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) {
+          gap_k = add_rn(gap_k, PK[i]);
+          if (NTK) gap_t = add_rn(gap_t, PT[i]);
+        }
+      } else {  // EPI_POOL: AvgPool 2x2/2 of both members (linear.py:3499-3572)
+        T* sK = stg + (r_fin & 1) * ((NTK ? 2 : 1) * S * SP);
+        T* sT = sK + S * SP;
+#pragma unroll
+        for (int i = 0; i < WPT; ++i) {
+          sK[(w0 + i) * SP + cw] = PK[i];
+          if (NTK) sT[(w0 + i) * SP + cw] = PT[i];
+        }
+        if (TPP > 32)
+          __syncthreads();
+        else
+          __syncwarp();
+        // this row feeds pooled row a = h/2 of column Ch (see DESIGN.md "pooling in the shear")
+        const int ii = h & 1;
+        int Ch;
+        if ((ch & 1) == 0)
+          Ch = ch >> 1;
+        else
+          Ch = (ii == 0 ? (ch - 1) >> 1 : ((ch + 1) >> 1) % SO);
+        const long long obase = ((p * SO + Ch) * SO + (h >> 1)) * (long long)(SO * SO);
+#pragma unroll
+        for (int k = 0; k < (SO * SO) / TPP; ++k) {
+          const int o = tg + k * TPP;
+          const int b = o / SO, Cw = o % SO;
+          const int c0 = 2 * Cw, c1 = (2 * Cw + 1) % S, cm = (2 * Cw + S - 1) % S;
+          const T* r0 = sK + (2 * b) * SP;
+          const T* r1 = sK + (2 * b + 1) * SP;
+          T v = add_rn(add_rn(r0[c0], r1[c0]), add_rn(r0[c1], r1[cm]));
+          if (live) atomicAdd(a.outK + obase + o, mul_rn(v, a.epi_scale));
+          if (NTK) {
+            const T* t0 = sT + (2 * b) * SP;
+            const T* t1 = sT + (2 * b + 1) * SP;
+            T u = add_rn(add_rn(t0[c0], t1[c0]), add_rn(t0[c1], t1[cm]));
+            if (live) atomicAdd(a.outT + obase + o, mul_rn(u, a.epi_scale));
+          }
+        }
+      }
+    }
+  };
+
+  constexpr int NSTEPS = NR + L;
+  for (int t0 = 0; t0 < NSTEPS; t0 += 2) {
+    step(t0, std::integral_constant<int, 0>{});
+    step(t0 + 1, std::integral_constant<int, 1>{});
+  }
+
+  if (EPI == EPI_GAP) {
+    // deterministic group reduction: lanes of the group inside each warp, then warps
+    T vk = gap_k, vt = gap_t;
+#pragma unroll
+    for (int o = LPG / 2; o > 0; o >>= 1) {
+      vk = add_rn(vk, __shfl_down_sync(0xffffffffu, vk, o));
+      if (NTK) vt = add_rn(vt, __shfl_down_sync(0xffffffffu, vt, o));
+    }
+    if (TPP > 32) {
+      __shared__ T red[2][G::NT / 32];
+      if ((tid & 31) == 0) {
+        red[0][tid >> 5] = vk;
+        red[1][tid >> 5] = vt;
+      }
+      __syncthreads();
+      if (tg == 0) {
+        T sk = (T)0, st = (T)0;
+        for (int w = 0; w < TPP / 32; ++w) {
+          sk = add_rn(sk, red[0][grp * (TPP / 32) + w]);
+          st = add_rn(st, red[1][grp * (TPP / 32) + w]);
+        }
+        vk = sk;
+        vt = st;
+      }
+    }
+    if (tg == 0 && live) {
+      a.outK[p] = mul_rn(vk, a.epi_scale);
+      if (NTK) a.outT[p] = mul_rn(vt, a.epi_scale);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// sheared <-> canonical layout conversion (only when a fused segment meets the general path)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_shear(const T* __restrict__ in, T* __restrict__ out, long long P, int S, int to_shear) {
+  const long long per = (long long)S * S * S * S;
+  const long long total = P * per;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long p = idx / per;
+    int r = (int)(idx % per);
+    // idx enumerates the sheared tensor [ch][h][w][cw]
+    int cw = r % S;
+    r /= S;
+    int w = r % S;
+    r /= S;
+    int h = r % S;
+    int ch = r / S;
+    int h2 = (h + ch) % S, w2 = (w + cw) % S;
+    long long can = p * per + (((long long)h * S + h2) * S + w) * S + w2;
+    if (to_shear)
+      out[idx] = in[can];
+    else
+      out[can] = in[idx];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side: plan + driver
+// ---------------------------------------------------------------------------------------
+struct FusedStage {
+  int L = 0;
+  double w2[kMaxFusedLayers], b2[kMaxFusedLayers], a[kMaxFusedLayers], b[kMaxFusedLayers];
+  int epi = EPI_STORE;  // what follows this chunk
+};
+
+struct FusedPlan {
+  bool ok = false;
+  std::vector<FusedStage> stages;    // chunks of <= 3 layers; resolution halves after EPI_POOL
+  std::vector<ntk_op_t> dense_tail;  // Dense ops applied to the [n1,n2] result
+};
+
+// Recognises:  ([Conv3x3/1/SAME, ABRelu]+  AvgPool2x2/2?)+  (AvgPool2x2/2)* (GAP | Flatten@1x1)  Dense*
+inline FusedPlan plan_fused(const std::vector<ntk_op_t>& ops, int n_slots, int out_slot) {
+  FusedPlan plan;
+  const int n = (int)ops.size();
+  // must be a linear chain ending in out_slot
+  for (int k = 0; k < n; ++k) {
+    if (ops[k].kind == NTK_OP_FANINSUM) return plan;
+    if (ops[k].src != (k == 0 ? 0 : ops[k - 1].dst)) return plan;
+  }
+  if (n == 0 || ops[n - 1].dst != out_slot) return plan;
+  auto is_conv = [](const ntk_op_t& o) {
+    return o.kind == NTK_OP_CONV && o.i[0] == 3 && o.i[1] == 3 && o.i[2] == 1 && o.i[3] == 1 &&
+           o.i[4] == NTK_PAD_SAME;
+  };
+  auto is_act = [](const ntk_op_t& o) { return o.kind == NTK_OP_ABRELU && o.i[0] == 0; };
+  auto is_pool = [](const ntk_op_t& o) {
+    return o.kind == NTK_OP_AVGPOOL && o.i[0] == 2 && o.i[1] == 2 && o.i[2] == 2 && o.i[3] == 2 &&
+           o.i[4] != NTK_PAD_CIRCULAR && !(o.i[4] == NTK_PAD_SAME && o.i[5]);
+  };
+  int k = 0;
+  int pending_pools = 0;  // pools seen after the last layer run
+  while (k < n) {
+    if (!(is_conv(ops[k]) && k + 1 < n && is_act(ops[k + 1]))) break;
+    if (!plan.stages.empty()) {
+      if (pending_pools > 1) return FusedPlan();
+      plan.stages.back().epi = pending_pools == 1 ? EPI_POOL : EPI_STORE;
+    }
+    // gather the run of conv+act layers and cut it into chunks of <= kMaxFusedLayers
+    std::vector<std::pair<int, int>> run;
+    while (k + 1 < n && is_conv(ops[k]) && is_act(ops[k + 1])) {
+      run.push_back({k, k + 1});
+      k += 2;
+    }
+    for (size_t s = 0; s < run.size(); s += kMaxFusedLayers) {
+      FusedStage st;
+      st.L = (int)std::min<size_t>(kMaxFusedLayers, run.size() - s);
+      for (int l = 0; l < st.L; ++l) {
+        const ntk_op_t& c = ops[run[s + l].first];
+        const ntk_op_t& act = ops[run[s + l].second];
+        st.w2[l] = c.f[0];
+        st.b2[l] = c.i[5] ? c.f[1] : 0.0;
+        st.a[l] = act.f[0];
+        st.b[l] = act.f[1];
+      }
+      st.epi = EPI_STORE;
+      plan.stages.push_back(st);
+    }
+    pending_pools = 0;
+    while (k < n && is_pool(ops[k])) {
+      ++pending_pools;
+      ++k;
+    }
+  }
+  if (plan.stages.empty() || k >= n) return FusedPlan();
+  if (ops[k].kind != NTK_OP_GAP && ops[k].kind != NTK_OP_FLATTEN) return FusedPlan();
+  // tail: `pending_pools` 2x2/2 pools then GAP (always a global mean) or Flatten (a global
+  // mean iff the pools reduced the map to 1x1 -- checked against S at run time).
+  plan.stages.back().epi = EPI_GAP;
+  const bool flatten = ops[k].kind == NTK_OP_FLATTEN;
+  ++k;
+  for (; k < n; ++k) {
+    if (ops[k].kind != NTK_OP_DENSE) return FusedPlan();
+    plan.dense_tail.push_back(ops[k]);
+  }
+  plan.ok = true;
+  // encode the tail requirement in an extra pseudo-stage field: L == 0 marker
+  FusedStage tail;
+  tail.L = 0;
+  tail.epi = flatten ? 1 : 0;
+  tail.w2[0] = (double)pending_pools;
+  plan.stages.push_back(tail);
+  return plan;
+}
+
+inline int fused_final_size(const FusedPlan& plan, int S) {
+  for (size_t s = 0; s + 1 < plan.stages.size(); ++s)
+    if (plan.stages[s].epi == EPI_POOL) S /= 2;
+  return S;
+}
+
+template <typename T>
+bool fused_supported(const FusedPlan& plan, int H, int W, int C) {
+  if (!plan.ok || H != W) return false;
+  if (H != 32 && H != 16 && H != 8) return false;
+  if (C != 3) return false;  // FROM_X stages are instantiated for RGB inputs
+  int S = H;
+  for (size_t s = 0; s + 1 < plan.stages.size(); ++s) {
+    if (plan.stages[s].epi == EPI_POOL) {
+      if (S <= 8) return false;  // S = 4 stages are not instantiated
+      S /= 2;
+    }
+  }
+  const FusedStage& tail = plan.stages.back();
+  const int pools = (int)tail.w2[0];
+  if (S % (1 << pools) != 0) return false;
+  if (tail.epi == 1 && (S >> pools) != 1) return false;  // Flatten needs a 1x1 map
+  return true;
+}
+
+template <typename T, int S>
+struct StageCfg {
+  // fp32: 8 w per thread (128-thread groups at S = 32); fp64: 4 (register pressure)
+  static constexpr int WPT = sizeof(T) == 4 ? 8 : 4;
+};
+
+template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN>
+size_t stage_smem_bytes() {
+  using G = StageGeom<S, WPT>;
+  const int xs1 = IN == IN_FROM_X ? S * S * CIN : 0;
+  const int xs2 = IN == IN_FROM_X ? S * S * 4 : 0;
+  const int qm = L * S * S * 2;
+  const int stg = EPI == EPI_POOL ? 2 * (NTK ? 2 : 1) * S * (S + 1) : 0;
+  return (size_t)G::GROUPS * (xs1 + xs2 + 2 * qm + stg) * sizeof(T);
+}
+
+template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN>
+int launch_stage_impl(cudaStream_t stream, int64_t* launches, const StageArgs<T>& a) {
+  using G = StageGeom<S, WPT>;
+  auto kern = k_stage<T, S, WPT, L, IN, EPI, NTK, CIN>;
+  const size_t smem = stage_smem_bytes<T, S, WPT, L, IN, EPI, NTK, CIN>();
+  static thread_local bool configured = false;
+  if (!configured) {
+    NTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const long long blocks = (a.P + G::GROUPS - 1) / G::GROUPS;
+  (*launches)++;
+  kern<<<(unsigned)blocks, G::NT, smem, stream>>>(a);
+  NTK_CUDA(cudaGetLastError());
+  return NTK_OK;
+}
+
+template <typename T, int S, int L, int IN, bool NTK, int CIN>
+int launch_stage_epi(cudaStream_t stream, int64_t* launches, int epi, const StageArgs<T>& a) {
+  constexpr int WPT = StageCfg<T, S>::WPT;
+  switch (epi) {
+    case EPI_STORE:
+      return launch_stage_impl<T, S, WPT, L, IN, EPI_STORE, NTK, CIN>(stream, launches, a);
+    case EPI_POOL:
+      return launch_stage_impl<T, S, WPT, L, IN, EPI_POOL, NTK, CIN>(stream, launches, a);
+    default:
+      return launch_stage_impl<T, S, WPT, L, IN, EPI_GAP, NTK, CIN>(stream, launches, a);
+  }
+}
+
+template <typename T, int S, int IN, bool NTK, int CIN>
+int launch_stage_L(cudaStream_t stream, int64_t* launches, int L, int epi, const StageArgs<T>& a) {
+  switch (L) {
+    case 1:
+      return launch_stage_epi<T, S, 1, IN, NTK, CIN>(stream, launches, epi, a);
+    case 2:
+      return launch_stage_epi<T, S, 2, IN, NTK, CIN>(stream, launches, epi, a);
+    default:
+      return launch_stage_epi<T, S, 3, IN, NTK, CIN>(stream, launches, epi, a);
+  }
+}
+
+template <typename T, bool NTK>
+int launch_stage(cudaStream_t stream, int64_t* launches, int S, int L, int from_x, int C, int epi,
+                 const StageArgs<T>& a) {
+  if (from_x) {
+    if (C != 3) return fail(NTK_EUNSUPPORTED, "fused FROM_X stages are instantiated for C == 3");
+    if (S == 32) return launch_stage_L<T, 32, IN_FROM_X, NTK, 3>(stream, launches, L, epi, a);
+    if (S == 16) return launch_stage_L<T, 16, IN_FROM_X, NTK, 3>(stream, launches, L, epi, a);
+    return launch_stage_L<T, 8, IN_FROM_X, NTK, 3>(stream, launches, L, epi, a);
+  }
+  if (S == 32) return launch_stage_L<T, 32, IN_LOAD, NTK, 1>(stream, launches, L, epi, a);
+  if (S == 16) return launch_stage_L<T, 16, IN_LOAD, NTK, 1>(stream, launches, L, epi, a);
+  return launch_stage_L<T, 8, IN_LOAD, NTK, 1>(stream, launches, L, epi, a);
+}
+
+template <typename T>
+int launch_qmaps(cudaStream_t stream, int64_t* launches, int S, const T* src, int src_mode, int n,
+                 int C, T in_scale, int L, const FLayer<T>* lp, T* qm) {
+  (*launches)++;
+  FLayer<T> z{(T)0, (T)0, (T)0};
+  FLayer<T> l0 = lp[0], l1 = L > 1 ? lp[1] : z, l2 = L > 2 ? lp[2] : z;
+  if (S == 32)
+    k_qmaps<T, 32><<<n, 256, 0, stream>>>(src, src_mode, C, in_scale, L, l0, l1, l2, qm);
+  else if (S == 16)
+    k_qmaps<T, 16><<<n, 256, 0, stream>>>(src, src_mode, C, in_scale, L, l0, l1, l2, qm);
+  else
+    k_qmaps<T, 8><<<n, 64, 0, stream>>>(src, src_mode, C, in_scale, L, l0, l1, l2, qm);
+  NTK_CUDA(cudaGetLastError());
+  return NTK_OK;
 }
 
 inline int fused_configure_device() { return NTK_OK; }
+
+// Per-stage layer constants: fold the NEXT conv's alpha = W^2/9 into this layer's ABRelu.
+template <typename T>
+void stage_constants(const FusedPlan& plan, size_t s, FLayer<T>* lp, double* next_alpha_out) {
+  const FusedStage& st = plan.stages[s];
+  const double two_pi = 2.0 * 3.14159265358979323846;
+  for (int l = 0; l < st.L; ++l) {
+    double alpha_next = 1.0;
+    if (l + 1 < st.L)
+      alpha_next = st.w2[l + 1] / 9.0;
+    else if (st.epi != EPI_GAP && s + 1 < plan.stages.size() && plan.stages[s + 1].L > 0)
+      alpha_next = plan.stages[s + 1].w2[0] / 9.0;
+    const double d = st.a[l] - st.b[l];
+    double coef = d * d / two_pi, half_ab = (st.a[l] * st.a[l] + st.b[l] * st.b[l]) / 2.0;
+    // the scale feeding a pooled boundary is applied by the pool epilogue instead
+    const bool via_epi = (l + 1 == st.L) && st.epi == EPI_POOL;
+    if (!via_epi) {
+      coef *= alpha_next;
+      half_ab *= alpha_next;
+    }
+    lp[l].coef = (T)coef;
+    lp[l].half_ab = (T)half_ab;
+    lp[l].bias = (T)st.b2[l];
+    if (l + 1 == st.L) *next_alpha_out = alpha_next;
+  }
+}
+
+// Whole Gram block through the fused stages.  x1/x2 are device pointers to all samples;
+// the pair grid is tiled so that the stage boundaries fit in the arena.
+template <typename T>
+int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t* launches,
+               const T* x1, int n1, const T* x2, int n2, bool symmetric, int S0, int /*W*/, int C,
+               bool want_ntk, T* out_nngp, T* out_ntk, long long ld) {
+  const size_t n_st = plan.stages.size() - 1;  // real stages (last entry is the tail marker)
+  // ---- 1. q-maps for every stage and both sample sets (self-pair pipeline) --------------
+  // qm[s][set]: [n][L][S][S][2]
+  std::vector<T*> qm1(n_st), qm2(n_st);
+  std::vector<int> Ss(n_st);
+  {
+    int S = S0;
+    for (size_t s = 0; s < n_st; ++s) {
+      Ss[s] = S;
+      if (plan.stages[s].epi == EPI_POOL) S /= 2;
+    }
+  }
+  for (size_t s = 0; s < n_st; ++s) {
+    const size_t per = (size_t)plan.stages[s].L * Ss[s] * Ss[s] * 2 * sizeof(T);
+    qm1[s] = (T*)arena.alloc(per * n1);
+    qm2[s] = symmetric ? qm1[s] : (T*)arena.alloc(per * n2);
+    if (!qm1[s] || !qm2[s]) return fail(NTK_ENOMEM, "workspace too small for the q-maps");
+  }
+  const double alpha0 = plan.stages[0].w2[0] / 9.0;
+  const T in_scale = (T)(alpha0 / (double)C);
+  for (int set = 0; set < (symmetric ? 1 : 2); ++set) {
+    const T* x = set == 0 ? x1 : x2;
+    const int n = set == 0 ? n1 : n2;
+    // self tensors are processed in chunks to bound the workspace
+    const int chunk = std::min(n, 512);
+    T* bufA = nullptr;
+    T* bufB = nullptr;
+    size_t cap = 0;
+    for (size_t s = 0; s < n_st; ++s) cap = std::max(cap, (size_t)Ss[s] * Ss[s] * Ss[s] * Ss[s]);
+    // only boundaries after stage 0 are materialised; the largest is at (S0/2 or S0)
+    size_t need = 0;
+    {
+      for (size_t s = 0; s + 1 < n_st; ++s) {
+        const int So = plan.stages[s].epi == EPI_POOL ? Ss[s] / 2 : Ss[s];
+        need = std::max(need, (size_t)So * So * So * So);
+      }
+    }
+    if (need > 0) {
+      bufA = (T*)arena.alloc(need * chunk * sizeof(T));
+      bufB = (T*)arena.alloc(need * chunk * sizeof(T));
+      if (!bufA || !bufB) return fail(NTK_ENOMEM, "workspace too small for the self-pair pipeline");
+    }
+    for (int c0 = 0; c0 < n; c0 += chunk) {
+      const int m = std::min(chunk, n - c0);
+      T* cur = nullptr;  // sheared self tensors entering stage s
+      for (size_t s = 0; s < n_st; ++s) {
+        FLayer<T> lp[kMaxFusedLayers];
+        double next_alpha = 1.0;
+        stage_constants<T>(plan, s, lp, &next_alpha);
+        T* qm = (set == 0 ? qm1[s] : qm2[s]) + (size_t)c0 * plan.stages[s].L * Ss[s] * Ss[s] * 2;
+        const int S = Ss[s];
+        if (s == 0)
+          NTK_TRY(launch_qmaps<T>(stream, launches, S, x + (size_t)c0 * S * S * C, 0, m, C, in_scale,
+                                  plan.stages[s].L, lp, qm));
+        else
+          NTK_TRY(launch_qmaps<T>(stream, launches, S, cur, 1, m, C, (T)1, plan.stages[s].L, lp, qm));
+        if (s + 1 == n_st) break;  // the last stage's self tensors are never needed
+        // run the stage on the self pairs (nngp only) to get the next boundary
+        StageArgs<T> a{};
+        a.x1 = a.x2 = x + (size_t)c0 * S * S * C;
+        a.inK = cur;
+        a.inT = nullptr;
+        T* nxt = (cur == bufA) ? bufB : bufA;
+        const int epi = plan.stages[s].epi;
+        const int So = epi == EPI_POOL ? S / 2 : S;
+        a.outK = nxt;
+        a.outT = nullptr;
+        a.qm1 = a.qm2 = qm;
+        a.P = m;
+        a.n2 = 1;
+        a.self = 1;
+        a.in_scale = in_scale;
+        a.epi_scale = (T)(next_alpha / 16.0);
+        for (int l = 0; l < plan.stages[s].L; ++l) a.lp[l] = lp[l];
+        if (epi == EPI_POOL)
+          NTK_CUDA(cudaMemsetAsync(nxt, 0, (size_t)m * So * So * So * So * sizeof(T), stream));
+        NTK_TRY((launch_stage<T, false>(stream, launches, S, plan.stages[s].L, s == 0, C, epi, a)));
+        cur = nxt;
+      }
+    }
+    if (bufA) arena.release(bufA);
+    if (bufB) arena.release(bufB);
+  }
+
+  // ---- 2. cross pairs, tiled --------------------------------------------------------------
+  // bytes per pair of the materialised boundaries (two live at a time: in + out)
+  size_t max_b = 0, sum2 = 0;
+  {
+    std::vector<size_t> bsz;
+    for (size_t s = 0; s + 1 < n_st; ++s) {
+      const int So = plan.stages[s].epi == EPI_POOL ? Ss[s] / 2 : Ss[s];
+      bsz.push_back((size_t)So * So * So * So * sizeof(T) * (want_ntk ? 2 : 1));
+    }
+    for (size_t i = 0; i < bsz.size(); ++i) {
+      max_b = std::max(max_b, bsz[i]);
+      sum2 = std::max(sum2, bsz[i] + (i + 1 < bsz.size() ? bsz[i + 1] : 0));
+    }
+  }
+  // free arena bytes: probe by allocating progressively smaller blocks
+  long long tile_pairs = (long long)n1 * n2;
+  T* bnd[2] = {nullptr, nullptr};
+  size_t bnd_bytes = 0;
+  if (sum2 > 0) {
+    for (;;) {
+      bnd_bytes = (size_t)tile_pairs * max_b;
+      bnd[0] = (T*)arena.alloc(bnd_bytes);
+      bnd[1] = bnd[0] ? (T*)arena.alloc(bnd_bytes) : nullptr;
+      if (bnd[0] && bnd[1]) break;
+      if (bnd[0]) arena.release(bnd[0]);
+      bnd[0] = bnd[1] = nullptr;
+      if (tile_pairs <= 1) return fail(NTK_ENOMEM, "workspace too small for one pair");
+      tile_pairs = (tile_pairs + 1) / 2;
+    }
+  }
+  // tile = t1 rows x n2 columns when possible, else 1 row x t2 columns
+  int t1, t2;
+  if (tile_pairs >= n2) {
+    t2 = n2;
+    t1 = (int)std::min<long long>(n1, tile_pairs / n2);
+  } else {
+    t1 = 1;
+    t2 = (int)tile_pairs;
+  }
+  T* resK = (T*)arena.alloc((size_t)t1 * t2 * sizeof(T));
+  T* resT = want_ntk ? (T*)arena.alloc((size_t)t1 * t2 * sizeof(T)) : nullptr;
+  if (!resK || (want_ntk && !resT)) return fail(NTK_ENOMEM, "workspace too small");
+
+  const FusedStage& tail = plan.stages.back();
+  const int S_last = Ss[n_st - 1];
+  (void)tail;
+  for (int r0 = 0; r0 < n1; r0 += t1) {
+    const int a1 = std::min(t1, n1 - r0);
+    for (int c0 = 0; c0 < n2; c0 += t2) {
+      const int a2 = std::min(t2, n2 - c0);
+      const long long P = (long long)a1 * a2;
+      T* cur = nullptr;
+      for (size_t s = 0; s < n_st; ++s) {
+        const int S = Ss[s];
+        FLayer<T> lp[kMaxFusedLayers];
+        double next_alpha = 1.0;
+        stage_constants<T>(plan, s, lp, &next_alpha);
+        StageArgs<T> a{};
+        a.x1 = x1 + (size_t)r0 * S * S * C;
+        a.x2 = x2 + (size_t)c0 * S * S * C;
+        const int epi = plan.stages[s].epi;
+        const int So = epi == EPI_POOL ? S / 2 : S;
+        const size_t in_per = (size_t)S * S * S * S, out_per = (size_t)So * So * So * So;
+        a.inK = cur;
+        a.inT = (cur && want_ntk) ? cur + (size_t)P * in_per : nullptr;
+        T* nxt = (cur == bnd[0]) ? bnd[1] : bnd[0];
+        if (epi == EPI_GAP) {
+          a.outK = resK;
+          a.outT = resT;
+          a.epi_scale = (T)(1.0 / ((double)S_last * S_last * S_last * S_last));
+        } else {
+          a.outK = nxt;
+          a.outT = want_ntk ? nxt + (size_t)P * out_per : nullptr;
+          a.epi_scale = (T)(next_alpha / 16.0);
+          if (epi == EPI_POOL)
+            NTK_CUDA(cudaMemsetAsync(nxt, 0, (size_t)P * out_per * sizeof(T) * (want_ntk ? 2 : 1), stream));
+        }
+        a.qm1 = qm1[s] + (size_t)r0 * plan.stages[s].L * S * S * 2;
+        a.qm2 = qm2[s] + (size_t)c0 * plan.stages[s].L * S * S * 2;
+        a.P = P;
+        a.n2 = a2;
+        a.self = 0;
+        a.in_scale = in_scale;
+        for (int l = 0; l < plan.stages[s].L; ++l) a.lp[l] = lp[l];
+        if (want_ntk)
+          NTK_TRY((launch_stage<T, true>(stream, launches, S, plan.stages[s].L, s == 0, C, epi, a)));
+        else
+          NTK_TRY((launch_stage<T, false>(stream, launches, S, plan.stages[s].L, s == 0, C, epi, a)));
+        cur = nxt;
+      }
+      // Dense tail on the [a1, a2] scalars (linear.py:899-926), then scatter into the result
+      for (const ntk_op_t& d : plan.dense_tail) {
+        (*launches)++;
+        k_dense<T><<<grid_for(P), kThreads, 0, stream>>>(resK, resT, P, (T)d.f[0],
+                                                         (T)(d.i[0] ? d.f[1] : 0.0), 0);
+        NTK_CUDA(cudaGetLastError());
+      }
+      (*launches)++;
+      k_scatter<T><<<grid_for(P), kThreads, 0, stream>>>(resK, out_nngp, a1, a2, 1LL, ld, r0, c0);
+      NTK_CUDA(cudaGetLastError());
+      if (want_ntk) {
+        (*launches)++;
+        k_scatter<T><<<grid_for(P), kThreads, 0, stream>>>(resT, out_ntk, a1, a2, 1LL, ld, r0, c0);
+        NTK_CUDA(cudaGetLastError());
+      }
+    }
+  }
+  return NTK_OK;
+}
 
 // FCN input Gram x1 x2^T / d  (requirements.py:585-638 for 2-D inputs).
 template <typename T>

@@ -72,7 +72,9 @@ def test_golden_full_kernel_layout(nt, golden, name, x64):
     if key not in golden.files:
       assert v is None
     else:
-      np.testing.assert_allclose(v, golden[key], rtol=RTOL[x64], atol=RTOL[x64] * 1e-3)
+      # x2=None kernels contain exact-duplicate entries (n1 == n2, h == h', w == w')
+      rt = RTOL_DUP[x64] if x2 is None else RTOL[x64]
+      np.testing.assert_allclose(v, golden[key], rtol=rt, atol=rt * 1e-3)
 
 
 @pytest.mark.parametrize('x64', [False, True])
@@ -143,7 +145,7 @@ def test_batch_equals_unbatched(nt):
     np.testing.assert_allclose(out.nngp, full.nngp, rtol=1e-6)
     np.testing.assert_allclose(out.ntk, full.ntk, rtol=1e-6)
   with pytest.raises(ValueError, match='must divide batch size'):
-    nt.batch(kernel_fn, batch_size=3, device_count=0)(x1[:7], x2[:3], 'nngp')
+    nt.batch(kernel_fn, batch_size=3, device_count=0)(x1, x2, 'nngp')   # gcd 4 -> 3; 8 % 3 != 0
   # Kernel outputs through the Python block loop (cov1/cov2 stitched, cov2 None for x2=None)
   _, _, kf_sp = cases.build(('serial', [cases.conv(), cases.RELU]), nt.stax)
   k_full = kf_sp(x1, None)
