@@ -3,11 +3,15 @@
   python bench.py --gpus N --steps K --warmup W            # ours (one rank per GPU)
   python bench.py --impl reference --steps K --warmup W    # CPU port of the reference path
 
-A *step* is one Gram block: every rank computes a [b1, b2] block of kernel entries of the
-Myrtle-10 (32x32x3) NNGP+NTK Gram matrix from synthetic N(0,1) inputs (the nt.batch tiling
-of the 10000x10000 configuration; entries/s does not depend on which block is computed).
-Rows are partitioned across ranks with no data-path collective ("weak" scaling: each rank
-owns its own slab of x1 rows, x2 is replicated).
+A *step* is one Gram block per rank: a [b1, b2] block of NNGP+NTK kernel entries of the
+Myrtle-10 (32x32x3) network on synthetic N(0,1) inputs, i.e. one block of the nt.batch
+tiling of the 10000x10000 configuration (entries/s does not depend on which block).  Rows
+are partitioned across ranks ("weak" scaling: every rank owns its own slab of x1 rows, x2 is
+broadcast from rank 0 and the result slabs are all-gathered inside the timed region; there
+is no reduction collective).
+
+JSON line keys follow the driver contract; `roofline` is for the dominant kernel (the first
+fused stage: Conv+Relu x3 + AvgPool at 32x32), timed with CUDA events on its launch stream.
 """
 import argparse
 import json
@@ -23,11 +27,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
 
+E32, E16, E8 = 32**4, 16**4, 8**4
+# name: (myrtle depth, algorithmic elements/entry for the whole net, for fused stage 0)  SURVEY §8d:
+# one HBM round trip (read nngp+ntk, write nngp+ntk) per Conv+Relu(+AvgPool) layer, layer 1 write-only.
 WORKLOADS = {
-    # name: (myrtle depth, algorithmic elements/entry  )
-    'myrtle5': (5, 4 * 32**4 + 4 * 16**4 + 4 * 8**4),
-    'myrtle7': (7, 4 * 32**4 + 8 * 16**4 + 8 * 8**4),
-    'myrtle10': (10, 8 * 32**4 + 12 * 16**4 + 12 * 8**4),
+    'myrtle5': (5, 4 * E32 + 4 * E16 + 4 * E8, 4 * E32 + 2 * E16),
+    'myrtle7': (7, 4 * E32 + 8 * E16 + 8 * E8, 4 * E32 + 2 * E16),
+    'myrtle10': (10, 8 * E32 + 12 * E16 + 12 * E8, 8 * E32 + 2 * E16),
 }
 
 
@@ -38,11 +44,21 @@ def peaks():
   return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}, 'fallback'
 
 
+def ncu_traffic_per_pair(workload, dtype):
+  """dram bytes per sample pair of the dominant kernel from the committed ncu capture."""
+  path = os.path.join(ROOT, 'profiles', 'ncu_stage0_summary.json')
+  try:
+    d = json.load(open(path))
+    return d[f'{workload}_{dtype}']['dram_bytes_per_pair']
+  except Exception:
+    return None
+
+
 class ClockSampler(threading.Thread):
   """Samples nvidia-smi SM clocks / throttle reasons during the timed region."""
   Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-       'clocks_event_reasons.sw_power_cap')
+       'clocks_event_reasons.sw_power_cap,power.draw')
 
   def __init__(self, index):
     super().__init__(daemon=True)
@@ -58,7 +74,7 @@ class ClockSampler(threading.Thread):
           self.samples.append(parts)
       except Exception:
         pass
-      self.stop_flag.wait(0.2)
+      self.stop_flag.wait(0.1)
 
   def summary(self):
     self.stop_flag.set()
@@ -71,52 +87,81 @@ class ClockSampler(threading.Thread):
       for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[2:6]):
         if v.lower().startswith('active'):
           reasons.add(name)
-    return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]),
-            'reasons': sorted(reasons), 'samples': len(sm)}
+    out = {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]),
+           'reasons': sorted(reasons), 'samples': len(sm)}
+    try:
+      out['power_w_max'] = max(float(s[6]) for s in self.samples)
+    except Exception:
+      pass
+    return out
 
 
-def cpu_port_entries_per_s(depth, n_pairs_side, dtype=np.float64):
-  """Times the NumPy oracle (port of the reference path) on a bounded sample."""
+# ---------------------------------------------------------------------------------------
+# CPU arm: the NumPy float64 oracle (port of the reference path) on all host cores
+# ---------------------------------------------------------------------------------------
+def _cpu_worker(job):
+  depth, seed, n_cols = job
+  os.environ.setdefault('OMP_NUM_THREADS', '1')
   from oracle import ntk_oracle as O
   import cases
   spec = cases.myrtle(depth)
-  x1 = np.random.default_rng(0).standard_normal((n_pairs_side, 32, 32, 3)).astype(np.float32)
-  x2 = np.random.default_rng(1).standard_normal((n_pairs_side, 32, 32, 3)).astype(np.float32)
+  x1 = np.random.default_rng(1000 + seed).standard_normal((1, 32, 32, 3)).astype(np.float32)
+  x2 = np.random.default_rng(1).standard_normal((n_cols, 32, 32, 3)).astype(np.float32)
+  out = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'), dtype=np.float64)
+  return float(out[0].sum() + out[1].sum())
+
+
+def cpu_port_step(pool, depth, cores, n_cols):
+  """One bounded CPU step: `cores` workers, each one x1 row against `n_cols` x2 columns."""
   t0 = time.perf_counter()
-  O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'), dtype=dtype)
+  res = pool.map(_cpu_worker, [(depth, s, n_cols) for s in range(cores)])
   dt = time.perf_counter() - t0
-  return n_pairs_side * n_pairs_side / dt, dt
+  assert all(np.isfinite(r) for r in res)
+  return cores * n_cols, dt
+
+
+def make_cpu_pool(cores):
+  import multiprocessing as mp
+  return mp.get_context('spawn').Pool(cores)
 
 
 def run_reference(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
-  depth, _ = WORKLOADS[args.workload]
+  depth = WORKLOADS[args.workload][0]
   cores = len(os.sched_getaffinity(0))
-  side = args.ref_side
-  for _ in range(max(args.warmup, 0) and 1):
-    cpu_port_entries_per_s(depth, 1)
-  vals, t_tot = [], 0.0
-  for _ in range(args.steps):
-    v, dt = cpu_port_entries_per_s(depth, side)
-    vals.append(v)
-    t_tot += dt
-  value = side * side * len(vals) / t_tot
+  pool = make_cpu_pool(cores)
+  try:
+    for _ in range(min(args.warmup, 1)):
+      cpu_port_step(pool, depth, cores, 1)
+    entries, t_tot = 0, 0.0
+    for _ in range(args.steps):
+      n, dt = cpu_port_step(pool, depth, cores, args.ref_cols)
+      entries += n
+      t_tot += dt
+  finally:
+    pool.terminate()
+  value = entries / t_tot
+  sample = (f'{cores} worker processes x (1 x {args.ref_cols}) pairs per step, NumPy float64 '
+            'restatement of the reference path (the reference itself needs JAX, not installable here)')
   line = {
       'impl': 'reference', 'metric': 'kernel_entries_per_sec', 'value': value, 'unit': 'entries/s',
       'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-      'ms_per_step': 1e3 * t_tot / len(vals), 'higher_is_better': True, 'scaling': 'weak',
+      'ms_per_step': 1e3 * t_tot / args.steps, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-      'config': {'workload': f'{args.workload}_32x32x3_nngp+ntk', 'block': [side, side]},
+      'config': {'workload': f'{args.workload}_32x32x3_nngp+ntk',
+                 'block': [cores, args.ref_cols]},
       'cpu_baseline': {'value': value, 'unit': 'entries/s', 'cores': cores, 'kind': 'port',
-                       'sample': f'{side}x{side} pairs per step, NumPy float64 restatement of the '
-                                 'reference path (reference needs JAX, not installable here)'},
+                       'sample': sample},
       'e2e': {'value': value, 'unit': 'entries/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
   }
   print(json.dumps(line))
 
 
+# ---------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------
 def run_ours(args):
   import torch
   import torch.distributed as dist
@@ -130,8 +175,9 @@ def run_ours(args):
   world = int(os.environ.get('WORLD_SIZE', '1'))
   local = int(os.environ.get('LOCAL_RANK', '0'))
   torch.cuda.set_device(local)
+  dev = torch.device('cuda', local)
   if world > 1:
-    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dist.init_process_group('nccl', device_id=dev)
   nt.config.update('device', local)
   x64 = args.dtype == 'f64'
   nt.config.update('enable_x64', x64)
@@ -139,25 +185,30 @@ def run_ours(args):
   t_dt = torch.float64 if x64 else torch.float32
   sz = 8 if x64 else 4
 
-  depth, elems = WORKLOADS[args.workload]
+  depth, elems_net, elems_stage0 = WORKLOADS[args.workload]
   _, _, kernel_fn = cases.build(cases.myrtle(depth), stax)
   low = stax._lowered(stax._strip(kernel_fn._spec), False, False, True)
   b1, b2 = args.block
-  # synthetic inputs: every rank owns its own x1 row slab, x2 is shared
+  # synthetic inputs: each rank owns a slab of x1 rows; x2 comes from rank 0
   x1_h = np.random.default_rng(100 + rank).standard_normal((b1, 32, 32, 3)).astype(np_dt)
   x2_h = np.random.default_rng(1).standard_normal((b2, 32, 32, 3)).astype(np_dt)
   ctx = _lib.get_context(local)
-  stream = torch.cuda.ExternalStream(ctx.stream, device=local)
-  x1_d = torch.from_numpy(x1_h).cuda(local)
-  x2_d = torch.from_numpy(x2_h).cuda(local)
-  nngp_d = torch.empty((b1, b2), dtype=t_dt, device=f'cuda:{local}')
-  ntk_d = torch.empty((b1, b2), dtype=t_dt, device=f'cuda:{local}')
-  flush = torch.empty(256 << 20, dtype=torch.uint8, device=f'cuda:{local}')  # > 126 MB L2
+  stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+  x1_d = torch.from_numpy(x1_h).to(dev)
+  x2_d = torch.from_numpy(x2_h).to(dev) if rank == 0 else torch.empty((b2, 32, 32, 3), dtype=t_dt, device=dev)
+  out_d = torch.empty((2, b1, b2), dtype=t_dt, device=dev)          # this rank's nngp / ntk slab
+  gath_d = torch.empty((world, 2, b1, b2), dtype=t_dt, device=dev) if world > 1 else None
+  flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
   flags = _lib.FLAG_NO_FUSION if args.no_fusion else 0
 
   def step_device():
+    # everything is ordered on the context stream (NCCL syncs with the current stream)
+    if world > 1:
+      dist.broadcast(x2_d, src=0)                                   # x2 over NVLink
     _lib.gram_device(ctx, low.program, np_dt, x1_d.data_ptr(), b1, x2_d.data_ptr(), b2, 32, 32, 3,
-                     flags, nngp_d.data_ptr(), ntk_d.data_ptr(), b2)
+                     flags, out_d[0].data_ptr(), out_d[1].data_ptr(), b2)
+    if world > 1:
+      dist.all_gather_into_tensor(gath_d, out_d)                    # result slabs; no reduction
 
   def barrier():
     torch.cuda.synchronize()
@@ -165,29 +216,31 @@ def run_ours(args):
       dist.barrier()
     torch.cuda.synchronize()
 
-  torch.cuda.synchronize()
-  for _ in range(args.warmup):
-    step_device()
+  with torch.cuda.stream(stream):
+    for _ in range(args.warmup):
+      step_device()
   ctx.synchronize()
   launches0 = ctx.launch_count
+  ctx.set_profiling(True)
   sampler = ClockSampler(local)
   if rank == 0:
     sampler.start()
   barrier()
   evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
          for _ in range(args.steps)]
-  for s, e in evs:
-    flush.zero_()                      # L2 flush between timed iterations (untimed)
-    torch.cuda.synchronize()
-    with torch.cuda.stream(stream):
+  with torch.cuda.stream(stream):
+    for s, e in evs:
+      flush.zero_()                      # L2 flush between timed iterations (outside the events)
       s.record(stream)
       step_device()
       e.record(stream)
   barrier()
   ms_dev = sum(s.elapsed_time(e) for s, e in evs)
   launches = ctx.launch_count - launches0
+  st0_ms, st0_n, st0_pairs = ctx.profile(0) if not args.no_fusion else (0.0, 0, 0)
+  ctx.set_profiling(False)
 
-  # end-to-end through the public API: host buffers in, host results out (nt.batch)
+  # end to end through the public API: HOST buffers in, HOST results out (nt.batch -> C-ABI)
   batched = nt.batch(kernel_fn, batch_size=args.e2e_batch, device_count=0)
   batched(x1_h[:args.e2e_batch], x2_h[:args.e2e_batch], ('nngp', 'ntk'))
   barrier()
@@ -199,7 +252,7 @@ def run_ours(args):
   barrier()
   clocks = sampler.summary() if rank == 0 else None
 
-  t = torch.tensor([ms_dev, e2e_s * 1e3], dtype=torch.float64, device=f'cuda:{local}')
+  t = torch.tensor([ms_dev, e2e_s * 1e3], dtype=torch.float64, device=dev)
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
   ms_dev_max, e2e_ms_max = t.tolist()
@@ -207,36 +260,60 @@ def run_ours(args):
     if world > 1:
       dist.destroy_process_group()
     return
+
+  # the device-resident result of the last timed step must equal the public-API result
+  np.testing.assert_allclose(out_d[0].cpu().numpy(), res.nngp, rtol=1e-5)
+  np.testing.assert_allclose(out_d[1].cpu().numpy(), res.ntk, rtol=1e-5)
+
   entries_per_step = b1 * b2 * world
   value = entries_per_step * args.steps / (ms_dev_max * 1e-3)
   e2e_value = entries_per_step * args.steps / (e2e_ms_max * 1e-3)
   pk, pk_kind = peaks()
-  bytes_per_entry = elems * sz
-  achieved = (b1 * b2 * args.steps * bytes_per_entry) / (ms_dev / 1e3) / 1e9   # rank 0, GB/s
-  # sanity: result must agree with the oracle-checked path (cheap spot check on 1 entry is in smoke())
-  assert np.isfinite(res.nngp).all() and np.isfinite(res.ntk).all()
-  cpu_v, cpu_dt = cpu_port_entries_per_s(depth, args.ref_side) if world == 1 else (None, None)
+  roof = {'bound': 'hbm', 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'peak_kind': pk_kind + ' (burst copy)'}
+  if st0_n > 0:
+    alg_bytes_per_pair = elems_stage0 * sz
+    achieved = st0_pairs * alg_bytes_per_pair / (st0_ms * 1e-3) / 1e9
+    tpp = ncu_traffic_per_pair(args.workload, args.dtype)
+    roof.update({
+        'kernel': 'k_stage<S=32,L=%d,FROM_X,POOL> (fused Conv+Relu x%d + AvgPool)' % ((3, 3) if depth == 10 else (2, 2)),
+        'achieved': achieved, 'frac': achieved / pk['hbm_gbs'],
+        'algorithmic_bytes_per_launch': alg_bytes_per_pair * st0_pairs // st0_n,
+        'avg_launch_ms': st0_ms / st0_n, 'launches_timed': st0_n,
+        'share_of_step': st0_ms / ms_dev,
+        'traffic': None if tpp is None else tpp * st0_pairs // st0_n,
+        'whole_net_achieved': b1 * b2 * args.steps * elems_net * sz / (ms_dev * 1e-3) / 1e9,
+    })
+    roof['whole_net_frac'] = roof['whole_net_achieved'] / pk['hbm_gbs']
+  else:
+    achieved = b1 * b2 * args.steps * elems_net * sz / (ms_dev * 1e-3) / 1e9
+    roof.update({'kernel': 'per-layer path (all kernels of the step)', 'achieved': achieved,
+                 'frac': achieved / pk['hbm_gbs'], 'traffic': None})
   line = {
       'metric': 'kernel_entries_per_sec', 'value': value, 'unit': 'entries/s', 'n_gpus': world,
       'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev_max / args.steps,
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,
       'data': 'synthetic',
       'config': {'workload': f'{args.workload}_32x32x3_nngp+ntk', 'block_per_gpu': [b1, b2],
-                 'parallelism': f'row-partition x{world}', 'l2': 'flushed between timed steps',
-                 'fusion': not args.no_fusion},
+                 'parallelism': f'x1-row partition over {world} rank(s), x2 broadcast, slabs all-gathered',
+                 'l2': 'flushed (256 MiB write) between timed steps', 'fusion': not args.no_fusion},
       'e2e': {'value': e2e_value, 'unit': 'entries/s',
               'h2d_bytes_per_step': int(x1_h.nbytes + x2_h.nbytes) * world,
               'd2h_bytes_per_step': int(2 * b1 * b2 * sz) * world},
       'gpu_launches': int(launches),
       'clocks': clocks,
-      'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                   'frac': achieved / pk['hbm_gbs'], 'traffic': None, 'peak_kind': pk_kind,
-                   'kernel': 'whole layer pipeline (algorithmic bytes/entry x entries / step time)'},
+      'roofline': roof,
   }
-  if cpu_v is not None:
-    line['cpu_baseline'] = {'value': cpu_v, 'unit': 'entries/s', 'cores': len(os.sched_getaffinity(0)),
-                            'kind': 'port',
-                            'sample': f'{args.ref_side}x{args.ref_side} pairs, NumPy float64 oracle, {cpu_dt:.1f}s'}
+  if world == 1 and not args.no_cpu:
+    cores = len(os.sched_getaffinity(0))
+    pool = make_cpu_pool(cores)
+    try:
+      cpu_port_step(pool, depth, cores, 1)
+      n, dt = cpu_port_step(pool, depth, cores, args.ref_cols)
+    finally:
+      pool.terminate()
+    line['cpu_baseline'] = {
+        'value': n / dt, 'unit': 'entries/s', 'cores': cores, 'kind': 'port',
+        'sample': f'{cores} worker processes x (1 x {args.ref_cols}) pairs, NumPy float64 oracle, {dt:.1f} s'}
   print(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()
@@ -245,15 +322,16 @@ def run_ours(args):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=5)
+  ap.add_argument('--steps', type=int, default=10)
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--workload', default='myrtle10', choices=sorted(WORKLOADS))
   ap.add_argument('--dtype', default='f32', choices=['f32', 'f64'])
-  ap.add_argument('--block', type=int, nargs=2, default=[64, 64])
+  ap.add_argument('--block', type=int, nargs=2, default=[96, 96])
   ap.add_argument('--e2e-batch', type=int, default=32)
-  ap.add_argument('--ref-side', type=int, default=4)
+  ap.add_argument('--ref-cols', type=int, default=4)
   ap.add_argument('--no-fusion', action='store_true')
+  ap.add_argument('--no-cpu', action='store_true')
   args = ap.parse_args()
   if args.impl == 'reference':
     run_reference(args)

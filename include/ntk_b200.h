@@ -138,6 +138,15 @@ void* ntk_context_stream(ntk_context_t* ctx);
 /* Number of CUDA kernels this context has launched so far (bench `gpu_launches`). */
 int64_t ntk_context_launch_count(const ntk_context_t* ctx);
 
+/* Per-kernel device timing for bench.py's roofline line: when enabled, the fused path
+ * brackets every stage kernel of the cross-pair pass with CUDA events on the context
+ * stream.  `ntk_context_profile` returns, for stage `stage` (0 = first fused stage), the
+ * accumulated device time, the number of launches and the number of sample pairs they
+ * processed since profiling was (re-)enabled; it synchronises the stream first. */
+int ntk_context_set_profiling(ntk_context_t* ctx, int32_t enabled);
+int ntk_context_profile(ntk_context_t* ctx, int32_t stage, double* total_ms, int64_t* launches,
+                        int64_t* pairs);
+
 /* ---- the hot path --------------------------------------------------------
  * kernel_fn(x1, x2, get) on raw inputs (`requirements.py:939-953`):
  *   x1: [n1, H, W, C] (or [n1, C] with H == W == 0), x2 likewise or NULL (== x1).

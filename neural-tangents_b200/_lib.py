@@ -24,7 +24,8 @@ E_INVAL, E_CUDA, E_NOMEM, E_NOTGAUSSIAN, E_UNSUPPORTED, E_SHAPE = -1, -2, -3, -4
 EXPORTED_SYMBOLS = (
     'ntk_abi_version', 'ntk_last_error', 'ntk_device_count', 'ntk_program_create',
     'ntk_program_destroy', 'ntk_program_output_shape', 'ntk_context_create', 'ntk_context_destroy',
-    'ntk_context_synchronize', 'ntk_context_stream', 'ntk_context_launch_count', 'ntk_gram_host',
+    'ntk_context_synchronize', 'ntk_context_stream', 'ntk_context_launch_count',
+    'ntk_context_set_profiling', 'ntk_context_profile', 'ntk_gram_host',
     'ntk_gram_device', 'ntk_apply_host', 'ntk_workspace_bytes', 'ntk_device_malloc',
     'ntk_device_free', 'ntk_memcpy_h2d', 'ntk_memcpy_d2h')
 
@@ -81,6 +82,8 @@ def load():
     lib.ntk_context_stream.restype = vp
     lib.ntk_context_launch_count.argtypes = [vp]
     lib.ntk_context_launch_count.restype = i64
+    lib.ntk_context_set_profiling.argtypes = [vp, i32]
+    lib.ntk_context_profile.argtypes = [vp, i32, P(ctypes.c_double), P(i64), P(i64)]
     gram_args = [vp, vp, i32, vp, i32, vp, i32, i32, i32, i32, u32, vp, vp, i64, vp, vp]
     lib.ntk_gram_host.argtypes = gram_args
     lib.ntk_gram_device.argtypes = gram_args
@@ -174,6 +177,15 @@ class Context:
   @property
   def launch_count(self):
     return int(self._lib.ntk_context_launch_count(self._h))
+
+  def set_profiling(self, enabled):
+    check(self._lib.ntk_context_set_profiling(self._h, int(bool(enabled))))
+
+  def profile(self, stage):
+    """(total_ms, launches, pairs) of fused stage `stage` since profiling was enabled."""
+    ms, n, pr = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+    check(self._lib.ntk_context_profile(self._h, stage, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(pr)))
+    return ms.value, n.value, pr.value
 
   def close(self):
     if self._h:

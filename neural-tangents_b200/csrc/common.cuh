@@ -128,4 +128,15 @@ class Arena {
 
 constexpr int kNumSMs = 148;  // B200
 
+// Optional per-stage device timing (ntk_context_set_profiling).
+struct StageProfile {
+  static constexpr int kMaxStages = 16;
+  bool enabled = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[kMaxStages];
+  std::vector<long long> pending_pairs[kMaxStages];
+  double total_ms[kMaxStages] = {0};
+  long long launches[kMaxStages] = {0};
+  long long pairs[kMaxStages] = {0};
+};
+
 }  // namespace ntk

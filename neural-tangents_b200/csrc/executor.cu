@@ -33,6 +33,7 @@ struct ntk_context {
   // grow-only device IO buffers for the *_host entry points
   void* io[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t io_bytes[6] = {0, 0, 0, 0, 0, 0};
+  StageProfile prof;
 };
 
 namespace {
@@ -631,7 +632,7 @@ int gram_device_t(ntk_context* ctx, const ntk_program* prog, const T* x1, int n1
   if (!(flags & NTK_FLAG_NO_FUSION) && prog->fused.ok && H > 0 &&
       fused_supported<T>(prog->fused, H, W, C) && !out.cov1 && !out.cov2) {
     ctx->arena.reset(ctx->ws, ctx->ws_bytes, false);
-    int st = fused_gram<T>(prog->fused, ctx->arena, ctx->stream, &env.launches, x1, n1, x2, n2,
+    int st = fused_gram<T>(prog->fused, ctx->arena, ctx->stream, &env.launches, &ctx->prof, x1, n1, x2, n2,
                            symmetric, H, W, C, want_ntk, (T*)out.nngp, (T*)out.ntk, out.ld);
     ctx->launches += env.launches;
     return st;
@@ -844,6 +845,49 @@ int ntk_context_synchronize(ntk_context_t* ctx) {
   if (!ctx) return fail(NTK_EINVAL, "ctx is NULL");
   NTK_CUDA(cudaSetDevice(ctx->device));
   NTK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NTK_OK;
+}
+
+int ntk_context_set_profiling(ntk_context_t* ctx, int32_t enabled) {
+  if (!ctx) return fail(NTK_EINVAL, "ctx is NULL");
+  NTK_CUDA(cudaSetDevice(ctx->device));
+  NTK_CUDA(cudaStreamSynchronize(ctx->stream));
+  StageProfile& p = ctx->prof;
+  for (int s = 0; s < StageProfile::kMaxStages; ++s) {
+    for (auto& ev : p.pending[s]) {
+      cudaEventDestroy(ev.first);
+      cudaEventDestroy(ev.second);
+    }
+    p.pending[s].clear();
+    p.pending_pairs[s].clear();
+    p.total_ms[s] = 0;
+    p.launches[s] = 0;
+    p.pairs[s] = 0;
+  }
+  p.enabled = enabled != 0;
+  return NTK_OK;
+}
+
+int ntk_context_profile(ntk_context_t* ctx, int32_t stage, double* total_ms, int64_t* launches,
+                        int64_t* pairs) {
+  if (!ctx || stage < 0 || stage >= StageProfile::kMaxStages) return fail(NTK_EINVAL, "bad arguments");
+  NTK_CUDA(cudaSetDevice(ctx->device));
+  NTK_CUDA(cudaStreamSynchronize(ctx->stream));
+  StageProfile& p = ctx->prof;
+  for (size_t k = 0; k < p.pending[stage].size(); ++k) {
+    float ms = 0.f;
+    NTK_CUDA(cudaEventElapsedTime(&ms, p.pending[stage][k].first, p.pending[stage][k].second));
+    p.total_ms[stage] += ms;
+    p.launches[stage] += 1;
+    p.pairs[stage] += p.pending_pairs[stage][k];
+    cudaEventDestroy(p.pending[stage][k].first);
+    cudaEventDestroy(p.pending[stage][k].second);
+  }
+  p.pending[stage].clear();
+  p.pending_pairs[stage].clear();
+  if (total_ms) *total_ms = p.total_ms[stage];
+  if (launches) *launches = p.launches[stage];
+  if (pairs) *pairs = p.pairs[stage];
   return NTK_OK;
 }
 

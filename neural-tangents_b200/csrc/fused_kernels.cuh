@@ -24,6 +24,7 @@
 // 36.9 MB "one round trip per layer" model used for the roofline.
 #pragma once
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -42,6 +43,7 @@ template <typename T>
 struct FLayer {
   T coef;     // alpha_next * (a-b)^2 / (2 pi)
   T half_ab;  // alpha_next * (a^2+b^2) / 2
+  T hab2;     // half_ab - coef * pi/2
   T bias;     // b_std^2 of this layer's conv
 };
 
@@ -110,27 +112,47 @@ __device__ __forceinline__ float acos_over_sin(float c) {
 // ABRelu on one element (elementwise.py:444-455), constants pre-scaled by alpha_next.
 //   s = sqrt(max(q1 q2 - K^2, 0)); theta = atan2(s, K);
 //   kd = half_ab - coef*theta;  K' = coef*s + kd*K;  T' = kd*T
-// fp32: theta = sin(theta) * G(|cos theta|) with sin/cos from the stored 1/sqrt(q) maps:
-// one MUFU (sqrt) per element, no division, no atan2.
+// fp32: with sin(theta) = s/sqrt(q1 q2) and cos(theta) = K/sqrt(q1 q2) from the stored
+// 1/sqrt(q) maps,  acos|cos| = sin * G(|cos|)  (G = acos(c)/sqrt(1-c^2), a degree-8 fit) and
+//   kd = hab2 + coef * copysign(pi/2 - acos|cos|, cos),   hab2 = half_ab - coef*pi/2:
+// one MUFU (sqrt) per element, no division, no atan2, no branch.
+constexpr float kHalfPiF = 1.57079632679489661923f;
+
+// kd of an exact-duplicate element (theta == 0): shared with the q-map kernel so that both
+// see bit-identical diagonals.
+__device__ __forceinline__ float kd_zero_angle(float coef, float half_ab, float hab2) {
+  (void)half_ab;
+  return __fmaf_rn(coef, kHalfPiF, hab2);
+}
+__device__ __forceinline__ double kd_zero_angle(double coef, double half_ab, double hab2) {
+  (void)coef;
+  (void)hab2;
+  return half_ab;
+}
+
 __device__ __forceinline__ void act_point(float K, float Tn, float q1, float b1, float q2, float b2,
-                                          float coef, float half_ab, float& Ko, float& To) {
+                                          float coef, float half_ab, float hab2, float& Ko,
+                                          float& To) {
+  (void)half_ab;
   const float p = __fmul_rn(q1, q2);
   const float rb = __fmul_rn(b1, b2);
-  const float s = sqrt_fast(fmaxf(__fsub_rn(p, __fmul_rn(K, K)), 0.f));
+  // |.|: a slightly negative difference is rounding noise of the same size as a slightly
+  // positive one; exact duplicates give exactly 0 either way.
+  const float s = sqrt_fast(fabsf(__fsub_rn(p, __fmul_rn(K, K))));
   const float sn = __fmul_rn(s, rb);
   const float c = __fmul_rn(K, rb);
-  const float th = __fmul_rn(sn, acos_over_sin(fminf(fabsf(c), 1.f)));
-  const float theta = c < 0.f ? __fsub_rn(3.14159265358979323846f, th) : th;
-  const float kd = __fmaf_rn(-coef, theta, half_ab);
+  const float u = __fmaf_rn(-sn, acos_over_sin(fabsf(c)), kHalfPiF);
+  const float kd = __fmaf_rn(coef, copysignf(u, c), hab2);
   Ko = __fmaf_rn(kd, K, __fmul_rn(coef, s));
   To = __fmul_rn(kd, Tn);
 }
 
 __device__ __forceinline__ void act_point(double K, double Tn, double q1, double b1, double q2,
-                                          double b2, double coef, double half_ab, double& Ko,
-                                          double& To) {
+                                          double b2, double coef, double half_ab, double hab2,
+                                          double& Ko, double& To) {
   (void)b1;
   (void)b2;
+  (void)hab2;
   const double p = __dmul_rn(q1, q2);
   const double s = sqrt(fmax(__dsub_rn(p, __dmul_rn(K, K)), 0.0));
   const double theta = (s == 0.0 && K == 0.0) ? 1.5707963267948966 : atan2(s, K);
@@ -195,7 +217,7 @@ __global__ void k_qmaps(const T* __restrict__ src, int src_mode, int C, T in_sca
       o.x = q;
       o.y = q > (T)0 ? rsqrt_t(q) : (T)0;
       out[(long long)l * S * S + e] = o;
-      P[e] = mul_rn(lp[l].half_ab, q);  // ABRelu on the diagonal: theta = 0
+      P[e] = mul_rn(kd_zero_angle(lp[l].coef, lp[l].half_ab, lp[l].hab2), q);  // theta == 0
     }
     __syncthreads();
   }
@@ -286,46 +308,47 @@ k_stage(const StageArgs<T> a) {
   // ---- per-thread constants -------------------------------------------------------------
   // lk[i]: link between w0+i-1 and w0+i is intact (both inside the image, w' does not wrap)
   T lk[WPT + 1];
+  int off2[WPT];  // (w0 + i + cw) mod S (column of the second member), as a byte offset into a V2 row
 #pragma unroll
   for (int i = 0; i <= WPT; ++i) {
     const int wl = w0 + i - 1, wr = w0 + i;
     lk[i] = (wl >= 0 && wr <= S - 1 && ((wl + cw) % S) != S - 1) ? (T)1 : (T)0;
   }
+#pragma unroll
+  for (int i = 0; i < WPT; ++i) off2[i] = ((w0 + i + cw) % S) * (int)sizeof(V2);
 
-  // sliding windows: RK[l][slot][i] = horizontally summed input row of layer l
+  // sliding windows: RK[l][slot][i] = horizontally summed input row of layer l.
+  // The pipeline runs unconditionally: rows outside [0, NR) are computed from clamped,
+  // finite data and never reach a result (their links are cut: vU = 0 at h = 0, vD = 0 at
+  // h = S-1), so the rings need no fill/drain special cases.
   T RK[L][2][WPT];
   T RT[L][2][WPT];
 #pragma unroll
   for (int l = 0; l < L; ++l)
 #pragma unroll
-    for (int s = 0; s < 2; ++s)
+    for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
       for (int i = 0; i < WPT; ++i) {
-        RK[l][s][i] = (T)0;
-        RT[l][s][i] = (T)0;
+        RK[l][sl][i] = (T)0;
+        RT[l][sl][i] = (T)0;
       }
 
   T gap_k = (T)0, gap_t = (T)0;
-  const T* inK = IN == IN_LOAD ? a.inK + p * (long long)NR * S * S : nullptr;
-  const T* inT = (IN == IN_LOAD && NTK) ? a.inT + p * (long long)NR * S * S : nullptr;
+  const T* inK = IN == IN_LOAD ? a.inK + p * (long long)NR * S * S + (long long)w0 * S + cw : nullptr;
+  const T* inT = (IN == IN_LOAD && NTK) ? a.inT + p * (long long)NR * S * S + (long long)w0 * S + cw : nullptr;
 
   // next input row (software prefetch for LOAD)
   T nK[WPT], nT[WPT];
   auto fetch = [&](int r) {
     if (IN == IN_LOAD) {
-      if (r < NR) {
-        const long long base = (long long)r * S * S + (long long)w0 * S + cw;
+      const int rc = r < NR ? r : NR - 1;
+      const T* gk = inK + (long long)rc * S * S;
 #pragma unroll
-        for (int i = 0; i < WPT; ++i) {
-          nK[i] = __ldg(inK + base + (long long)i * S);
-          if (NTK) nT[i] = __ldg(inT + base + (long long)i * S);
-        }
-      } else {
+      for (int i = 0; i < WPT; ++i) nK[i] = __ldg(gk + i * S);
+      if (NTK) {
+        const T* gt = inT + (long long)rc * S * S;
 #pragma unroll
-        for (int i = 0; i < WPT; ++i) {
-          nK[i] = (T)0;
-          nT[i] = (T)0;
-        }
+        for (int i = 0; i < WPT; ++i) nT[i] = __ldg(gt + i * S);
       }
     }
   };
@@ -336,98 +359,86 @@ k_stage(const StageArgs<T> a) {
     constexpr int par = decltype(par_c)::value;
     T PK[WPT], PT[WPT];
     // ---- input row r = t of layer 1 ----------------------------------------------------
-    {
-      const int r = t;
-      if (IN == IN_FROM_X) {
-        if (r < NR) {
-          const int ch = r / S, h = r % S;
-          const int h2 = (h + ch) % S;
+    if (IN == IN_FROM_X) {
+      const int r = t < NR ? t : NR - 1;
+      const int ch = r / S, h = r % S;
+      const int h2 = (h + ch) % S;
+      const T* xa = x1s + (h * S + w0) * CIN;
+      const char* xb = reinterpret_cast<const char*>(x2s + h2 * S * 4);
 #pragma unroll
-          for (int i = 0; i < WPT; ++i) {
-            const int w = w0 + i, w2 = (w + cw) % S;
-            const T* xa = x1s + (h * S + w) * CIN;
-            const T* xb = x2s + (h2 * S + w2) * 4;
-            T acc = mul_rn(xa[0], xb[0]);
+      for (int i = 0; i < WPT; ++i) {
+        const T* b4 = reinterpret_cast<const T*>(xb + off2[i] * 2);  // 4 T per pixel = 2 V2
+        T acc = mul_rn(xa[i * CIN], b4[0]);
 #pragma unroll
-            for (int c = 1; c < CIN; ++c) acc = fma_t(xa[c], xb[c], acc);
-            PK[i] = acc;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < WPT; ++i) PK[i] = (T)0;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < WPT; ++i) {
-          PK[i] = nK[i];
-          PT[i] = nT[i];
-        }
-        fetch(r + 1);
+        for (int c = 1; c < CIN; ++c) acc = fma_t(xa[i * CIN + c], b4[c], acc);
+        PK[i] = acc;
       }
+    } else {
+#pragma unroll
+      for (int i = 0; i < WPT; ++i) {
+        PK[i] = nK[i];
+        PT[i] = nT[i];
+      }
+      fetch(t + 1);
     }
 #pragma unroll
     for (int l = 0; l < L; ++l) {
-      const int r_in = t - l;  // row of layer-l input now in PK/PT
-      const int slot = (par + l) & 1;  // == r_in & 1 (compile-time)
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int slot = (par + l) & 1;  // == (t - l) & 1, compile-time
       const bool has_t = NTK && (l > 0 || IN == IN_LOAD);
-      if (r_in >= 0 && r_in <= NR) {  // uniform: pipeline fill / drain
-        // ---- horizontal 3-tap (register-local + one halo shuffle pair) -----------------
-        T Rk[WPT], Rt[WPT];
-        {
-          T left = (T)0, right = (T)0, leftT = (T)0, rightT = (T)0;
-          if (NWB > 1) {
-            left = __shfl_up_sync(0xffffffffu, PK[WPT - 1], LW);
-            right = __shfl_down_sync(0xffffffffu, PK[0], LW);
-            if (has_t) {
-              leftT = __shfl_up_sync(0xffffffffu, PT[WPT - 1], LW);
-              rightT = __shfl_down_sync(0xffffffffu, PT[0], LW);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < WPT; ++i) {
-            Rk[i] = hsum3<T>(i == 0 ? left : PK[i == 0 ? 0 : i - 1], PK[i],
-                             i == WPT - 1 ? right : PK[i == WPT - 1 ? i : i + 1], lk[i], lk[i + 1]);
-            if (has_t)
-              Rt[i] = hsum3<T>(i == 0 ? leftT : PT[i == 0 ? 0 : i - 1], PT[i],
-                               i == WPT - 1 ? rightT : PT[i == WPT - 1 ? i : i + 1], lk[i], lk[i + 1]);
+      // ---- horizontal 3-tap (register-local + one halo shuffle pair) -------------------
+      T Rk[WPT], Rt[WPT];
+      {
+        T left = (T)0, right = (T)0, leftT = (T)0, rightT = (T)0;
+        if (NWB > 1) {
+          left = __shfl_up_sync(0xffffffffu, PK[WPT - 1], LW);
+          right = __shfl_down_sync(0xffffffffu, PK[0], LW);
+          if (has_t) {
+            leftT = __shfl_up_sync(0xffffffffu, PT[WPT - 1], LW);
+            rightT = __shfl_down_sync(0xffffffffu, PT[0], LW);
           }
         }
-        // ---- vertical 3-tap: emit conv row r_out = r_in - 1 ------------------------------
-        const int r_out = r_in - 1;
-        if (r_out >= 0) {
-          const int ch = r_out / S, h = r_out % S;
-          const int h2 = (h + ch) % S;
-          const T vU = (h > 0 && h2 != 0) ? (T)1 : (T)0;
-          const T vD = (h < S - 1 && h2 != S - 1) ? (T)1 : (T)0;
-          const V2* q1r = q1m + (l * S + h) * S + w0;
-          const V2* q2r = q2m + (l * S + h2) * S;
-          const T coef = a.lp[l].coef, half_ab = a.lp[l].half_ab, bias = a.lp[l].bias;
-#pragma unroll
-          for (int i = 0; i < WPT; ++i) {
-            const T ck = vsum3<T>(RK[l][slot][i], RK[l][slot ^ 1][i], Rk[i], vU, vD, bias);
-            T ct = (T)0;
-            if (NTK) {
-              // linear.py:1396-1398 (T0 == 0 for the first layer of a FROM_X stage)
-              ct = has_t ? add_rn(fma_t(vD, Rt[i], fma_t(vU, RT[l][slot][i], RT[l][slot ^ 1][i])), ck)
-                         : ck;
-            }
-            const V2 qa = q1r[i];
-            const V2 qb = q2r[(w0 + i + cw) % S];
-            act_point(ck, ct, qa.x, qa.y, qb.x, qb.y, coef, half_ab, PK[i], PT[i]);
-          }
-        }
-        // ---- rotate the window: the new row replaces the oldest one ---------------------
 #pragma unroll
         for (int i = 0; i < WPT; ++i) {
-          RK[l][slot][i] = Rk[i];
-          if (has_t) RT[l][slot][i] = Rt[i];
+          Rk[i] = hsum3<T>(i == 0 ? left : PK[i == 0 ? 0 : i - 1], PK[i],
+                           i == WPT - 1 ? right : PK[i == WPT - 1 ? i : i + 1], lk[i], lk[i + 1]);
+          if (has_t)
+            Rt[i] = hsum3<T>(i == 0 ? leftT : PT[i == 0 ? 0 : i - 1], PT[i],
+                             i == WPT - 1 ? rightT : PT[i == WPT - 1 ? i : i + 1], lk[i], lk[i + 1]);
         }
-      } else if (r_in > NR) {  // this layer has drained: feed a zero row downstream
+      }
+      // ---- vertical 3-tap: conv row r_out = t - l - 1 (clamped outside the image) ---------
+      {
+        int r_out = t - l - 1;
+        r_out = r_out < 0 ? 0 : (r_out > NR - 1 ? NR - 1 : r_out);
+        const int ch = r_out / S, h = r_out % S;
+        const int h2 = (h + ch) % S;
+        const T vU = (h > 0 && h2 != 0) ? (T)1 : (T)0;
+        const T vD = (h < S - 1 && h2 != S - 1) ? (T)1 : (T)0;
+        const V2* q1r = q1m + (l * S + h) * S + w0;
+        const char* q2r = reinterpret_cast<const char*>(q2m + (l * S + h2) * S);
+        const T coef = a.lp[l].coef, half_ab = a.lp[l].half_ab, hab2 = a.lp[l].hab2,
+                bias = a.lp[l].bias;
 #pragma unroll
         for (int i = 0; i < WPT; ++i) {
-          PK[i] = (T)0;
-          PT[i] = (T)0;
+          const T ck = vsum3<T>(RK[l][slot][i], RK[l][slot ^ 1][i], Rk[i], vU, vD, bias);
+          T ct = (T)0;
+          if (NTK) {
+            // linear.py:1396-1398 (T0 == 0 for the first layer of a FROM_X stage)
+            ct = has_t ? add_rn(fma_t(vD, Rt[i], fma_t(vU, RT[l][slot][i], RT[l][slot ^ 1][i])), ck)
+                       : ck;
+          }
+          const V2 qa = q1r[i];
+          const V2 qb = *reinterpret_cast<const V2*>(q2r + off2[i]);
+          act_point(ck, ct, qa.x, qa.y, qb.x, qb.y, coef, half_ab, hab2, PK[i], PT[i]);
         }
+      }
+      // ---- rotate the window: the new row replaces the oldest one -----------------------
+#pragma unroll
+      for (int i = 0; i < WPT; ++i) {
+        RK[l][slot][i] = Rk[i];
+        if (has_t) RT[l][slot][i] = Rt[i];
       }
     }
     // ---- epilogue on the finished row r_fin = t - L -----------------------------------------
@@ -489,7 +500,7 @@ k_stage(const StageArgs<T> a) {
     }
   };
 
-  constexpr int NSTEPS = NR + L;
+  constexpr int NSTEPS = NR + L + ((NR + L) & 1);
   for (int t0 = 0; t0 < NSTEPS; t0 += 2) {
     step(t0, std::integral_constant<int, 0>{});
     step(t0 + 1, std::integral_constant<int, 1>{});
@@ -701,9 +712,28 @@ int launch_stage_impl(cudaStream_t stream, int64_t* launches, const StageArgs<T>
   return NTK_OK;
 }
 
+inline int wpt_override() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NTK_B200_WPT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 template <typename T, int S, int L, int IN, bool NTK, int CIN>
 int launch_stage_epi(cudaStream_t stream, int64_t* launches, int epi, const StageArgs<T>& a) {
   constexpr int WPT = StageCfg<T, S>::WPT;
+  if (sizeof(T) == 4 && S == 32 && L == 3 && wpt_override() == 4) {
+    switch (epi) {
+      case EPI_STORE:
+        return launch_stage_impl<T, S, 4, L, IN, EPI_STORE, NTK, CIN>(stream, launches, a);
+      case EPI_POOL:
+        return launch_stage_impl<T, S, 4, L, IN, EPI_POOL, NTK, CIN>(stream, launches, a);
+      default:
+        return launch_stage_impl<T, S, 4, L, IN, EPI_GAP, NTK, CIN>(stream, launches, a);
+    }
+  }
   switch (epi) {
     case EPI_STORE:
       return launch_stage_impl<T, S, WPT, L, IN, EPI_STORE, NTK, CIN>(stream, launches, a);
@@ -744,7 +774,7 @@ template <typename T>
 int launch_qmaps(cudaStream_t stream, int64_t* launches, int S, const T* src, int src_mode, int n,
                  int C, T in_scale, int L, const FLayer<T>* lp, T* qm) {
   (*launches)++;
-  FLayer<T> z{(T)0, (T)0, (T)0};
+  FLayer<T> z{(T)0, (T)0, (T)0, (T)0};
   FLayer<T> l0 = lp[0], l1 = L > 1 ? lp[1] : z, l2 = L > 2 ? lp[2] : z;
   if (S == 32)
     k_qmaps<T, 32><<<n, 256, 0, stream>>>(src, src_mode, C, in_scale, L, l0, l1, l2, qm);
@@ -779,6 +809,7 @@ void stage_constants(const FusedPlan& plan, size_t s, FLayer<T>* lp, double* nex
     }
     lp[l].coef = (T)coef;
     lp[l].half_ab = (T)half_ab;
+    lp[l].hab2 = (T)(half_ab - coef * 1.57079632679489661923);
     lp[l].bias = (T)st.b2[l];
     if (l + 1 == st.L) *next_alpha_out = alpha_next;
   }
@@ -788,7 +819,7 @@ void stage_constants(const FusedPlan& plan, size_t s, FLayer<T>* lp, double* nex
 // the pair grid is tiled so that the stage boundaries fit in the arena.
 template <typename T>
 int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t* launches,
-               const T* x1, int n1, const T* x2, int n2, bool symmetric, int S0, int /*W*/, int C,
+               StageProfile* prof, const T* x1, int n1, const T* x2, int n2, bool symmetric, int S0, int /*W*/, int C,
                bool want_ntk, T* out_nngp, T* out_ntk, long long ld) {
   const size_t n_st = plan.stages.size() - 1;  // real stages (last entry is the tail marker)
   // ---- 1. q-maps for every stage and both sample sets (self-pair pipeline) --------------
@@ -958,10 +989,22 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
         a.self = 0;
         a.in_scale = in_scale;
         for (int l = 0; l < plan.stages[s].L; ++l) a.lp[l] = lp[l];
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        const bool timed = prof && prof->enabled && s < (size_t)StageProfile::kMaxStages;
+        if (timed) {
+          NTK_CUDA(cudaEventCreate(&ev0));
+          NTK_CUDA(cudaEventCreate(&ev1));
+          NTK_CUDA(cudaEventRecord(ev0, stream));
+        }
         if (want_ntk)
           NTK_TRY((launch_stage<T, true>(stream, launches, S, plan.stages[s].L, s == 0, C, epi, a)));
         else
           NTK_TRY((launch_stage<T, false>(stream, launches, S, plan.stages[s].L, s == 0, C, epi, a)));
+        if (timed) {
+          NTK_CUDA(cudaEventRecord(ev1, stream));
+          prof->pending[s].push_back({ev0, ev1});
+          prof->pending_pairs[s].push_back(P);
+        }
         cur = nxt;
       }
       // Dense tail on the [a1, a2] scalars (linear.py:899-926), then scatter into the result
