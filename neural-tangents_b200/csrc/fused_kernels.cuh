@@ -33,6 +33,10 @@
 namespace ntk {
 
 constexpr int kMaxFusedLayers = 3;
+#ifndef NTK_LAG
+#define NTK_LAG 1
+#endif
+constexpr int LAG = NTK_LAG;  // rows of lag between consecutive fused layers (1 or 2)
 
 enum { IN_FROM_X = 0, IN_LOAD = 1 };
 enum { EPI_STORE = 0, EPI_POOL = 1, EPI_GAP = 2 };
@@ -75,6 +79,23 @@ __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, 
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+
+// 8/16-byte shared-memory load from a 32-bit shared-window address
+template <typename T>
+__device__ __forceinline__ typename std::conditional<sizeof(T) == 4, float2, double2>::type lds_v2(
+    unsigned addr);
+template <>
+__device__ __forceinline__ float2 lds_v2<float>(unsigned addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+template <>
+__device__ __forceinline__ double2 lds_v2<double>(unsigned addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
 
 // R = P0 + mL*Pm + mR*Pp
 template <typename T>
@@ -161,6 +182,22 @@ __device__ __forceinline__ void act_point(double K, double Tn, double q1, double
   To = __dmul_rn(kd, Tn);
 }
 
+// Vertical link masks per row r = ch*S + h of a pair (row-major march order):
+//   .x = vU: rows r-1 and r are linked (h > 0 and h' = (h+ch) mod S did not wrap),
+//   .y = vD: rows r and r+1 are linked.
+// Held in constant memory so that one uniform load replaces ~18 uniform-datapath
+// instructions per layer and step.  Entry 0 / NR+1.. (clamped rows) reuse valid rows.
+__constant__ float2 c_vmask32[32 * 32];
+__constant__ float2 c_vmask16[16 * 16];
+__constant__ float2 c_vmask8[8 * 8];
+
+template <int S>
+__device__ __forceinline__ float2 vmask_at(int r) {
+  if (S == 32) return c_vmask32[r];
+  if (S == 16) return c_vmask16[r];
+  return c_vmask8[r];
+}
+
 template <typename T>
 struct Vec2;
 template <>
@@ -230,10 +267,10 @@ __global__ void k_qmaps(const T* __restrict__ src, int src_mode, int C, T in_sca
 // A *group* of TPP = S*S/WPT threads owns one sample pair and marches over its S*S rows
 // (ch-major: row r = ch*S + h).  NT threads per CTA hold NT/TPP groups.
 // ---------------------------------------------------------------------------------------
-template <int S, int WPT>
+template <int S, int WPT, int SH = 1>
 struct StageGeom {
   static constexpr int TPP = S * S / WPT;               // threads per plane == per group
-  static constexpr int NT = TPP < 128 ? 128 : TPP;      // threads per CTA
+  static constexpr int NT = TPP < 128 ? 128 : TPP * SH; // threads per CTA
   static constexpr int GROUPS = NT / TPP;
   static constexpr int LPG = TPP < 32 ? TPP : 32;       // lanes of one group inside a warp
   static constexpr int NWB = S / WPT;                   // w-blocks
@@ -241,10 +278,12 @@ struct StageGeom {
   static constexpr int NR = S * S;                      // rows per pair
 };
 
-template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN>
-__global__ void __launch_bounds__(StageGeom<S, WPT>::NT)
+// SH > 1: the SH groups of a CTA work on SH consecutive columns of the same Gram row, so the
+// row sample x1[i] and its q-maps are staged once and shared (more resident warps per SM).
+template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN, int SH>
+__global__ void __launch_bounds__(StageGeom<S, WPT, SH>::NT)
 k_stage(const StageArgs<T> a) {
-  using G = StageGeom<S, WPT>;
+  using G = StageGeom<S, WPT, SH>;
   using V2 = typename Vec2<T>::type;
   constexpr int TPP = G::TPP, LPG = G::LPG, NWB = G::NWB, LW = G::LW, NR = G::NR;
   constexpr int SO = S / 2;
@@ -256,14 +295,19 @@ k_stage(const StageArgs<T> a) {
   constexpr int XS2 = IN == IN_FROM_X ? S * S * 4 : 0;
   constexpr int QM = L * S * S * 2;
   constexpr int STG = EPI == EPI_POOL ? 2 * (NTK ? 2 : 1) * S * SP : 0;
-  constexpr int PER_GROUP = XS1 + XS2 + 2 * QM + STG;
+  constexpr bool SHARED_ROW = SH > 1;
+  constexpr int ROW_PART = XS1 + QM;        // x1 sample + its q-maps
+  constexpr int COL_PART = XS2 + QM + STG;  // x2 sample + its q-maps + pool staging
   const int tid = threadIdx.x;
   const int grp = tid / TPP, tg = tid % TPP;
-  T* sm = reinterpret_cast<T*>(smem_raw) + (size_t)grp * PER_GROUP;
-  T* x1s = sm;
-  T* x2s = x1s + XS1;
-  V2* q1m = reinterpret_cast<V2*>(x2s + XS2);
-  V2* q2m = q1m + L * S * S;
+  T* sm_row = reinterpret_cast<T*>(smem_raw) + (SHARED_ROW ? 0 : (size_t)grp * (ROW_PART + COL_PART));
+  T* sm_col = reinterpret_cast<T*>(smem_raw) +
+              (SHARED_ROW ? (size_t)ROW_PART + (size_t)grp * COL_PART
+                          : (size_t)grp * (ROW_PART + COL_PART) + ROW_PART);
+  T* x1s = sm_row;
+  V2* q1m = reinterpret_cast<V2*>(x1s + XS1);
+  T* x2s = sm_col;
+  V2* q2m = reinterpret_cast<V2*>(x2s + XS2);
   T* stg = reinterpret_cast<T*>(q2m + L * S * S);
 
   const int lig = tg % LPG, wig = tg / 32;
@@ -271,34 +315,45 @@ k_stage(const StageArgs<T> a) {
   const int cw = wig * LW + cwsub;
   const int w0 = wblk * WPT;
 
-  long long p = (long long)blockIdx.x * G::GROUPS + grp;
-  const bool live = p < a.P;
-  if (!live) p = a.P - 1;
+  long long p;
+  bool live;
   int si, sj;
-  if (a.self) {
-    si = sj = (int)p;
+  if (SHARED_ROW) {
+    const int bpr = (a.n2 + SH - 1) / SH;  // CTAs per Gram row
+    si = blockIdx.x / bpr;
+    sj = (blockIdx.x % bpr) * SH + grp;
+    live = sj < a.n2;
+    if (!live) sj = a.n2 - 1;
+    p = (long long)si * a.n2 + sj;
   } else {
-    si = (int)(p / a.n2);
-    sj = (int)(p % a.n2);
+    p = (long long)blockIdx.x * G::GROUPS + grp;
+    live = p < a.P;
+    if (!live) p = a.P - 1;
+    if (a.self) {
+      si = sj = (int)p;
+    } else {
+      si = (int)(p / a.n2);
+      sj = (int)(p % a.n2);
+    }
   }
 
   // ---- stage the two samples and their q-maps in shared memory -------------------------
-  if (IN == IN_FROM_X) {
-    const T* g1 = a.x1 + (long long)si * S * S * CIN;
-    const T* g2 = a.x2 + (long long)sj * S * S * CIN;
-    for (int e = tg; e < S * S * CIN; e += TPP) x1s[e] = mul_rn(g1[e], a.in_scale);
-    for (int e = tg; e < S * S; e += TPP) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) x2s[e * 4 + c] = c < CIN ? g2[e * CIN + c] : (T)0;
-    }
-  }
   {
+    // the row part is loaded by the whole CTA when shared, else by its group
+    const int rt = SHARED_ROW ? tid : tg, rn = SHARED_ROW ? G::NT : TPP;
+    if (IN == IN_FROM_X) {
+      const T* g1 = a.x1 + (long long)si * S * S * CIN;
+      const T* g2 = a.x2 + (long long)sj * S * S * CIN;
+      for (int e = rt; e < S * S * CIN; e += rn) x1s[e] = mul_rn(g1[e], a.in_scale);
+      for (int e = tg; e < S * S; e += TPP) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) x2s[e * 4 + c] = c < CIN ? g2[e * CIN + c] : (T)0;
+      }
+    }
     const V2* g1 = reinterpret_cast<const V2*>(a.qm1) + (long long)si * L * S * S;
     const V2* g2 = reinterpret_cast<const V2*>(a.qm2) + (long long)sj * L * S * S;
-    for (int e = tg; e < L * S * S; e += TPP) {
-      q1m[e] = g1[e];
-      q2m[e] = g2[e];
-    }
+    for (int e = rt; e < L * S * S; e += rn) q1m[e] = g1[e];
+    for (int e = tg; e < L * S * S; e += TPP) q2m[e] = g2[e];
   }
   if (TPP > 32)
     __syncthreads();
@@ -316,6 +371,7 @@ k_stage(const StageArgs<T> a) {
   }
 #pragma unroll
   for (int i = 0; i < WPT; ++i) off2[i] = ((w0 + i + cw) % S) * (int)sizeof(V2);
+  const unsigned q2base = (unsigned)__cvta_generic_to_shared(q2m);
 
   // sliding windows: RK[l][slot][i] = horizontally summed input row of layer l.
   // The pipeline runs unconditionally: rows outside [0, NR) are computed from clamped,
@@ -354,6 +410,18 @@ k_stage(const StageArgs<T> a) {
   };
   fetch(0);
 
+  // Layer-to-layer hand-over rows.  With LAG == 2 a layer consumes the row its predecessor
+  // produced in the PREVIOUS step, so the L layer blocks of one step are independent and the
+  // scheduler can overlap their latencies (shuffle -> taps -> sqrt -> polynomial chains).
+  T BK[L][WPT], BT[L][WPT];
+#pragma unroll
+  for (int l = 0; l < L; ++l)
+#pragma unroll
+    for (int i = 0; i < WPT; ++i) {
+      BK[l][i] = (T)0;
+      BT[l][i] = (T)0;
+    }
+
   auto step = [&](const int t, auto par_c) {
     // `par` = t & 1 as a compile-time constant: the ring slot of each layer alternates.
     constexpr int par = decltype(par_c)::value;
@@ -382,67 +450,74 @@ k_stage(const StageArgs<T> a) {
       fetch(t + 1);
     }
 #pragma unroll
-    for (int l = 0; l < L; ++l) {
-      constexpr int dummy = 0;
-      (void)dummy;
-      const int slot = (par + l) & 1;  // == (t - l) & 1, compile-time
+    for (int li = 0; li < L; ++li) {
+      // LAG == 2: last layer first, so BK[l-1] still holds the previous step's row
+      const int l = LAG == 2 ? L - 1 - li : li;
+      const int lm = l == 0 ? 0 : l - 1;
+      const int slot = (par + (LAG == 1 ? l : 0)) & 1;  // == (t - LAG*l) & 1, compile-time
       const bool has_t = NTK && (l > 0 || IN == IN_LOAD);
-      // ---- horizontal 3-tap (register-local + one halo shuffle pair) -------------------
-      T Rk[WPT], Rt[WPT];
+#define INK(i) (l == 0 ? PK[i] : BK[lm][i])
+#define INT(i) (l == 0 ? PT[i] : BT[lm][i])
+      // ---- conv row r_out = t - LAG*l - 1 (clamped outside the image) ---------------------
+      int r_out = t - LAG * l - 1;
+      r_out = r_out < 0 ? 0 : (r_out > NR - 1 ? NR - 1 : r_out);
+      const int ch = r_out / S, h = r_out % S;
+      const int h2 = (h + ch) % S;
+      const float2 vm = vmask_at<S>(r_out);
+      const T vU = (T)vm.x, vD = (T)vm.y;
+      // ---- vertical taps of the two OLD rows first (last use of the oldest row) ----------
+      T tk[WPT], tt[WPT];
+#pragma unroll
+      for (int i = 0; i < WPT; ++i) {
+        tk[i] = fma_t(vU, RK[l][slot][i], RK[l][slot ^ 1][i]);
+        if (has_t) tt[i] = fma_t(vU, RT[l][slot][i], RT[l][slot ^ 1][i]);
+      }
+      // ---- horizontal 3-tap of the new row, written straight into the freed ring slot ----
       {
         T left = (T)0, right = (T)0, leftT = (T)0, rightT = (T)0;
         if (NWB > 1) {
-          left = __shfl_up_sync(0xffffffffu, PK[WPT - 1], LW);
-          right = __shfl_down_sync(0xffffffffu, PK[0], LW);
+          left = __shfl_up_sync(0xffffffffu, INK(WPT - 1), LW);
+          right = __shfl_down_sync(0xffffffffu, INK(0), LW);
           if (has_t) {
-            leftT = __shfl_up_sync(0xffffffffu, PT[WPT - 1], LW);
-            rightT = __shfl_down_sync(0xffffffffu, PT[0], LW);
+            leftT = __shfl_up_sync(0xffffffffu, INT(WPT - 1), LW);
+            rightT = __shfl_down_sync(0xffffffffu, INT(0), LW);
           }
         }
 #pragma unroll
         for (int i = 0; i < WPT; ++i) {
-          Rk[i] = hsum3<T>(i == 0 ? left : PK[i == 0 ? 0 : i - 1], PK[i],
-                           i == WPT - 1 ? right : PK[i == WPT - 1 ? i : i + 1], lk[i], lk[i + 1]);
+          RK[l][slot][i] = hsum3<T>(i == 0 ? left : INK(i == 0 ? 0 : i - 1), INK(i),
+                                    i == WPT - 1 ? right : INK(i == WPT - 1 ? i : i + 1), lk[i],
+                                    lk[i + 1]);
           if (has_t)
-            Rt[i] = hsum3<T>(i == 0 ? leftT : PT[i == 0 ? 0 : i - 1], PT[i],
-                             i == WPT - 1 ? rightT : PT[i == WPT - 1 ? i : i + 1], lk[i], lk[i + 1]);
+            RT[l][slot][i] = hsum3<T>(i == 0 ? leftT : INT(i == 0 ? 0 : i - 1), INT(i),
+                                      i == WPT - 1 ? rightT : INT(i == WPT - 1 ? i : i + 1), lk[i],
+                                      lk[i + 1]);
         }
       }
-      // ---- vertical 3-tap: conv row r_out = t - l - 1 (clamped outside the image) ---------
+      // ---- finish the vertical sum, add the bias, apply the activation ---------------------
       {
-        int r_out = t - l - 1;
-        r_out = r_out < 0 ? 0 : (r_out > NR - 1 ? NR - 1 : r_out);
-        const int ch = r_out / S, h = r_out % S;
-        const int h2 = (h + ch) % S;
-        const T vU = (h > 0 && h2 != 0) ? (T)1 : (T)0;
-        const T vD = (h < S - 1 && h2 != S - 1) ? (T)1 : (T)0;
         const V2* q1r = q1m + (l * S + h) * S + w0;
-        const char* q2r = reinterpret_cast<const char*>(q2m + (l * S + h2) * S);
+        const unsigned q2row = q2base + (unsigned)((l * S + h2) * S * (int)sizeof(V2));
         const T coef = a.lp[l].coef, half_ab = a.lp[l].half_ab, hab2 = a.lp[l].hab2,
                 bias = a.lp[l].bias;
 #pragma unroll
         for (int i = 0; i < WPT; ++i) {
-          const T ck = vsum3<T>(RK[l][slot][i], RK[l][slot ^ 1][i], Rk[i], vU, vD, bias);
+          const T ck = add_rn(fma_t(vD, RK[l][slot][i], tk[i]), bias);
           T ct = (T)0;
           if (NTK) {
             // linear.py:1396-1398 (T0 == 0 for the first layer of a FROM_X stage)
-            ct = has_t ? add_rn(fma_t(vD, Rt[i], fma_t(vU, RT[l][slot][i], RT[l][slot ^ 1][i])), ck)
-                       : ck;
+            ct = has_t ? add_rn(fma_t(vD, RT[l][slot][i], tt[i]), ck) : ck;
           }
           const V2 qa = q1r[i];
-          const V2 qb = *reinterpret_cast<const V2*>(q2r + off2[i]);
-          act_point(ck, ct, qa.x, qa.y, qb.x, qb.y, coef, half_ab, hab2, PK[i], PT[i]);
+          const V2 qb = lds_v2<T>(q2row + off2[i]);
+          act_point(ck, ct, qa.x, qa.y, qb.x, qb.y, coef, half_ab, hab2, BK[l][i], BT[l][i]);
         }
       }
-      // ---- rotate the window: the new row replaces the oldest one -----------------------
-#pragma unroll
-      for (int i = 0; i < WPT; ++i) {
-        RK[l][slot][i] = Rk[i];
-        if (has_t) RT[l][slot][i] = Rt[i];
-      }
+#undef INK
+#undef INT
     }
-    // ---- epilogue on the finished row r_fin = t - L -----------------------------------------
-    const int r_fin = t - L;
+    // ---- epilogue on the finished row of the last layer ---------------------------------------
+    const int r_fin = t - LAG * (L - 1) - 1;
     if (r_fin >= 0 && r_fin < NR) {
       const int ch = r_fin / S, h = r_fin % S;
       if (EPI == EPI_STORE) {
@@ -450,23 +525,23 @@ k_stage(const StageArgs<T> a) {
           const long long base = (p * NR + r_fin) * (long long)(S * S) + (long long)w0 * S + cw;
 #pragma unroll
           for (int i = 0; i < WPT; ++i) {
-            a.outK[base + (long long)i * S] = PK[i];
-            if (NTK) a.outT[base + (long long)i * S] = PT[i];
+            a.outK[base + (long long)i * S] = BK[L - 1][i];
+            if (NTK) a.outT[base + (long long)i * S] = BT[L - 1][i];
           }
         }
       } else if (EPI == EPI_GAP) {
 #pragma unroll
         for (int i = 0; i < WPT; ++i) {
-          gap_k = add_rn(gap_k, PK[i]);
-          if (NTK) gap_t = add_rn(gap_t, PT[i]);
+          gap_k = add_rn(gap_k, BK[L - 1][i]);
+          if (NTK) gap_t = add_rn(gap_t, BT[L - 1][i]);
         }
       } else {  // EPI_POOL: AvgPool 2x2/2 of both members (linear.py:3499-3572)
         T* sK = stg + (r_fin & 1) * ((NTK ? 2 : 1) * S * SP);
         T* sT = sK + S * SP;
 #pragma unroll
         for (int i = 0; i < WPT; ++i) {
-          sK[(w0 + i) * SP + cw] = PK[i];
-          if (NTK) sT[(w0 + i) * SP + cw] = PT[i];
+          sK[(w0 + i) * SP + cw] = BK[L - 1][i];
+          if (NTK) sT[(w0 + i) * SP + cw] = BT[L - 1][i];
         }
         if (TPP > 32)
           __syncthreads();
@@ -500,7 +575,8 @@ k_stage(const StageArgs<T> a) {
     }
   };
 
-  constexpr int NSTEPS = NR + L + ((NR + L) & 1);
+  constexpr int NSTEPS0 = NR + LAG * (L - 1) + 1;
+  constexpr int NSTEPS = NSTEPS0 + (NSTEPS0 & 1);
   for (int t0 = 0; t0 < NSTEPS; t0 += 2) {
     step(t0, std::integral_constant<int, 0>{});
     step(t0 + 1, std::integral_constant<int, 1>{});
@@ -685,37 +761,39 @@ struct StageCfg {
   static constexpr int WPT = sizeof(T) == 4 ? 8 : 4;
 };
 
-template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN>
+template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN, int SH>
 size_t stage_smem_bytes() {
-  using G = StageGeom<S, WPT>;
+  using G = StageGeom<S, WPT, SH>;
   const int xs1 = IN == IN_FROM_X ? S * S * CIN : 0;
   const int xs2 = IN == IN_FROM_X ? S * S * 4 : 0;
   const int qm = L * S * S * 2;
   const int stg = EPI == EPI_POOL ? 2 * (NTK ? 2 : 1) * S * (S + 1) : 0;
+  if (SH > 1) return (size_t)((xs1 + qm) + G::GROUPS * (xs2 + qm + stg)) * sizeof(T);
   return (size_t)G::GROUPS * (xs1 + xs2 + 2 * qm + stg) * sizeof(T);
 }
 
-template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN>
+template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN, int SH = 1>
 int launch_stage_impl(cudaStream_t stream, int64_t* launches, const StageArgs<T>& a) {
-  using G = StageGeom<S, WPT>;
-  auto kern = k_stage<T, S, WPT, L, IN, EPI, NTK, CIN>;
-  const size_t smem = stage_smem_bytes<T, S, WPT, L, IN, EPI, NTK, CIN>();
+  using G = StageGeom<S, WPT, SH>;
+  auto kern = k_stage<T, S, WPT, L, IN, EPI, NTK, CIN, SH>;
+  const size_t smem = stage_smem_bytes<T, S, WPT, L, IN, EPI, NTK, CIN, SH>();
   static thread_local bool configured = false;
   if (!configured) {
     NTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  const long long blocks = (a.P + G::GROUPS - 1) / G::GROUPS;
+  long long blocks = (a.P + G::GROUPS - 1) / G::GROUPS;
+  if (SH > 1) blocks = (a.P / a.n2) * ((a.n2 + SH - 1) / SH);
   (*launches)++;
   kern<<<(unsigned)blocks, G::NT, smem, stream>>>(a);
   NTK_CUDA(cudaGetLastError());
   return NTK_OK;
 }
 
-inline int wpt_override() {
+inline int share_override() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("NTK_B200_WPT");
+    const char* e = getenv("NTK_B200_SHARE");
     v = e ? atoi(e) : 0;
   }
   return v;
@@ -724,14 +802,18 @@ inline int wpt_override() {
 template <typename T, int S, int L, int IN, bool NTK, int CIN>
 int launch_stage_epi(cudaStream_t stream, int64_t* launches, int epi, const StageArgs<T>& a) {
   constexpr int WPT = StageCfg<T, S>::WPT;
-  if (sizeof(T) == 4 && S == 32 && L == 3 && wpt_override() == 4) {
+  // Optional (NTK_B200_SHARE=3): three column samples share one row sample per CTA, i.e. 12
+  // instead of 8 resident warps per SM at 32x32 fp32.  Measured on B200: no gain (the issue
+  // rate stays ~73 %, profiles/README.md), so independent 128-thread CTAs are the default.
+  constexpr int SHC = (sizeof(T) == 4 && S == 32) ? 3 : 1;
+  if (SHC > 1 && !a.self && a.n2 >= SHC && share_override() == 3) {
     switch (epi) {
       case EPI_STORE:
-        return launch_stage_impl<T, S, 4, L, IN, EPI_STORE, NTK, CIN>(stream, launches, a);
+        return launch_stage_impl<T, S, WPT, L, IN, EPI_STORE, NTK, CIN, SHC>(stream, launches, a);
       case EPI_POOL:
-        return launch_stage_impl<T, S, 4, L, IN, EPI_POOL, NTK, CIN>(stream, launches, a);
+        return launch_stage_impl<T, S, WPT, L, IN, EPI_POOL, NTK, CIN, SHC>(stream, launches, a);
       default:
-        return launch_stage_impl<T, S, 4, L, IN, EPI_GAP, NTK, CIN>(stream, launches, a);
+        return launch_stage_impl<T, S, WPT, L, IN, EPI_GAP, NTK, CIN, SHC>(stream, launches, a);
     }
   }
   switch (epi) {
@@ -786,7 +868,23 @@ int launch_qmaps(cudaStream_t stream, int64_t* launches, int S, const T* src, in
   return NTK_OK;
 }
 
-inline int fused_configure_device() { return NTK_OK; }
+// Uploads the vertical link masks to the current device (once per context).
+inline int fused_configure_device() {
+  for (int S : {32, 16, 8}) {
+    std::vector<float2> m((size_t)S * S);
+    for (int ch = 0; ch < S; ++ch)
+      for (int h = 0; h < S; ++h) {
+        const int h2 = (h + ch) % S;
+        m[(size_t)ch * S + h].x = (h > 0 && h2 != 0) ? 1.f : 0.f;
+        m[(size_t)ch * S + h].y = (h < S - 1 && h2 != S - 1) ? 1.f : 0.f;
+      }
+    const size_t bytes = m.size() * sizeof(float2);
+    if (S == 32) NTK_CUDA(cudaMemcpyToSymbol(c_vmask32, m.data(), bytes));
+    if (S == 16) NTK_CUDA(cudaMemcpyToSymbol(c_vmask16, m.data(), bytes));
+    if (S == 8) NTK_CUDA(cudaMemcpyToSymbol(c_vmask8, m.data(), bytes));
+  }
+  return NTK_OK;
+}
 
 // Per-stage layer constants: fold the NEXT conv's alpha = W^2/9 into this layer's ABRelu.
 template <typename T>
