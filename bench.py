@@ -241,8 +241,11 @@ def run_ours(args):
   ctx.set_profiling(False)
 
   # end to end through the public API: HOST buffers in, HOST results out (nt.batch -> C-ABI)
-  batched = nt.batch(kernel_fn, batch_size=args.e2e_batch, device_count=0)
-  batched(x1_h[:args.e2e_batch], x2_h[:args.e2e_batch], ('nngp', 'ntk'))
+  import math
+  g_ = math.gcd(b1, b2)
+  e2e_bs = max(d for d in range(1, min(args.e2e_batch, g_) + 1) if g_ % d == 0)
+  batched = nt.batch(kernel_fn, batch_size=e2e_bs, device_count=0)
+  batched(x1_h[:e2e_bs], x2_h[:e2e_bs], ('nngp', 'ntk'))
   barrier()
   t0 = time.perf_counter()
   for _ in range(args.steps):
