@@ -114,7 +114,7 @@ __device__ __forceinline__ float sqrt_fast(float x) {
   return r;
 }
 __device__ __forceinline__ float rsqrt_t(float x) { return rsqrtf(x); }
-__device__ __forceinline__ double rsqrt_t(double x) { return 1.0 / sqrt(x); }
+__device__ __forceinline__ double rsqrt_t(double x) { return 1.0 / sqrt(x); }  // q-maps only (cold)
 
 // acos(c)/sqrt(1-c^2) on [0,1], degree-8 fit (max abs error 1.0e-7 before rounding).
 __device__ __forceinline__ float acos_over_sin(float c) {
@@ -146,9 +146,8 @@ __device__ __forceinline__ float kd_zero_angle(float coef, float half_ab, float 
   return __fmaf_rn(coef, kHalfPiF, hab2);
 }
 __device__ __forceinline__ double kd_zero_angle(double coef, double half_ab, double hab2) {
-  (void)coef;
-  (void)hab2;
-  return half_ab;
+  (void)half_ab;
+  return __fma_rn(coef, 1.5707963267948966, hab2);
 }
 
 __device__ __forceinline__ void act_point(float K, float Tn, float q1, float b1, float q2, float b2,
@@ -168,16 +167,61 @@ __device__ __forceinline__ void act_point(float K, float Tn, float q1, float b1,
   To = __fmul_rn(kd, Tn);
 }
 
+// fp64: same structure with a degree-20 fit of G (|err| < 8e-16) and a Newton square root
+// seeded by MUFU.RSQ64H -- about 45 DP instructions per element instead of ~120 for
+// sqrt + atan2.
+__device__ __forceinline__ double acos_over_sin(double c) {
+  double g = 0.00011498440214312142;
+  g = __fma_rn(g, c, -0.0013425118048028357);
+  g = __fma_rn(g, c, 0.0074255005353718135);
+  g = __fma_rn(g, c, -0.02601071230644528);
+  g = __fma_rn(g, c, 0.06524925918867551);
+  g = __fma_rn(g, c, -0.12612943586868636);
+  g = __fma_rn(g, c, 0.19838900896440054);
+  g = __fma_rn(g, c, -0.2662737577356398);
+  g = __fma_rn(g, c, 0.31902721592859684);
+  g = __fma_rn(g, c, -0.35579825919378716);
+  g = __fma_rn(g, c, 0.3823450610436574);
+  g = __fma_rn(g, c, -0.40531257550488764);
+  g = __fma_rn(g, c, 0.4293159767563122);
+  g = __fma_rn(g, c, -0.45711379217247317);
+  g = __fma_rn(g, c, 0.49087069104128306);
+  g = __fma_rn(g, c, -0.5333330865934092);
+  g = __fma_rn(g, c, 0.5890486093468758);
+  g = __fma_rn(g, c, -0.6666666662100986);
+  g = __fma_rn(g, c, 0.7853981633879067);
+  g = __fma_rn(g, c, -0.9999999999998898);
+  g = __fma_rn(g, c, 1.5707963267948963);
+  return g;
+}
+
+// sqrt(x) for x >= 0 to ~1 ulp: rsqrt seed + two coupled Newton steps (x == 0 -> ~1e-150).
+__device__ __forceinline__ double sqrt_fast(double x) {
+  x = fmax(x, 1e-300);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = __dmul_rn(x, y), h = __dmul_rn(0.5, y);
+  double r = __fma_rn(-g, h, 0.5);
+  g = __fma_rn(g, r, g);
+  h = __fma_rn(h, r, h);
+  r = __fma_rn(-g, h, 0.5);
+  g = __fma_rn(g, r, g);
+  h = __fma_rn(h, r, h);
+  r = __fma_rn(-g, h, 0.5);
+  return __fma_rn(g, r, g);
+}
+
 __device__ __forceinline__ void act_point(double K, double Tn, double q1, double b1, double q2,
                                           double b2, double coef, double half_ab, double hab2,
                                           double& Ko, double& To) {
-  (void)b1;
-  (void)b2;
-  (void)hab2;
+  (void)half_ab;
   const double p = __dmul_rn(q1, q2);
-  const double s = sqrt(fmax(__dsub_rn(p, __dmul_rn(K, K)), 0.0));
-  const double theta = (s == 0.0 && K == 0.0) ? 1.5707963267948966 : atan2(s, K);
-  const double kd = __fma_rn(-coef, theta, half_ab);
+  const double rb = __dmul_rn(b1, b2);
+  const double s = sqrt_fast(fabs(__dsub_rn(p, __dmul_rn(K, K))));
+  const double sn = __dmul_rn(s, rb);
+  const double c = __dmul_rn(K, rb);
+  const double u = __fma_rn(-sn, acos_over_sin(fmin(fabs(c), 1.0)), 1.5707963267948966);
+  const double kd = __fma_rn(coef, copysign(u, c), hab2);
   Ko = __fma_rn(kd, K, __dmul_rn(coef, s));
   To = __dmul_rn(kd, Tn);
 }
