@@ -186,3 +186,95 @@ def test_reference_errors_on_gpu(nt):
                      stax.FanInSum())
   with pytest.raises(ValueError, match='shapes should be equal'):  # branching.py:71-75
     mism[2](x, None, 'nngp')
+
+
+def test_fused_vs_per_layer_path_full_size(nt):
+  """The fused kernels and the one-kernel-per-layer path are independent implementations;
+  at BASELINE's Myrtle-10 / 32x32x3 size they must agree (fp32 5e-5, fp64 1e-11), incl. ragged
+  block shapes that exercise partial CTA groups and tile edges."""
+  x1 = np.random.default_rng(51).standard_normal((7, 32, 32, 3)).astype(np.float32)
+  x2 = np.random.default_rng(52).standard_normal((5, 32, 32, 3)).astype(np.float32)
+  _, _, kernel_fn = cases.build(cases.myrtle(10), nt.stax)
+  for x64, tol in ((False, 5e-5), (True, 1e-11)):
+    nt.config.update('enable_x64', x64)
+    nt.config.update('disable_fusion', False)
+    a = kernel_fn(x1, x2, ('nngp', 'ntk'))
+    nt.config.update('disable_fusion', True)
+    b = kernel_fn(x1, x2, ('nngp', 'ntk'))
+    nt.config.update('disable_fusion', False)
+    np.testing.assert_allclose(a.nngp, b.nngp, rtol=tol)
+    np.testing.assert_allclose(a.ntk, b.ntk, rtol=tol)
+
+
+def test_gram_properties_at_scale(nt):
+  """Size-independent properties on a 96x96 Myrtle-10 block (fp32): symmetry of K(x, x),
+  positive semi-definiteness, block consistency (a sub-block equals the same entries of the
+  large block), and exact agreement of duplicated columns."""
+  nt.config.update('enable_x64', False)
+  _, _, kernel_fn = cases.build(cases.myrtle(10), nt.stax)
+  x = np.random.default_rng(61).standard_normal((96, 32, 32, 3)).astype(np.float32)
+  k = kernel_fn(x, None, ('nngp', 'ntk'))
+  for m in (k.nngp, k.ntk):
+    np.testing.assert_allclose(m, m.T, rtol=2e-5)
+    w = np.linalg.eigvalsh((m.astype(np.float64) + m.T.astype(np.float64)) / 2)
+    assert w.min() > -1e-4 * w.max()
+  sub = kernel_fn(x[10:17], x[40:45], ('nngp', 'ntk'))
+  np.testing.assert_allclose(sub.nngp, k.nngp[10:17, 40:45], rtol=2e-5)
+  np.testing.assert_allclose(sub.ntk, k.ntk[10:17, 40:45], rtol=2e-5)
+  x2 = np.concatenate([x[:4], x[:4]])        # duplicated columns give bit-identical entries
+  d = kernel_fn(x[20:23], x2, ('nngp', 'ntk'))
+  np.testing.assert_array_equal(d.nngp[:, :4], d.nngp[:, 4:])
+  np.testing.assert_array_equal(d.ntk[:, :4], d.ntk[:, 4:])
+
+
+def test_edge_shapes_and_fallbacks(nt):
+  """n = 1, non-square images / C != 3 / 28x28 (per-layer fallback), nngp-only fused call."""
+  from oracle import ntk_oracle as O
+  nt.config.update('enable_x64', True)
+  spec = ('serial', [cases.conv(), cases.RELU, cases.conv(), cases.RELU, ('gap',), ('dense', 1.3, 0.1)])
+  _, _, kernel_fn = cases.build(spec, nt.stax)
+  for shape1, shape2 in (((1, 8, 8, 3), (1, 8, 8, 3)), ((2, 6, 10, 3), (3, 6, 10, 3)),
+                         ((2, 8, 8, 1), (1, 8, 8, 1)), ((1, 28, 28, 1), (2, 28, 28, 1)),
+                         ((3, 16, 16, 3), (2, 16, 16, 3))):
+    x1 = np.random.default_rng(71).standard_normal(shape1).astype(np.float32)
+    x2 = np.random.default_rng(72).standard_normal(shape2).astype(np.float32)
+    ref = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'))
+    out = kernel_fn(x1, x2, ('nngp', 'ntk'))
+    np.testing.assert_allclose(out.nngp, ref[0], rtol=1e-10)
+    np.testing.assert_allclose(out.ntk, ref[1], rtol=1e-10)
+    np.testing.assert_allclose(kernel_fn(x1, x2, 'nngp'), ref[0], rtol=1e-10)
+  nt.config.update('enable_x64', False)
+
+
+def test_deep_stack_chunking(nt):
+  """7 Conv+Relu layers at one resolution are cut into fused chunks 3+3+1 with STORE/LOAD
+  boundaries in the sheared layout (README.md:370-386 style net)."""
+  from oracle import ntk_oracle as O
+  spec = ('serial', [cases.conv(W=1.4, b=0.1), cases.RELU] * 7 + [('gap',), ('dense', 1., 0.)])
+  _, _, kernel_fn = cases.build(spec, nt.stax)
+  x1 = np.random.default_rng(81).standard_normal((3, 16, 16, 3)).astype(np.float32)
+  x2 = np.random.default_rng(82).standard_normal((2, 16, 16, 3)).astype(np.float32)
+  ref = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'))
+  for x64 in (False, True):
+    nt.config.update('enable_x64', x64)
+    out = kernel_fn(x1, x2, ('nngp', 'ntk'))
+    np.testing.assert_allclose(out.nngp, ref[0], rtol=RTOL[x64])
+    np.testing.assert_allclose(out.ntk, ref[1], rtol=RTOL[x64])
+  nt.config.update('enable_x64', False)
+
+
+def test_batch_multi_device_threads(nt):
+  """nt.batch(device_count=D): one host thread + one context per GPU (skips on 1 GPU)."""
+  from neural_tangents_b200 import _lib
+  if _lib.device_count() < 2:
+    pytest.skip('needs 2 GPUs')
+  nt.config.update('enable_x64', False)
+  _, _, kernel_fn = cases.build(cases.myrtle(5), nt.stax)
+  x1 = np.random.default_rng(91).standard_normal((8, 32, 32, 3)).astype(np.float32)
+  x2 = np.random.default_rng(92).standard_normal((4, 32, 32, 3)).astype(np.float32)
+  full = kernel_fn(x1, x2, ('nngp', 'ntk'))
+  out = nt.batch(kernel_fn, batch_size=2, device_count=2)(x1, x2, ('nngp', 'ntk'))
+  np.testing.assert_array_equal(out.nngp, full.nngp)
+  np.testing.assert_array_equal(out.ntk, full.ntk)
+  with pytest.raises(ValueError, match='too small|must divide'):
+    nt.batch(kernel_fn, batch_size=2, device_count=2)(x1[:5], x2, 'nngp')
