@@ -28,6 +28,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "gemm_kernels.cuh"
 #include "generic_kernels.cuh"
 
 namespace ntk {
@@ -1169,17 +1170,19 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
   return NTK_OK;
 }
 
-// FCN input Gram x1 x2^T / d  (requirements.py:585-638 for 2-D inputs).
+// FCN input Gram x1 x2^T / d  (requirements.py:585-638 for 2-D inputs): tensor cores
+// (gemm_kernels.cuh) unless the feature dimension is tiny or NTK_B200_NO_TC is set.
 template <typename T>
 int fcn_input_gram(bool dry, cudaStream_t stream, int64_t* launches, const T* x1, int t1, const T* x2,
                    int t2, int C, T* out) {
   (*launches)++;
-  if (!dry) {
-    const long long P = (long long)t1 * t2;
-    k_rowdot<T><<<grid_for(P * 32), kThreads, 0, stream>>>(x1, x2, out, P, PairMap{t2, 0}, C,
-                                                           (T)(1.0 / (double)C));
-    NTK_CUDA(cudaGetLastError());
-  }
+  if (dry) return NTK_OK;
+  static const bool no_tc = getenv("NTK_B200_NO_TC") != nullptr;
+  if (C >= 16 && !no_tc) return launch_gram_tc(stream, x1, t1, x2, t2, C, out);
+  const long long P = (long long)t1 * t2;
+  k_rowdot<T><<<grid_for(P * 32), kThreads, 0, stream>>>(x1, x2, out, P, PairMap{t2, 0}, C,
+                                                         (T)(1.0 / (double)C));
+  NTK_CUDA(cudaGetLastError());
   return NTK_OK;
 }
 

@@ -278,3 +278,27 @@ def test_batch_multi_device_threads(nt):
   np.testing.assert_array_equal(out.ntk, full.ntk)
   with pytest.raises(ValueError, match='too small|must divide'):
     nt.batch(kernel_fn, batch_size=2, device_count=2)(x1[:5], x2, 'nngp')
+
+
+def test_fcn_config1_tensor_core_gram(nt):
+  """BASELINE configs[0]: Dense-Relu x3 FCN, 1000 x 1000, 784-d.  The input Gram runs on the
+  tensor cores (tcgen05 kind::tf32 with the 3xTF32 split in fp32, DMMA in fp64); ragged sizes
+  (1000 and 784 are not tile multiples) exercise the zero-padded edges."""
+  from oracle import ntk_oracle as O
+  spec = cases.fcn(3)
+  x1 = np.random.default_rng(101).standard_normal((1000, 784)).astype(np.float32)
+  x2 = np.random.default_rng(102).standard_normal((1000, 784)).astype(np.float32)
+  ref = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'))
+  _, _, kernel_fn = cases.build(spec, nt.stax)
+  for x64 in (False, True):
+    nt.config.update('enable_x64', x64)
+    out = kernel_fn(x1, x2, ('nngp', 'ntk'))
+    np.testing.assert_allclose(out.nngp, ref[0], rtol=RTOL[x64])
+    np.testing.assert_allclose(out.ntk, ref[1], rtol=RTOL[x64])
+  # the split must recover (almost) full fp32 accuracy of the raw Gram: a single TF32 pass would
+  # be off by ~1e-3 relative to the Gram scale, 3xTF32 stays below 2e-6
+  nt.config.update('enable_x64', False)
+  _, _, dense = nt.stax.serial(nt.stax.Dense(1, 1., None))
+  g = dense(x1[:300], x2[:200], 'nngp')
+  g64 = x1[:300].astype(np.float64) @ x2[:200].astype(np.float64).T / 784
+  assert np.abs(g - g64).max() < 2e-6 * np.abs(g64).max()
