@@ -37,6 +37,30 @@ WORKLOADS = {
 }
 
 
+def stage_elements(depth, per_layer):
+  """Algorithmic elements (K and T, read + written) per pair for every stage kernel launch of the
+  cross-pair pass, in launch order (SURVEY §8d traffic model)."""
+  f = {5: [2, 1, 1], 7: [2, 2, 2], 10: [3, 3, 3]}[depth]
+  res = [E32, E16, E8]
+  out = []
+  for g, (n_layers, e) in enumerate(zip(f, res)):
+    e_next = res[g + 1] if g + 1 < 3 else 0          # after the pool (last group: 2 scalars)
+    chunks = [1] * n_layers if per_layer else [n_layers]
+    done = 0
+    for c in chunks:
+      first = g == 0 and done == 0
+      last = done + c == n_layers
+      if per_layer:
+        rd = 0 if first else 2 * e
+        wr = 2 * (e_next if last else e)
+        out.append(rd + wr)
+      else:                                            # the whole group in one launch
+        rd = 0 if first else 2 * e
+        out.append(rd + (n_layers - 1) * 4 * e + 2 * e_next)
+      done += c
+  return out
+
+
 def peaks():
   path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
   if os.path.exists(path):
@@ -199,7 +223,7 @@ def run_ours(args):
   out_d = torch.empty((2, b1, b2), dtype=t_dt, device=dev)          # this rank's nngp / ntk slab
   gath_d = torch.empty((world, 2, b1, b2), dtype=t_dt, device=dev) if world > 1 else None
   flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
-  flags = _lib.FLAG_NO_FUSION if args.no_fusion else 0
+  flags = (_lib.FLAG_NO_FUSION if args.no_fusion else 0) | (_lib.FLAG_PER_LAYER if args.per_layer else 0)
 
   def step_device():
     # everything is ordered on the context stream (NCCL syncs with the current stream)
@@ -238,6 +262,13 @@ def run_ours(args):
   ms_dev = sum(s.elapsed_time(e) for s, e in evs)
   launches = ctx.launch_count - launches0
   st0_ms, st0_n, st0_pairs = ctx.profile(0) if not args.no_fusion else (0.0, 0, 0)
+  per_stage = []
+  if not args.no_fusion:
+    elems = stage_elements(depth, args.per_layer)
+    for si, el in enumerate(elems):
+      ms_, n_, pr_ = ctx.profile(si)
+      if n_ > 0:
+        per_stage.append({'stage': si, 'ms_per_launch': ms_ / n_, 'algorithmic_GBps': pr_ * el * sz / (ms_ * 1e-3) / 1e9})
   ctx.set_profiling(False)
 
   # end to end through the public API: HOST buffers in, HOST results out (nt.batch -> C-ABI)
@@ -285,7 +316,14 @@ def run_ours(args):
         'share_of_step': st0_ms / ms_dev,
         'traffic': None if tpp is None else tpp * st0_pairs // st0_n,
         'whole_net_achieved': b1 * b2 * args.steps * elems_net * sz / (ms_dev * 1e-3) / 1e9,
+        'per_stage': per_stage,
     })
+    if args.per_layer and per_stage:
+      # one layer per launch: the dominant kernel is the slowest stage; its traffic is real
+      dom = max(per_stage, key=lambda d_: d_['ms_per_launch'])
+      roof.update({'kernel': 'k_stage<S=32,L=1,LOAD,STORE> (stage %d, one Conv+Relu layer)' % dom['stage'],
+                   'achieved': dom['algorithmic_GBps'], 'frac': dom['algorithmic_GBps'] / pk['hbm_gbs'],
+                   'avg_launch_ms': dom['ms_per_launch'], 'traffic': None})
     roof['whole_net_frac'] = roof['whole_net_achieved'] / pk['hbm_gbs']
   else:
     achieved = b1 * b2 * args.steps * elems_net * sz / (ms_dev * 1e-3) / 1e9
@@ -298,7 +336,7 @@ def run_ours(args):
       'data': 'synthetic',
       'config': {'workload': f'{args.workload}_32x32x3_nngp+ntk', 'block_per_gpu': [b1, b2],
                  'parallelism': f'x1-row partition over {world} rank(s), x2 broadcast, slabs all-gathered',
-                 'l2': 'flushed (256 MiB write) between timed steps', 'fusion': not args.no_fusion},
+                 'l2': 'flushed (256 MiB write) between timed steps', 'fusion': ('per-layer stencil kernels' if args.per_layer else not args.no_fusion)},
       'e2e': {'value': e2e_value, 'unit': 'entries/s',
               'h2d_bytes_per_step': int(x1_h.nbytes + x2_h.nbytes) * world,
               'd2h_bytes_per_step': int(2 * b1 * b2 * sz) * world},
@@ -335,6 +373,8 @@ def main():
   ap.add_argument('--ref-cols', type=int, default=4)
   ap.add_argument('--no-fusion', action='store_true')
   ap.add_argument('--no-cpu', action='store_true')
+  ap.add_argument('--per-layer', action='store_true',
+                  help='one Conv+Relu layer per kernel launch (one HBM round trip per layer)')
   args = ap.parse_args()
   if args.impl == 'reference':
     run_reference(args)

@@ -105,7 +105,10 @@ typedef struct ntk_state {
 
 /* flags for the gram entry points */
 #define NTK_FLAG_NTK 1u          /* compute ntk as well as nngp                */
-#define NTK_FLAG_NO_FUSION 2u    /* force the one-kernel-per-layer path        */
+#define NTK_FLAG_NO_FUSION 2u    /* force the general one-kernel-per-op path   */
+#define NTK_FLAG_PER_LAYER 8u    /* stencil kernels, but ONE Conv+ABRelu layer per
+                                    launch: every layer makes one HBM round trip
+                                    (the traffic model of the roofline)          */
 #define NTK_FLAG_WANT_COV 4u     /* also return cov1 / cov2                    */
 
 typedef struct ntk_program ntk_program_t;

@@ -21,6 +21,7 @@ struct ntk_program {
   int out_slot = 0;
   std::vector<int> last_use;  // per slot: index of the last op reading it (or n_ops if output)
   FusedPlan fused;            // fast-path plan (fused_kernels.cuh); empty if not matched
+  FusedPlan per_layer;        // same kernels, one layer per launch (NTK_FLAG_PER_LAYER)
 };
 
 struct ntk_context {
@@ -632,7 +633,8 @@ int gram_device_t(ntk_context* ctx, const ntk_program* prog, const T* x1, int n1
   if (!(flags & NTK_FLAG_NO_FUSION) && prog->fused.ok && H > 0 &&
       fused_supported<T>(prog->fused, H, W, C) && !out.cov1 && !out.cov2) {
     ctx->arena.reset(ctx->ws, ctx->ws_bytes, false);
-    int st = fused_gram<T>(prog->fused, ctx->arena, ctx->stream, &env.launches, &ctx->prof, x1, n1, x2, n2,
+    const FusedPlan& plan = (flags & NTK_FLAG_PER_LAYER) ? prog->per_layer : prog->fused;
+    int st = fused_gram<T>(plan, ctx->arena, ctx->stream, &env.launches, &ctx->prof, x1, n1, x2, n2,
                            symmetric, H, W, C, want_ntk, (T*)out.nngp, (T*)out.ntk, out.ld);
     ctx->launches += env.launches;
     return st;
@@ -738,6 +740,7 @@ int ntk_program_create(const ntk_op_t* ops, int32_t n_ops, int32_t n_slots, int3
   p->out_slot = out_slot;
   NTK_TRY(validate_program(*p));
   p->fused = plan_fused(p->ops, p->n_slots, p->out_slot);
+  p->per_layer = plan_fused(p->ops, p->n_slots, p->out_slot, 1);
   *out = p.release();
   return NTK_OK;
 }

@@ -702,7 +702,8 @@ struct FusedPlan {
 };
 
 // Recognises:  ([Conv3x3/1/SAME, ABRelu]+  AvgPool2x2/2?)+  (AvgPool2x2/2)* (GAP | Flatten@1x1)  Dense*
-inline FusedPlan plan_fused(const std::vector<ntk_op_t>& ops, int n_slots, int out_slot) {
+inline FusedPlan plan_fused(const std::vector<ntk_op_t>& ops, int n_slots, int out_slot,
+                            int max_layers = kMaxFusedLayers) {
   FusedPlan plan;
   const int n = (int)ops.size();
   // must be a linear chain ending in out_slot
@@ -734,9 +735,9 @@ inline FusedPlan plan_fused(const std::vector<ntk_op_t>& ops, int n_slots, int o
       run.push_back({k, k + 1});
       k += 2;
     }
-    for (size_t s = 0; s < run.size(); s += kMaxFusedLayers) {
+    for (size_t s = 0; s < run.size(); s += max_layers) {
       FusedStage st;
-      st.L = (int)std::min<size_t>(kMaxFusedLayers, run.size() - s);
+      st.L = (int)std::min<size_t>(max_layers, run.size() - s);
       for (int l = 0; l < st.L; ++l) {
         const ntk_op_t& c = ops[run[s + l].first];
         const ntk_op_t& act = ops[run[s + l].second];
