@@ -106,6 +106,9 @@ typedef struct ntk_state {
 /* flags for the gram entry points */
 #define NTK_FLAG_NTK 1u          /* compute ntk as well as nngp                */
 #define NTK_FLAG_NO_FUSION 2u    /* force the general one-kernel-per-op path   */
+#define NTK_FLAG_FULL_SQUARE 16u /* x2 == NULL: compute all n x n entries like the
+                                    reference (`_src/batching.py:370`) instead of
+                                    the upper triangle + mirror                  */
 #define NTK_FLAG_PER_LAYER 8u    /* stencil kernels, but ONE Conv+ABRelu layer per
                                     launch: every layer makes one HBM round trip
                                     (the traffic model of the roofline)          */

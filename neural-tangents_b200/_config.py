@@ -19,11 +19,13 @@ class _Config:
     self.disable_fusion = os.environ.get('NT_B200_NO_FUSION', '0') not in ('0', '')
     # stencil kernels with one Conv+ABRelu layer per launch (one HBM round trip per layer)
     self.per_layer = os.environ.get('NT_B200_PER_LAYER', '0') not in ('0', '')
+    # x2=None: compute the full n x n square like the reference instead of triangle + mirror
+    self.full_square = os.environ.get('NT_B200_FULL_SQUARE', '0') not in ('0', '')
 
   def update(self, name, value):
     if name in ('enable_x64', 'jax_enable_x64'):
       self.enable_x64 = bool(value)
-    elif name in ('device', 'workspace_bytes', 'disable_fusion', 'per_layer'):
+    elif name in ('device', 'workspace_bytes', 'disable_fusion', 'per_layer', 'full_square'):
       setattr(self, name, type(getattr(self, name))(value))
     else:
       raise AttributeError(f'unknown config option {name!r}')

@@ -16,7 +16,7 @@ NTK_F32, NTK_F64 = 0, 1
 OP_DENSE, OP_CONV, OP_ABRELU, OP_ERF, OP_AVGPOOL, OP_GAP, OP_FLATTEN, OP_FANINSUM, OP_IDENTITY = range(1, 10)
 PAD = {'VALID': 0, 'SAME': 1, 'CIRCULAR': 2}
 NTK_NONE, NTK_ZERO, NTK_TENSOR = 0, 1, 2
-FLAG_NTK, FLAG_NO_FUSION, FLAG_WANT_COV, FLAG_PER_LAYER = 1, 2, 4, 8
+FLAG_NTK, FLAG_NO_FUSION, FLAG_WANT_COV, FLAG_PER_LAYER, FLAG_FULL_SQUARE = 1, 2, 4, 8, 16
 
 E_INVAL, E_CUDA, E_NOMEM, E_NOTGAUSSIAN, E_UNSUPPORTED, E_SHAPE = -1, -2, -3, -4, -5, -6
 

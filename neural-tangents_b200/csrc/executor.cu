@@ -635,7 +635,8 @@ int gram_device_t(ntk_context* ctx, const ntk_program* prog, const T* x1, int n1
     ctx->arena.reset(ctx->ws, ctx->ws_bytes, false);
     const FusedPlan& plan = (flags & NTK_FLAG_PER_LAYER) ? prog->per_layer : prog->fused;
     int st = fused_gram<T>(plan, ctx->arena, ctx->stream, &env.launches, &ctx->prof, x1, n1, x2, n2,
-                           symmetric, H, W, C, want_ntk, (T*)out.nngp, (T*)out.ntk, out.ld);
+                           symmetric, H, W, C, want_ntk, (T*)out.nngp, (T*)out.ntk, out.ld,
+                           (flags & NTK_FLAG_FULL_SQUARE) != 0);
     ctx->launches += env.launches;
     return st;
   }

@@ -65,10 +65,29 @@ struct StageArgs {
   long long P;
   int n2;         // pair p -> (p / n2, p % n2), or (p, p) when self
   int self;
+  int tri;        // pairs enumerate the upper triangle (j >= i) of an n2 x n2 block, row-major
+  int col_start;  // marched ch columns: (col_start + i) mod S, i < col_count  (S for all)
+  int col_count;
   T in_scale;     // FROM_X: alpha_1 / C folded into x1
   T epi_scale;    // POOL: alpha_next/16; GAP: 1/S^4; STORE: unused (folded in coef)
   FLayer<T> lp[kMaxFusedLayers];
 };
+
+// Upper-triangular pair enumeration of a W x W block: row l holds the W - l pairs (l, l..W-1)
+// and starts at prefix(l) = l*W - l(l-1)/2.  Returns l and the offset inside the row.
+__host__ __device__ __forceinline__ long long tri_prefix(long long l, long long W) {
+  return l * W - l * (l - 1) / 2;
+}
+__device__ __forceinline__ void tri_unrank(long long p, long long W, int& l, int& off) {
+  const double b = 2.0 * (double)W + 1.0;
+  long long li = (long long)((b - sqrt(b * b - 8.0 * (double)p)) * 0.5);
+  if (li < 0) li = 0;
+  if (li > W - 1) li = W - 1;
+  while (li > 0 && tri_prefix(li, W) > p) --li;
+  while (li + 1 < W && tri_prefix(li + 1, W) <= p) ++li;
+  l = (int)li;
+  off = (int)(p - tri_prefix(li, W));
+}
 
 // ---------------------------------------------------------------------------------------
 // arithmetic shared by the stage kernel and the q-map kernels (identical rounding, so a
@@ -325,7 +344,9 @@ struct StageGeom {
 
 // SH > 1: the SH groups of a CTA work on SH consecutive columns of the same Gram row, so the
 // row sample x1[i] and its q-maps are staged once and shared (more resident warps per SM).
-template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN, int SH>
+// RC ("runtime columns"): march only the ch columns [col_start, col_start + col_count) -- used by
+// the self-pair pipeline; the cross-pair kernels keep compile-time trip counts.
+template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN, int SH, bool RC>
 __global__ void __launch_bounds__(StageGeom<S, WPT, SH>::NT)
 k_stage(const StageArgs<T> a) {
   using G = StageGeom<S, WPT, SH>;
@@ -376,6 +397,10 @@ k_stage(const StageArgs<T> a) {
     if (!live) p = a.P - 1;
     if (a.self) {
       si = sj = (int)p;
+    } else if (a.tri) {
+      int off;
+      tri_unrank(p, a.n2, si, off);
+      sj = si + off;
     } else {
       si = (int)(p / a.n2);
       sj = (int)(p % a.n2);
@@ -434,6 +459,12 @@ k_stage(const StageArgs<T> a) {
         RT[l][sl][i] = (T)0;
       }
 
+  // Rows marched: nrows = col_count * S; marched row r -> column ch = (col_start + r/S) mod S,
+  // full row index rf = ch*S + h (position in the sheared tensor and in the mask table).
+  const int nrows = RC ? a.col_count * S : NR;
+  const int col_start = RC ? a.col_start : 0;
+  auto full_row = [&](int r) { return RC ? (((col_start + r / S) % S) * S) + (r % S) : r; };
+
   T gap_k = (T)0, gap_t = (T)0;
   const T* inK = IN == IN_LOAD ? a.inK + p * (long long)NR * S * S + (long long)w0 * S + cw : nullptr;
   const T* inT = (IN == IN_LOAD && NTK) ? a.inT + p * (long long)NR * S * S + (long long)w0 * S + cw : nullptr;
@@ -442,7 +473,7 @@ k_stage(const StageArgs<T> a) {
   T nK[WPT], nT[WPT];
   auto fetch = [&](int r) {
     if (IN == IN_LOAD) {
-      const int rc = r < NR ? r : NR - 1;
+      const int rc = full_row(r < nrows ? r : nrows - 1);
       const T* gk = inK + (long long)rc * S * S;
 #pragma unroll
       for (int i = 0; i < WPT; ++i) nK[i] = __ldg(gk + i * S);
@@ -473,7 +504,7 @@ k_stage(const StageArgs<T> a) {
     T PK[WPT], PT[WPT];
     // ---- input row r = t of layer 1 ----------------------------------------------------
     if (IN == IN_FROM_X) {
-      const int r = t < NR ? t : NR - 1;
+      const int r = full_row(t < nrows ? t : nrows - 1);
       const int ch = r / S, h = r % S;
       const int h2 = (h + ch) % S;
       const T* xa = x1s + (h * S + w0) * CIN;
@@ -505,7 +536,7 @@ k_stage(const StageArgs<T> a) {
 #define INT(i) (l == 0 ? PT[i] : BT[lm][i])
       // ---- conv row r_out = t - LAG*l - 1 (clamped outside the image) ---------------------
       int r_out = t - LAG * l - 1;
-      r_out = r_out < 0 ? 0 : (r_out > NR - 1 ? NR - 1 : r_out);
+      r_out = full_row(r_out < 0 ? 0 : (r_out > nrows - 1 ? nrows - 1 : r_out));
       const int ch = r_out / S, h = r_out % S;
       const int h2 = (h + ch) % S;
       const float2 vm = vmask_at<S>(r_out);
@@ -563,11 +594,12 @@ k_stage(const StageArgs<T> a) {
     }
     // ---- epilogue on the finished row of the last layer ---------------------------------------
     const int r_fin = t - LAG * (L - 1) - 1;
-    if (r_fin >= 0 && r_fin < NR) {
-      const int ch = r_fin / S, h = r_fin % S;
+    if (r_fin >= 0 && r_fin < nrows) {
+      const int rf = full_row(r_fin);
+      const int ch = rf / S, h = rf % S;
       if (EPI == EPI_STORE) {
         if (live) {
-          const long long base = (p * NR + r_fin) * (long long)(S * S) + (long long)w0 * S + cw;
+          const long long base = (p * NR + rf) * (long long)(S * S) + (long long)w0 * S + cw;
 #pragma unroll
           for (int i = 0; i < WPT; ++i) {
             a.outK[base + (long long)i * S] = BK[L - 1][i];
@@ -620,8 +652,8 @@ k_stage(const StageArgs<T> a) {
     }
   };
 
-  constexpr int NSTEPS0 = NR + LAG * (L - 1) + 1;
-  constexpr int NSTEPS = NSTEPS0 + (NSTEPS0 & 1);
+  const int NSTEPS0 = nrows + LAG * (L - 1) + 1;
+  const int NSTEPS = NSTEPS0 + (NSTEPS0 & 1);
   for (int t0 = 0; t0 < NSTEPS; t0 += 2) {
     step(t0, std::integral_constant<int, 0>{});
     step(t0 + 1, std::integral_constant<int, 1>{});
@@ -683,6 +715,29 @@ __global__ void k_shear(const T* __restrict__ in, T* __restrict__ out, long long
       out[idx] = in[can];
     else
       out[can] = in[idx];
+  }
+}
+
+// triangular tile result -> matrix: pair p = (l, l + off) of the block starting at (r0, r0)
+template <typename T>
+__global__ void k_scatter_tri(const T* __restrict__ src, T* __restrict__ dst, long long P, int W,
+                              long long ld, int r0) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < P;
+       p += (long long)gridDim.x * blockDim.x) {
+    int l, off;
+    tri_unrank(p, W, l, off);
+    dst[(long long)(r0 + l) * ld + r0 + l + off] = src[p];
+  }
+}
+
+// m[i, j] = m[j, i] for j < i (fills the strictly lower triangle from the upper one)
+template <typename T>
+__global__ void k_mirror(T* __restrict__ m, int n, long long ld) {
+  const long long total = (long long)n * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / n), j = (int)(idx % n);
+    if (j < i) m[(long long)i * ld + j] = m[(long long)j * ld + i];
   }
 }
 
@@ -818,10 +873,10 @@ size_t stage_smem_bytes() {
   return (size_t)G::GROUPS * (xs1 + xs2 + 2 * qm + stg) * sizeof(T);
 }
 
-template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN, int SH = 1>
+template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN, int SH = 1, bool RC = false>
 int launch_stage_impl(cudaStream_t stream, int64_t* launches, const StageArgs<T>& a) {
   using G = StageGeom<S, WPT, SH>;
-  auto kern = k_stage<T, S, WPT, L, IN, EPI, NTK, CIN, SH>;
+  auto kern = k_stage<T, S, WPT, L, IN, EPI, NTK, CIN, SH, RC>;
   const size_t smem = stage_smem_bytes<T, S, WPT, L, IN, EPI, NTK, CIN, SH>();
   static thread_local bool configured = false;
   if (!configured) {
@@ -852,7 +907,7 @@ int launch_stage_epi(cudaStream_t stream, int64_t* launches, int epi, const Stag
   // instead of 8 resident warps per SM at 32x32 fp32.  Measured on B200: no gain (the issue
   // rate stays ~73 %, profiles/README.md), so independent 128-thread CTAs are the default.
   constexpr int SHC = (sizeof(T) == 4 && S == 32) ? 3 : 1;
-  if (SHC > 1 && !a.self && a.n2 >= SHC && share_override() == 3) {
+  if (SHC > 1 && !a.self && !a.tri && a.n2 >= SHC && share_override() == 3) {
     switch (epi) {
       case EPI_STORE:
         return launch_stage_impl<T, S, WPT, L, IN, EPI_STORE, NTK, CIN, SHC>(stream, launches, a);
@@ -860,6 +915,16 @@ int launch_stage_epi(cudaStream_t stream, int64_t* launches, int epi, const Stag
         return launch_stage_impl<T, S, WPT, L, IN, EPI_POOL, NTK, CIN, SHC>(stream, launches, a);
       default:
         return launch_stage_impl<T, S, WPT, L, IN, EPI_GAP, NTK, CIN, SHC>(stream, launches, a);
+    }
+  }
+  if (!NTK && a.col_count != S) {  // self-pair pipeline (nngp only): partial column range
+    switch (epi) {
+      case EPI_STORE:
+        return launch_stage_impl<T, S, WPT, L, IN, EPI_STORE, false, CIN, 1, true>(stream, launches, a);
+      case EPI_POOL:
+        return launch_stage_impl<T, S, WPT, L, IN, EPI_POOL, false, CIN, 1, true>(stream, launches, a);
+      default:
+        return fail(NTK_EINVAL, "partial column range with a GAP epilogue");
     }
   }
   switch (epi) {
@@ -963,8 +1028,10 @@ void stage_constants(const FusedPlan& plan, size_t s, FLayer<T>* lp, double* nex
 // the pair grid is tiled so that the stage boundaries fit in the arena.
 template <typename T>
 int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t* launches,
-               StageProfile* prof, const T* x1, int n1, const T* x2, int n2, bool symmetric, int S0, int /*W*/, int C,
-               bool want_ntk, T* out_nngp, T* out_ntk, long long ld) {
+               StageProfile* prof, const T* x1, int n1, const T* x2, int n2, bool symmetric, int S0,
+               int /*W*/, int C, bool want_ntk, T* out_nngp, T* out_ntk, long long ld,
+               bool full_square = false) {
+  const bool triangular = symmetric && !full_square && n1 == n2 && n1 > 1;
   const size_t n_st = plan.stages.size() - 1;  // real stages (last entry is the tail marker)
   // ---- 1. q-maps for every stage and both sample sets (self-pair pipeline) --------------
   // qm[s][set]: [n][L][S][S][2]
@@ -985,6 +1052,14 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
   }
   const double alpha0 = plan.stages[0].w2[0] / 9.0;
   const T in_scale = (T)(alpha0 / (double)C);
+  // Self pairs only feed the q-maps, i.e. the diagonal column (ch = cw = 0) of each boundary.
+  // Conv layers never mix ch columns and AvgPool couples Ch with {2Ch-1, 2Ch, 2Ch+1}, so the
+  // self-pair run of stage s has to march only the columns [-k_in[s], k_in[s]] (mod S).
+  std::vector<int> k_in(n_st, 0);
+  for (int s = (int)n_st - 2, k_out = 0; s >= 0; --s) {
+    k_in[s] = plan.stages[s].epi == EPI_POOL ? 2 * k_out + 1 : k_out;
+    k_out = k_in[s];
+  }
   for (int set = 0; set < (symmetric ? 1 : 2); ++set) {
     const T* x = set == 0 ? x1 : x2;
     const int n = set == 0 ? n1 : n2;
@@ -1036,6 +1111,8 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
         a.P = m;
         a.n2 = 1;
         a.self = 1;
+        a.col_count = std::min(S, 2 * k_in[s] + 1);
+        a.col_start = a.col_count == S ? 0 : (S - k_in[s]) % S;
         a.in_scale = in_scale;
         a.epi_scale = (T)(next_alpha / 16.0);
         for (int l = 0; l < plan.stages[s].L; ++l) a.lp[l] = lp[l];
@@ -1097,9 +1174,13 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
   (void)tail;
   for (int r0 = 0; r0 < n1; r0 += t1) {
     const int a1 = std::min(t1, n1 - r0);
-    for (int c0 = 0; c0 < n2; c0 += t2) {
-      const int a2 = std::min(t2, n2 - c0);
-      const long long P = (long long)a1 * a2;
+    // K(x, x) is symmetric: only pairs (i, j >= i) are computed and the strictly lower triangle
+    // is mirrored afterwards (the reference computes the full square, `_src/batching.py:370`).
+    // Full-width tiles enumerate the triangle pair by pair; single-row tiles start at c0 = r0.
+    const bool tri_tile = triangular && t2 == n2;
+    for (int c0 = triangular ? r0 : 0; c0 < n2; c0 += t2) {
+      const int a2 = tri_tile ? n2 - r0 : std::min(t2, n2 - c0);
+      const long long P = tri_tile ? tri_prefix(a1, a2) : (long long)a1 * a2;
       T* cur = nullptr;
       for (size_t s = 0; s < n_st; ++s) {
         const int S = Ss[s];
@@ -1131,6 +1212,9 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
         a.P = P;
         a.n2 = a2;
         a.self = 0;
+        a.tri = tri_tile ? 1 : 0;
+        a.col_start = 0;
+        a.col_count = S;
         a.in_scale = in_scale;
         for (int l = 0; l < plan.stages[s].L; ++l) a.lp[l] = lp[l];
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1159,13 +1243,30 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
         NTK_CUDA(cudaGetLastError());
       }
       (*launches)++;
-      k_scatter<T><<<grid_for(P), kThreads, 0, stream>>>(resK, out_nngp, a1, a2, 1LL, ld, r0, c0);
+      if (tri_tile)
+        k_scatter_tri<T><<<grid_for(P), kThreads, 0, stream>>>(resK, out_nngp, P, a2, ld, r0);
+      else
+        k_scatter<T><<<grid_for(P), kThreads, 0, stream>>>(resK, out_nngp, a1, a2, 1LL, ld, r0, c0);
       NTK_CUDA(cudaGetLastError());
       if (want_ntk) {
         (*launches)++;
-        k_scatter<T><<<grid_for(P), kThreads, 0, stream>>>(resT, out_ntk, a1, a2, 1LL, ld, r0, c0);
+        if (tri_tile)
+          k_scatter_tri<T><<<grid_for(P), kThreads, 0, stream>>>(resT, out_ntk, P, a2, ld, r0);
+        else
+          k_scatter<T><<<grid_for(P), kThreads, 0, stream>>>(resT, out_ntk, a1, a2, 1LL, ld, r0, c0);
         NTK_CUDA(cudaGetLastError());
       }
+      if (tri_tile) break;  // one triangular tile covers all columns of this row block
+    }
+  }
+  if (triangular) {
+    (*launches)++;
+    k_mirror<T><<<grid_for((long long)n1 * n1), kThreads, 0, stream>>>(out_nngp, n1, ld);
+    NTK_CUDA(cudaGetLastError());
+    if (want_ntk) {
+      (*launches)++;
+      k_mirror<T><<<grid_for((long long)n1 * n1), kThreads, 0, stream>>>(out_ntk, n1, ld);
+      NTK_CUDA(cudaGetLastError());
     }
   }
   return NTK_OK;

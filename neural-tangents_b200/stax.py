@@ -370,7 +370,7 @@ def _apply_to_inputs(spec, x1, x2, get_c):
   want_ntk = get_c is None or 'ntk' in get_c
   want_cov = get_c is None or 'cov1' in get_c or 'cov2' in get_c
   ctx = _lib.get_context()
-  flags = (_lib.FLAG_NO_FUSION if config.disable_fusion else 0) | (_lib.FLAG_PER_LAYER if config.per_layer else 0)
+  flags = (_lib.FLAG_NO_FUSION if config.disable_fusion else 0) | (_lib.FLAG_PER_LAYER if config.per_layer else 0) | (_lib.FLAG_FULL_SQUARE if config.full_square else 0)
   res = _lib.gram_host(ctx, low.program, x1c, x2c, H, W, C, flags, oh, ow, want_ntk, want_cov)
   m = low.out_meta
   ntk = res['ntk']

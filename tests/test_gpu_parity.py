@@ -302,3 +302,21 @@ def test_fcn_config1_tensor_core_gram(nt):
   g = dense(x1[:300], x2[:200], 'nngp')
   g64 = x1[:300].astype(np.float64) @ x2[:200].astype(np.float64).T / 784
   assert np.abs(g - g64).max() < 2e-6
+
+
+def test_triangular_schedule_equals_full_square(nt):
+  """x2=None computes the upper triangle and mirrors it; NTK_FLAG_FULL_SQUARE computes all
+  n x n entries like the reference (batching.py:370).  Both must agree (and be symmetric)."""
+  nt.config.update('enable_x64', False)
+  _, _, kernel_fn = cases.build(cases.myrtle(7), nt.stax)
+  x = np.random.default_rng(111).standard_normal((9, 32, 32, 3)).astype(np.float32)
+  tri = kernel_fn(x, None, ('nngp', 'ntk'))
+  nt.config.update('full_square', True)
+  full = kernel_fn(x, None, ('nngp', 'ntk'))
+  nt.config.update('full_square', False)
+  np.testing.assert_array_equal(tri.nngp, tri.nngp.T)
+  np.testing.assert_array_equal(tri.ntk, tri.ntk.T)
+  np.testing.assert_allclose(tri.nngp, full.nngp, rtol=1e-5)
+  np.testing.assert_allclose(tri.ntk, full.ntk, rtol=1e-5)
+  iu = np.triu_indices(9)
+  np.testing.assert_array_equal(tri.nngp[iu], full.nngp[iu])
