@@ -422,8 +422,47 @@ k_stage(const StageArgs<T> a) {
     }
     const V2* g1 = reinterpret_cast<const V2*>(a.qm1) + (long long)si * L * S * S;
     const V2* g2 = reinterpret_cast<const V2*>(a.qm2) + (long long)sj * L * S * S;
-    for (int e = rt; e < L * S * S; e += rn) q1m[e] = g1[e];
-    for (int e = tg; e < L * S * S; e += TPP) q2m[e] = g2[e];
+    if (TPP >= 128) {
+      // q-maps are contiguous 16-byte-aligned blocks: one elected thread hands both copies to
+      // the TMA bulk-copy engine (cp.async.bulk, SASS UBLKCP) and the group waits on an mbarrier.
+      __shared__ __align__(8) unsigned long long qbar[G::GROUPS];
+      constexpr unsigned kBytes = (unsigned)(L * S * S * sizeof(V2));
+      const unsigned bar = (unsigned)__cvta_generic_to_shared(&qbar[grp]);
+      const bool copy_row = !SHARED_ROW || grp == 0;
+      if (tg == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                     "r"(copy_row ? 2 * kBytes : kBytes));
+        if (copy_row)
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                  (unsigned)__cvta_generic_to_shared(q1m)),
+              "l"(g1), "r"(kBytes), "r"(bar)
+              : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                (unsigned)__cvta_generic_to_shared(q2m)),
+            "l"(g2), "r"(kBytes), "r"(bar)
+            : "memory");
+      }
+      __syncthreads();  // barrier initialised (and, for SHARED_ROW, group 0 issued the row copy)
+      unsigned done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar)
+            : "memory");
+      }
+    } else {
+      for (int e = rt; e < L * S * S; e += rn) q1m[e] = g1[e];
+      for (int e = tg; e < L * S * S; e += TPP) q2m[e] = g2[e];
+    }
   }
   if (TPP > 32)
     __syncthreads();

@@ -22,8 +22,36 @@ from . import _lib
 from ._config import config
 from .kernel import Kernel
 
+import enum
+
 __all__ = ['serial', 'parallel', 'FanOut', 'FanInSum', 'Identity', 'Dense', 'Conv', 'Relu',
-           'ABRelu', 'LeakyRelu', 'Abs', 'Erf', 'AvgPool', 'GlobalAvgPool', 'Flatten']
+           'ABRelu', 'LeakyRelu', 'Abs', 'Erf', 'AvgPool', 'GlobalAvgPool', 'Flatten', 'Padding']
+
+
+class Padding(enum.Enum):
+  """`_src/stax/linear.py:54-69`."""
+  CIRCULAR = 'CIRCULAR'
+  SAME = 'SAME'
+  VALID = 'VALID'
+
+
+# Names the reference's `stax` exports that are outside the B200 hot path (SURVEY §2): asking
+# for them fails loudly instead of with an AttributeError that looks like a typo.
+_OUT_OF_SCOPE = ('repeat', 'Cos', 'Elementwise', 'ElementwiseNumerical', 'Exp', 'ExpNormalized',
+                 'Gabor', 'Gaussian', 'Gelu', 'Hermite', 'Monomial', 'Polynomial', 'Rbf',
+                 'RectifiedMonomial', 'Sigmoid_like', 'Sign', 'Sin', 'Aggregate', 'ConvLocal',
+                 'ConvTranspose', 'Index', 'DotGeneral', 'Dropout', 'GlobalSelfAttention',
+                 'GlobalSumPool', 'ImageResize', 'LayerNorm', 'SumPool', 'Slice', 'FanInConcat',
+                 'FanInProd', 'AggregateImplementation', 'AttentionMechanism', 'PositionalEmbedding',
+                 'Bool', 'Diagonal', 'MaskedArray', 'layer', 'requires', 'supports_masking', 'unmask_fn')
+
+
+def __getattr__(name):
+  if name in _OUT_OF_SCOPE:
+    raise NotImplementedError(f'stax.{name} exists in neural_tangents but is outside the B200 '
+                              'hot path (Dense/Conv/Relu/Erf/AvgPool/GlobalAvgPool/Flatten/'
+                              'FanOut/FanInSum/serial/parallel); see DESIGN.md §9')
+  raise AttributeError(name)
 
 
 # ----------------------------------------------------------------------------
