@@ -34,12 +34,28 @@ WORKLOADS = {
     'myrtle5': (5, 4 * E32 + 4 * E16 + 4 * E8, 4 * E32 + 2 * E16),
     'myrtle7': (7, 4 * E32 + 8 * E16 + 8 * E8, 4 * E32 + 2 * E16),
     'myrtle10': (10, 8 * E32 + 12 * E16 + 12 * E8, 8 * E32 + 2 * E16),
+    # README.md:370-395: 21 x [Conv3x3 SAME + Relu] + GlobalAvgPool, the only network the reference
+    # publishes GPU timings for (V100 fp32: 2.7001 ms / NTK entry = 370.4 entries/s).
+    'readme21': (21, 80 * E32, 10 * E32),
 }
+PUBLISHED = {('readme21', 'f32'): 1e3 / 2.7001, ('readme21', 'f64'): 1e3 / 6.2058}
+
+
+def workload_spec(name):
+  import cases
+  if name == 'readme21':
+    return ('serial', [cases.conv(W=1., b=None), cases.RELU] * 21 + [('gap',)])
+  return cases.myrtle(WORKLOADS[name][0])
 
 
 def stage_elements(depth, per_layer):
   """Algorithmic elements (K and T, read + written) per pair for every stage kernel launch of the
   cross-pair pass, in launch order (SURVEY §8d traffic model)."""
+  if depth == 21:   # readme21: 21 layers at 32x32, chunks of 3 (or 1), GAP at the end
+    n = 21 if per_layer else 7
+    per = 1 if per_layer else 3
+    return [(0 if i == 0 else 2 * E32) + (per - 1) * 4 * E32 + (0 if i == n - 1 else 2 * E32)
+            for i in range(n)]
   f = {5: [2, 1, 1], 7: [2, 2, 2], 10: [3, 3, 3]}[depth]
   res = [E32, E16, E8]
   out = []
@@ -128,7 +144,7 @@ def _cpu_worker(job):
   os.environ.setdefault('OMP_NUM_THREADS', '1')
   from oracle import ntk_oracle as O
   import cases
-  spec = cases.myrtle(depth)
+  spec = workload_spec('readme21' if depth == 21 else {5: 'myrtle5', 7: 'myrtle7', 10: 'myrtle10'}[depth])
   x1 = np.random.default_rng(1000 + seed).standard_normal((1, 32, 32, 3)).astype(np.float32)
   x2 = np.random.default_rng(1).standard_normal((n_cols, 32, 32, 3)).astype(np.float32)
   out = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'), dtype=np.float64)
@@ -210,7 +226,7 @@ def run_ours(args):
   sz = 8 if x64 else 4
 
   depth, elems_net, elems_stage0 = WORKLOADS[args.workload]
-  _, _, kernel_fn = cases.build(cases.myrtle(depth), stax)
+  _, _, kernel_fn = cases.build(workload_spec(args.workload), stax)
   low = stax._lowered(stax._strip(kernel_fn._spec), False, False, True)
   b1, b2 = args.block
   # synthetic inputs: each rank owns a slab of x1 rows; x2 comes from rank 0
@@ -314,7 +330,8 @@ def run_ours(args):
     achieved = st0_pairs * alg_bytes_per_pair / (st0_ms * 1e-3) / 1e9
     tpp = ncu_traffic_per_pair(args.workload, args.dtype)
     roof.update({
-        'kernel': 'k_stage<S=32,L=%d,FROM_X,POOL> (fused Conv+Relu x%d + AvgPool)' % ((3, 3) if depth == 10 else (2, 2)),
+        'kernel': ('k_stage<S=32,L=3,FROM_X,STORE> (first 3 fused Conv+Relu layers)' if depth == 21 else
+                   'k_stage<S=32,L=%d,FROM_X,POOL> (fused Conv+Relu x%d + AvgPool)' % ((3, 3) if depth == 10 else (2, 2))),
         'achieved': achieved, 'frac': achieved / pk['hbm_gbs'],
         'algorithmic_bytes_per_launch': alg_bytes_per_pair * st0_pairs // st0_n,
         'avg_launch_ms': st0_ms / st0_n, 'launches_timed': st0_n,
@@ -337,8 +354,10 @@ def run_ours(args):
   line = {
       'metric': 'kernel_entries_per_sec', 'value': value, 'unit': 'entries/s', 'n_gpus': world,
       'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev_max / args.steps,
-      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,
-      'data': 'synthetic',
+      'higher_is_better': True, 'scaling': 'weak',
+      'vs_baseline': (value / world / PUBLISHED[(args.workload, args.dtype)]
+                      if (args.workload, args.dtype) in PUBLISHED else None),
+      'dtype': args.dtype, 'data': 'synthetic',
       'config': {'workload': f'{args.workload}_32x32x3_nngp+ntk', 'block_per_gpu': [b1, b2],
                  'parallelism': f'x1-row partition over {world} rank(s), x2 broadcast, slabs all-gathered',
                  'l2': 'flushed (256 MiB write) between timed steps', 'fusion': ('per-layer stencil kernels' if args.per_layer else not args.no_fusion),
