@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "generic_kernels.cuh"
 #include "fused_kernels.cuh"
+#include "res_kernels.cuh"
 
 using namespace ntk;
 
@@ -22,6 +23,7 @@ struct ntk_program {
   std::vector<int> last_use;  // per slot: index of the last op reading it (or n_ops if output)
   FusedPlan fused;            // fast-path plan (fused_kernels.cuh); empty if not matched
   FusedPlan per_layer;        // same kernels, one layer per launch (NTK_FLAG_PER_LAYER)
+  ResPlan res;                // residual-network plan (res_kernels.cuh)
 };
 
 struct ntk_context {
@@ -641,6 +643,17 @@ int gram_device_t(ntk_context* ctx, const ntk_program* prog, const T* x1, int n1
     return st;
   }
 
+  // Residual networks (WideResNet): fused column-sparse kernels (res_kernels.cuh).
+  if (!(flags & NTK_FLAG_NO_FUSION) && prog->res.ok && H > 0 && res_supported<T>(prog->res, H, W, C) &&
+      !out.cov1 && !out.cov2) {
+    ctx->arena.reset(ctx->ws, ctx->ws_bytes, false);
+    int st = res_gram<T>(prog->res, ctx->arena, ctx->stream, &env.launches, x1, n1, x2, n2, symmetric,
+                         H, C, want_ntk, (T*)out.nngp, (T*)out.ntk, out.ld,
+                         (flags & NTK_FLAG_FULL_SQUARE) != 0);
+    ctx->launches += env.launches;
+    return st;
+  }
+
   int t1 = 0, t2 = 0;
   NTK_TRY(choose_tile<T>(*prog, ctx->ws_bytes, n1, n2, H, W, C, want_ntk, &t1, &t2));
   const size_t row = (size_t)(H > 0 ? (size_t)H * W * C : (size_t)C);
@@ -742,6 +755,7 @@ int ntk_program_create(const ntk_op_t* ops, int32_t n_ops, int32_t n_slots, int3
   NTK_TRY(validate_program(*p));
   p->fused = plan_fused(p->ops, p->n_slots, p->out_slot);
   p->per_layer = plan_fused(p->ops, p->n_slots, p->out_slot, 1);
+  p->res = plan_resnet(p->ops, p->out_slot);
   *out = p.release();
   return NTK_OK;
 }

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import cases
+from cases import pool
 
 pytestmark = pytest.mark.gpu
 
@@ -320,3 +321,36 @@ def test_triangular_schedule_equals_full_square(nt):
   np.testing.assert_allclose(tri.ntk, full.ntk, rtol=1e-5)
   iu = np.triu_indices(9)
   np.testing.assert_array_equal(tri.nngp[iu], full.nngp[iu])
+
+
+@pytest.mark.parametrize('size', [16, 32])
+def test_wide_resnet_fused_column_sparse_path(nt, size):
+  """WideResNet-style nets (README.md:192-222: pre-activation blocks, identity and conv shortcuts,
+  stride-2 blocks, FanInSum) go through the column-sparse residual kernels (res_kernels.cuh).
+  Checked against the oracle and against the general per-op path."""
+  from oracle import ntk_oracle as O
+  spec = cases.wrn() if size == 16 else ('serial', [
+      cases.conv(W=1., b=0.1), cases.wrn_block(1, True), cases.wrn_block(1, False),
+      cases.wrn_block(2, True), cases.wrn_block(1, False), cases.wrn_block(2, True),
+      cases.wrn_block(1, False), pool((8, 8), (1, 1)), ('flatten',), ('dense', 1., 0.)])
+  x1 = np.random.default_rng(121).standard_normal((3, size, size, 3)).astype(np.float32)
+  x2 = np.random.default_rng(122).standard_normal((2, size, size, 3)).astype(np.float32)
+  ref = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'))
+  _, _, kernel_fn = cases.build(spec, nt.stax)
+  for x64 in (False, True):
+    nt.config.update('enable_x64', x64)
+    out = kernel_fn(x1, x2, ('nngp', 'ntk'))
+    np.testing.assert_allclose(out.nngp, ref[0], rtol=RTOL[x64])
+    np.testing.assert_allclose(out.ntk, ref[1], rtol=RTOL[x64])
+    nt.config.update('disable_fusion', True)
+    gen = kernel_fn(x1, x2, ('nngp', 'ntk'))
+    nt.config.update('disable_fusion', False)
+    np.testing.assert_allclose(out.nngp, gen.nngp, rtol=RTOL[x64] / 2)
+    np.testing.assert_allclose(out.ntk, gen.ntk, rtol=RTOL[x64] / 2)
+  nt.config.update('enable_x64', False)
+  sym = kernel_fn(x1, None, ('nngp', 'ntk'))
+  refs = O.kernel_fn(spec, x1, None, ('nngp', 'ntk'))
+  off = ~np.eye(3, dtype=bool)
+  np.testing.assert_allclose(sym.nngp[off], refs[0][off], rtol=1e-4)
+  np.testing.assert_allclose(sym.ntk[off], refs[1][off], rtol=1e-4)
+  np.testing.assert_allclose(np.diag(sym.ntk), np.diag(refs[1]), rtol=2e-3)
