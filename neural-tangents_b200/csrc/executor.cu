@@ -24,6 +24,7 @@ struct ntk_program {
   FusedPlan fused;            // fast-path plan (fused_kernels.cuh); empty if not matched
   FusedPlan per_layer;        // same kernels, one layer per launch (NTK_FLAG_PER_LAYER)
   ResPlan res;                // residual-network plan (res_kernels.cuh)
+  DiagPlan diag;              // pool-free nets ending in Flatten: diagonal column only
 };
 
 struct ntk_context {
@@ -643,6 +644,17 @@ int gram_device_t(ntk_context* ctx, const ntk_program* prog, const T* x1, int n1
     return st;
   }
 
+  // Pool-free networks ending in Flatten: only the diagonal column matters (res_kernels.cuh).
+  if (!(flags & NTK_FLAG_NO_FUSION) && prog->diag.ok && H > 0 && H == W && H <= 32 && !out.cov1 &&
+      !out.cov2) {
+    ctx->arena.reset(ctx->ws, ctx->ws_bytes, false);
+    int st = diag_gram<T>(prog->diag, ctx->arena, ctx->stream, &env.launches, x1, n1, x2, n2, symmetric,
+                          H, C, want_ntk, (T*)out.nngp, (T*)out.ntk, out.ld,
+                          (flags & NTK_FLAG_FULL_SQUARE) != 0);
+    ctx->launches += env.launches;
+    return st;
+  }
+
   // Residual networks (WideResNet): fused column-sparse kernels (res_kernels.cuh).
   if (!(flags & NTK_FLAG_NO_FUSION) && prog->res.ok && H > 0 && res_supported<T>(prog->res, H, W, C) &&
       !out.cov1 && !out.cov2) {
@@ -756,6 +768,7 @@ int ntk_program_create(const ntk_op_t* ops, int32_t n_ops, int32_t n_slots, int3
   p->fused = plan_fused(p->ops, p->n_slots, p->out_slot);
   p->per_layer = plan_fused(p->ops, p->n_slots, p->out_slot, 1);
   p->res = plan_resnet(p->ops, p->out_slot);
+  p->diag = plan_diag(p->ops, p->last_use, p->out_slot);
   *out = p.release();
   return NTK_OK;
 }

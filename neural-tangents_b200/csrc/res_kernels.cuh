@@ -459,6 +459,7 @@ struct QProg {
   signed char dst[kMaxQOps], src[kMaxQOps], stride[kMaxQOps];
   short act_id[kMaxQOps];
   T alpha[kMaxQOps], bias[kMaxQOps], kd0[kMaxQOps];
+  T coef[kMaxQOps], hab2[kMaxQOps];  // Q_ACT on cross pairs (k_diagnet)
 };
 
 template <typename T>
@@ -703,6 +704,8 @@ int res_gram(const ResPlan& plan, Arena& arena, cudaStream_t stream, int64_t* la
   QProg<T> qp{};
   auto push = [&](int kind, int dst, int src, int stride, int act_id, double alpha, double bias, T kd0) {
     const int i = qp.n++;
+    qp.coef[i] = (T)0;
+    qp.hab2[i] = (T)0;
     qp.kind[i] = kind;
     qp.dst[i] = (signed char)dst;
     qp.src[i] = (signed char)src;
@@ -937,6 +940,351 @@ int res_gram(const ResPlan& plan, Arena& arena, cudaStream_t stream, int64_t* la
       }
       if (tri_tile) break;
     }
+  }
+  if (triangular) {
+    (*launches)++;
+    k_mirror<T><<<grid_for((long long)n1 * n1), kThreads, 0, stream>>>(out_nngp, n1, ld);
+    NTK_CUDA(cudaGetLastError());
+    if (want_ntk) {
+      (*launches)++;
+      k_mirror<T><<<grid_for((long long)n1 * n1), kThreads, 0, stream>>>(out_ntk, n1, ld);
+      NTK_CUDA(cudaGetLastError());
+    }
+  }
+  return NTK_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Pool-free networks ending in Flatten (the reference's `diagonal_spatial` fast path,
+// `_src/stax/linear.py:3381-3437`, README.md:399-416): Flatten only reads the diagonal column
+// (ch = cw = 0), and conv / activation / FanInSum never mix columns, so the whole cross-pair
+// computation is the q-program run on K[h,h,w,w] (and T) of every pair.  One CTA per pair.
+// ---------------------------------------------------------------------------------------
+template <typename T, bool NTK>
+__global__ void __launch_bounds__(128)
+k_diagnet(const T* __restrict__ x1, const T* __restrict__ x2, int S0, int C, T in_scale,
+          const QProg<T>* __restrict__ prog_g, long long qm_stride, const long long* __restrict__ act_off,
+          const T* __restrict__ qm1, const T* __restrict__ qm2, long long P, int n2, int tri,
+          T* __restrict__ outK, T* __restrict__ outT) {
+  using V2 = typename Vec2<T>::type;
+  extern __shared__ __align__(16) unsigned char dsm[];
+  const int SS = S0 * S0;
+  T* imgK = reinterpret_cast<T*>(dsm);       // 3 buffers
+  T* imgT = imgK + 3 * SS;                   // 3 buffers
+  T* scK = imgT + 3 * SS;
+  T* scT = scK + SS;
+  __shared__ int cur_S[3];
+  __shared__ int has_t[3];
+  __shared__ T red[2][4];
+  const QProg<T>& prog = *prog_g;
+  for (long long p = blockIdx.x; p < P; p += gridDim.x) {
+    int si, sj;
+    if (tri) {
+      int off;
+      tri_unrank(p, n2, si, off);
+      sj = si + off;
+    } else {
+      si = (int)(p / n2);
+      sj = (int)(p % n2);
+    }
+    const V2* q1 = reinterpret_cast<const V2*>(qm1) + (long long)si * qm_stride;
+    const V2* q2 = reinterpret_cast<const V2*>(qm2) + (long long)sj * qm_stride;
+    for (int op = 0; op < prog.n; ++op) {
+      const int kind = prog.kind[op], d = prog.dst[op], sidx = prog.src[op];
+      T* DK = imgK + d * SS;
+      T* DT = imgT + d * SS;
+      if (kind == Q_INPUT) {
+        for (int e = threadIdx.x; e < SS; e += blockDim.x) {
+          const T* xa = x1 + ((long long)si * SS + e) * C;
+          const T* xb = x2 + ((long long)sj * SS + e) * C;
+          T v = mul_rn(mul_rn(xa[0], in_scale), xb[0]);
+          for (int ci = 1; ci < C; ++ci) v = fma_t(mul_rn(xa[ci], in_scale), xb[ci], v);
+          DK[e] = v;
+        }
+        if (threadIdx.x == 0) {
+          cur_S[d] = S0;
+          has_t[d] = 0;
+        }
+      } else if (kind == Q_CONV) {
+        const int S = cur_S[sidx];
+        const bool ht = NTK && has_t[sidx];
+        const T* PK = imgK + sidx * SS;
+        const T* PT = imgT + sidx * SS;
+        for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+          const int h = e / S, w = e % S;
+          const T mL = w > 0 ? (T)1 : (T)0, mR = w < S - 1 ? (T)1 : (T)0;
+          const int el = h * S + (w > 0 ? w - 1 : w), er = h * S + (w < S - 1 ? w + 1 : w);
+          scK[e] = hsum3<T>(PK[el], PK[e], PK[er], mL, mR);
+          if (ht) scT[e] = hsum3<T>(PT[el], PT[e], PT[er], mL, mR);
+        }
+        __syncthreads();
+        const int st = prog.stride[op];
+        const int So = S / st;
+        for (int e = threadIdx.x; e < So * So; e += blockDim.x) {
+          const int a_ = e / So, b_ = e % So;
+          const int h = st == 2 ? 2 * a_ + 1 : a_, w = st == 2 ? 2 * b_ + 1 : b_;
+          const T vU = h > 0 ? (T)1 : (T)0, vD = h < S - 1 ? (T)1 : (T)0;
+          const int eu = (h > 0 ? h - 1 : h) * S + w, ed = (h < S - 1 ? h + 1 : h) * S + w;
+          const T k = fma_t(fma_t(vD, scK[ed], fma_t(vU, scK[eu], scK[h * S + w])), prog.alpha[op],
+                            prog.bias[op]);
+          DK[e] = k;
+          if (NTK)
+            DT[e] = ht ? fma_t(fma_t(vD, scT[ed], fma_t(vU, scT[eu], scT[h * S + w])), prog.alpha[op], k) : k;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          cur_S[d] = So;
+          has_t[d] = 1;
+        }
+      } else if (kind == Q_ACT) {
+        const int S = cur_S[d];
+        const V2* a1 = q1 + act_off[prog.act_id[op]];
+        const V2* a2 = q2 + act_off[prog.act_id[op]];
+        const bool ht = NTK && has_t[d];
+        for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+          const V2 qa = a1[e], qb = a2[e];
+          T ko, to;
+          act_point(DK[e], ht ? DT[e] : (T)0, qa.x, qa.y, qb.x, qb.y, prog.coef[op], (T)0, prog.hab2[op], ko, to);
+          DK[e] = ko;
+          if (ht) DT[e] = to;
+        }
+      } else if (kind == Q_COPY) {
+        const int S = cur_S[sidx];
+        for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+          DK[e] = imgK[sidx * SS + e];
+          if (NTK) DT[e] = imgT[sidx * SS + e];
+        }
+        if (threadIdx.x == 0) {
+          cur_S[d] = S;
+          has_t[d] = has_t[sidx];
+        }
+      } else if (kind == Q_ADD) {
+        const int S = cur_S[d];
+        const bool hd = NTK && has_t[d], hs = NTK && has_t[sidx];
+        for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+          DK[e] = add_rn(DK[e], imgK[sidx * SS + e]);
+          if (hd && hs)
+            DT[e] = add_rn(DT[e], imgT[sidx * SS + e]);
+          else if (hs)
+            DT[e] = imgT[sidx * SS + e];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) has_t[d] = has_t[d] | has_t[sidx];
+      }
+      __syncthreads();
+    }
+    // Flatten: mean over the diagonal (linear.py:1880-1882) of buffer 0
+    {
+      const int S = cur_S[0];
+      const bool ht = NTK && has_t[0];
+      T sk = (T)0, st = (T)0;
+      for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+        sk = add_rn(sk, imgK[e]);
+        if (ht) st = add_rn(st, imgT[e]);
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        sk = add_rn(sk, __shfl_down_sync(0xffffffffu, sk, o));
+        st = add_rn(st, __shfl_down_sync(0xffffffffu, st, o));
+      }
+      if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = sk;
+        red[1][threadIdx.x >> 5] = st;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        T a_ = (T)0, b_ = (T)0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+          a_ = add_rn(a_, red[0][w]);
+          b_ = add_rn(b_, red[1][w]);
+        }
+        const T inv = (T)1 / (T)(S * S);
+        outK[p] = a_ * inv;
+        if (NTK) outT[p] = b_ * inv;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Generic q-program compiler for programs made of Conv3x3(/1|/2, SAME), ABRelu, FanInSum and
+// Identity ending in Flatten + Dense*.  Slots are mapped onto three image buffers.
+struct DiagPlan {
+  bool ok = false;
+  std::vector<QOp> ops;
+  int n_act = 0;
+  std::vector<ntk_op_t> dense_tail;
+  double w_first = 0;  // alpha of the first conv is folded into the input scale
+};
+
+inline DiagPlan plan_diag(const std::vector<ntk_op_t>& ops, const std::vector<int>& last_use, int out_slot) {
+  DiagPlan plan;
+  const int n = (int)ops.size();
+  std::vector<int> buf_of(last_use.size(), -1);
+  bool busy[3] = {false, false, false};
+  auto grab = [&]() {
+    for (int b = 0; b < 3; ++b)
+      if (!busy[b]) {
+        busy[b] = true;
+        return b;
+      }
+    return -1;
+  };
+  buf_of[0] = grab();
+  plan.ops.push_back(QOp{Q_INPUT, buf_of[0], buf_of[0], 1, 0, 1.0, 0.0, 0.0});
+  int k = 0;
+  for (; k < n; ++k) {
+    const ntk_op_t& o = ops[k];
+    if (o.kind == NTK_OP_FLATTEN) break;
+    if (o.src < 0 || buf_of[o.src] < 0) return DiagPlan();
+    const bool src_dies = last_use[o.src] == k;
+    auto dst_buf = [&](int src_slot, bool dies) {
+      if (dies) return buf_of[src_slot];  // in place
+      const int b = grab();
+      if (b >= 0) plan.ops.push_back(QOp{Q_COPY, b, buf_of[src_slot], 1, 0, 1.0, 0.0, 0.0});
+      return b;
+    };
+    if (o.kind == NTK_OP_CONV) {
+      if (!(o.i[0] == 3 && o.i[1] == 3 && o.i[2] == o.i[3] && (o.i[2] == 1 || o.i[2] == 2) &&
+            o.i[4] == NTK_PAD_SAME))
+        return DiagPlan();
+      const int b = dst_buf(o.src, src_dies);
+      if (b < 0) return DiagPlan();
+      plan.ops.push_back(QOp{Q_CONV, b, b, o.i[2], 0, o.f[0] / 9.0, o.i[5] ? o.f[1] : 0.0, 0.0});
+      buf_of[o.dst] = b;
+    } else if (o.kind == NTK_OP_ABRELU) {
+      if (o.i[0]) return DiagPlan();
+      const int b = dst_buf(o.src, src_dies);
+      if (b < 0) return DiagPlan();
+      QOp q{Q_ACT, b, b, 1, plan.n_act++, o.f[0], o.f[1], 0.0};  // alpha/bias carry (a, b) of the ABRelu
+      plan.ops.push_back(q);
+      buf_of[o.dst] = b;
+    } else if (o.kind == NTK_OP_FANINSUM) {
+      if (buf_of[o.src2] < 0) return DiagPlan();
+      const int b = dst_buf(o.src, src_dies);
+      if (b < 0) return DiagPlan();
+      plan.ops.push_back(QOp{Q_ADD, b, buf_of[o.src2], 1, 0, 1.0, 0.0, 0.0});
+      if (last_use[o.src2] == k && buf_of[o.src2] != b) busy[buf_of[o.src2]] = false;
+      buf_of[o.dst] = b;
+    } else if (o.kind == NTK_OP_IDENTITY) {
+      buf_of[o.dst] = buf_of[o.src];
+      continue;
+    } else {
+      return DiagPlan();
+    }
+    if (src_dies && buf_of[o.src] != buf_of[o.dst]) busy[buf_of[o.src]] = false;
+  }
+  if (k >= n || ops[k].kind != NTK_OP_FLATTEN || buf_of[ops[k].src] < 0) return DiagPlan();
+  if (buf_of[ops[k].src] != 0)
+    plan.ops.push_back(QOp{Q_COPY, 0, buf_of[ops[k].src], 1, 0, 1.0, 0.0, 0.0});
+  int z = ops[k].dst;
+  for (++k; k < n; ++k) {
+    if (ops[k].kind != NTK_OP_DENSE || ops[k].src != z) return DiagPlan();
+    z = ops[k].dst;
+    plan.dense_tail.push_back(ops[k]);
+  }
+  if (z != out_slot || plan.ops.size() > (size_t)kMaxQOps || plan.n_act == 0) return DiagPlan();
+  plan.ok = true;
+  return plan;
+}
+
+template <typename T>
+int diag_gram(const DiagPlan& plan, Arena& arena, cudaStream_t stream, int64_t* launches, const T* x1,
+              int n1, const T* x2, int n2, bool symmetric, int S0, int C, bool want_ntk, T* out_nngp,
+              T* out_ntk, long long ld, bool full_square) {
+  const bool triangular = symmetric && !full_square && n1 == n2 && n1 > 1;
+  QProg<T> qp{};
+  std::vector<long long> act_off;
+  {
+    // track the resolution to size the q-maps
+    int Sb[3] = {S0, S0, S0};
+    long long off = 0;
+    for (const QOp& o : plan.ops) {
+      const int i = qp.n++;
+      qp.kind[i] = o.kind;
+      qp.dst[i] = (signed char)o.dst;
+      qp.src[i] = (signed char)o.src;
+      qp.stride[i] = (signed char)o.stride;
+      qp.act_id[i] = (short)o.act_id;
+      qp.alpha[i] = (T)o.alpha;
+      qp.bias[i] = (T)o.bias;
+      qp.kd0[i] = qp.coef[i] = qp.hab2[i] = (T)0;
+      if (o.kind == Q_CONV) {
+        Sb[o.dst] = Sb[o.src] / o.stride;
+        if (Sb[o.dst] < 1) return fail(NTK_EINVAL, "Conv output would be empty");
+      } else if (o.kind == Q_COPY) {
+        Sb[o.dst] = Sb[o.src];
+      } else if (o.kind == Q_ACT) {
+        const FLayer<T> f = res_act_consts<T>(o.alpha, o.bias, 1.0, 0.0);
+        qp.coef[i] = f.coef;
+        qp.hab2[i] = f.hab2;
+        qp.kd0[i] = host_kd0(f.coef, f.hab2);
+        qp.alpha[i] = qp.bias[i] = (T)0;
+        act_off.push_back(off);
+        off += (long long)Sb[o.dst] * Sb[o.dst];
+      }
+    }
+    act_off.push_back(off);
+  }
+  const long long qm_stride = act_off.back();
+  QProg<T>* qp_d = (QProg<T>*)arena.alloc(sizeof(QProg<T>));
+  long long* off_d = (long long*)arena.alloc(act_off.size() * sizeof(long long));
+  T* qm1 = (T*)arena.alloc((size_t)n1 * qm_stride * 2 * sizeof(T));
+  T* qm2 = symmetric ? qm1 : (T*)arena.alloc((size_t)n2 * qm_stride * 2 * sizeof(T));
+  const long long Pmax = (long long)n1 * n2;
+  T* resK = (T*)arena.alloc((size_t)Pmax * sizeof(T));
+  T* resT = want_ntk ? (T*)arena.alloc((size_t)Pmax * sizeof(T)) : nullptr;
+  if (!qp_d || !off_d || !qm1 || !qm2 || !resK || (want_ntk && !resT))
+    return fail(NTK_ENOMEM, "workspace too small for the diagonal path");
+  NTK_CUDA(cudaMemcpyAsync(qp_d, &qp, sizeof(qp), cudaMemcpyHostToDevice, stream));
+  NTK_CUDA(cudaMemcpyAsync(off_d, act_off.data(), act_off.size() * sizeof(long long), cudaMemcpyHostToDevice, stream));
+  NTK_CUDA(cudaStreamSynchronize(stream));
+  const T in_scale = (T)(1.0 / (double)C);
+  for (int set = 0; set < (symmetric ? 1 : 2); ++set) {
+    (*launches)++;
+    k_qprog<T><<<set == 0 ? n1 : n2, 256, (size_t)4 * S0 * S0 * sizeof(T), stream>>>(
+        set == 0 ? x1 : x2, S0, C, in_scale, qp_d, qm_stride, off_d, set == 0 ? qm1 : qm2);
+    NTK_CUDA(cudaGetLastError());
+  }
+  const long long P = triangular ? tri_prefix(n1, n2) : Pmax;
+  const size_t smem = (size_t)8 * S0 * S0 * sizeof(T);
+  const int grid = (int)std::min<long long>(P, (long long)kNumSMs * 32);
+  (*launches)++;
+  if (want_ntk) {
+    static thread_local bool cfg = false;
+    if (!cfg) {
+      NTK_CUDA(cudaFuncSetAttribute(k_diagnet<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * 32 * 8));
+      cfg = true;
+    }
+    k_diagnet<T, true><<<grid, 128, smem, stream>>>(x1, x2, S0, C, in_scale, qp_d, qm_stride, off_d, qm1, qm2,
+                                                   P, n2, triangular ? 1 : 0, resK, resT);
+  } else {
+    static thread_local bool cfg = false;
+    if (!cfg) {
+      NTK_CUDA(cudaFuncSetAttribute(k_diagnet<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * 32 * 8));
+      cfg = true;
+    }
+    k_diagnet<T, false><<<grid, 128, smem, stream>>>(x1, x2, S0, C, in_scale, qp_d, qm_stride, off_d, qm1, qm2,
+                                                    P, n2, triangular ? 1 : 0, resK, resT);
+  }
+  NTK_CUDA(cudaGetLastError());
+  for (const ntk_op_t& d : plan.dense_tail) {
+    (*launches)++;
+    k_dense<T><<<grid_for(P), kThreads, 0, stream>>>(resK, resT, P, (T)d.f[0], (T)(d.i[0] ? d.f[1] : 0.0), 0);
+    NTK_CUDA(cudaGetLastError());
+  }
+  (*launches)++;
+  if (triangular)
+    k_scatter_tri<T><<<grid_for(P), kThreads, 0, stream>>>(resK, out_nngp, P, n2, ld, 0);
+  else
+    k_scatter<T><<<grid_for(P), kThreads, 0, stream>>>(resK, out_nngp, n1, n2, 1LL, ld, 0, 0);
+  NTK_CUDA(cudaGetLastError());
+  if (want_ntk) {
+    (*launches)++;
+    if (triangular)
+      k_scatter_tri<T><<<grid_for(P), kThreads, 0, stream>>>(resT, out_ntk, P, n2, ld, 0);
+    else
+      k_scatter<T><<<grid_for(P), kThreads, 0, stream>>>(resT, out_ntk, n1, n2, 1LL, ld, 0, 0);
+    NTK_CUDA(cudaGetLastError());
   }
   if (triangular) {
     (*launches)++;

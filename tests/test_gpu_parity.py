@@ -354,3 +354,33 @@ def test_wide_resnet_fused_column_sparse_path(nt, size):
   np.testing.assert_allclose(sym.nngp[off], refs[0][off], rtol=1e-4)
   np.testing.assert_allclose(sym.ntk[off], refs[1][off], rtol=1e-4)
   np.testing.assert_allclose(np.diag(sym.ntk), np.diag(refs[1]), rtol=2e-3)
+
+
+def test_pool_free_flatten_nets_diagonal_path(nt):
+  """Pool-free networks ending in Flatten only need the diagonal column (the reference's
+  `diagonal_spatial` fast path, linear.py:3381-3437, README.md:399-416): plain, strided and
+  residual variants against the oracle and the general path."""
+  from oracle import ntk_oracle as O
+  specs = {
+      'plain': ('serial', [cases.conv(W=1.3, b=0.1), cases.RELU] * 5 + [('flatten',), ('dense', 1.1, 0.2)]),
+      'strided': ('serial', [cases.conv(W=1.3, b=0.1), cases.RELU, cases.conv(s=(2, 2)), ('abrelu', 0.1, 1., False),
+                             cases.conv(), cases.RELU, ('flatten',), ('dense', 1., 0.)]),
+      'residual': ('serial', [cases.conv(W=1., b=0.1), cases.wrn_block(1, True), cases.wrn_block(2, True),
+                              cases.wrn_block(1, False), ('flatten',), ('dense', 1., 0.1)]),
+  }
+  for name, spec in specs.items():
+    for size in (8, 32):
+      x1 = np.random.default_rng(131).standard_normal((3, size, size, 3)).astype(np.float32)
+      x2 = np.random.default_rng(132).standard_normal((4, size, size, 3)).astype(np.float32)
+      ref = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'))
+      _, _, kernel_fn = cases.build(spec, nt.stax)
+      for x64 in (False, True):
+        nt.config.update('enable_x64', x64)
+        out = kernel_fn(x1, x2, ('nngp', 'ntk'))
+        np.testing.assert_allclose(out.nngp, ref[0], rtol=RTOL[x64], err_msg=f'{name} {size}')
+        np.testing.assert_allclose(out.ntk, ref[1], rtol=RTOL[x64], err_msg=f'{name} {size}')
+        np.testing.assert_allclose(kernel_fn(x1, x2, 'nngp'), ref[0], rtol=RTOL[x64])
+      nt.config.update('enable_x64', False)
+      sym = kernel_fn(x1, None, ('nngp', 'ntk'))
+      np.testing.assert_array_equal(sym.ntk, sym.ntk.T)
+      np.testing.assert_allclose(sym.nngp, O.kernel_fn(spec, x1, None, ('nngp',))[0], rtol=1e-4)
