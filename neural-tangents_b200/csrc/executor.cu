@@ -10,8 +10,14 @@
 
 #include "common.cuh"
 #include "generic_kernels.cuh"
-#include "fused_kernels.cuh"
-#include "res_kernels.cuh"
+#include "instantiate.cuh"
+
+namespace ntk {
+NTK_FUSED_INSTANCES(extern, float)
+NTK_FUSED_INSTANCES(extern, double)
+NTK_RES_INSTANCES(extern, float)
+NTK_RES_INSTANCES(extern, double)
+}  // namespace ntk
 
 using namespace ntk;
 
@@ -856,7 +862,8 @@ int ntk_context_create(int32_t device, size_t workspace_bytes, ntk_context_t** o
   }
   NTK_CUDA(cudaMalloc((void**)&c->ws, workspace_bytes));
   c->ws_bytes = workspace_bytes;
-  NTK_TRY(fused_configure_device());
+  NTK_TRY(fused_configure_device<float>());
+  NTK_TRY(fused_configure_device<double>());
   *out = c.release();
   return NTK_OK;
 }

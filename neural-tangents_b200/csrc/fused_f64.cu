@@ -1,0 +1,5 @@
+// Stage kernels (fused_kernels.cuh) for double: one translation unit per dtype (parallel build).
+#include "instantiate.cuh"
+namespace ntk {
+NTK_FUSED_INSTANCES(, double)
+}  // namespace ntk

@@ -251,9 +251,10 @@ __device__ __forceinline__ void act_point(double K, double Tn, double q1, double
 //   .y = vD: rows r and r+1 are linked.
 // Held in constant memory so that one uniform load replaces ~18 uniform-datapath
 // instructions per layer and step.  Entry 0 / NR+1.. (clamped rows) reuse valid rows.
-__constant__ float2 c_vmask32[32 * 32];
-__constant__ float2 c_vmask16[16 * 16];
-__constant__ float2 c_vmask8[8 * 8];
+// `static`: every translation unit that instantiates the stage kernels owns (and uploads) its copy.
+static __constant__ float2 c_vmask32[32 * 32];
+static __constant__ float2 c_vmask16[16 * 16];
+static __constant__ float2 c_vmask8[8 * 8];
 
 template <int S>
 __device__ __forceinline__ float2 vmask_at(int r) {
@@ -1018,8 +1019,10 @@ int launch_qmaps(cudaStream_t stream, int64_t* launches, int S, const T* src, in
   return NTK_OK;
 }
 
-// Uploads the vertical link masks to the current device (once per context).
-inline int fused_configure_device() {
+// Uploads the vertical link masks to the current device (once per context).  Templated on the
+// dtype so that each translation unit (fused_f32.cu / fused_f64.cu) uploads its own copy.
+template <typename T>
+int fused_configure_device() {
   for (int S : {32, 16, 8}) {
     std::vector<float2> m((size_t)S * S);
     for (int ch = 0; ch < S; ++ch)

@@ -61,7 +61,7 @@ __device__ __forceinline__ float to_tf32(float x) {
 constexpr int kGemmBM = 128, kGemmBN = 128, kGemmBK = 32;
 
 // One CTA (128 threads) per 128 x 128 output tile.
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_gram_tf32x3(const float* __restrict__ x1, const float* __restrict__ x2, float* __restrict__ out,
               int n1, int n2, int d, float inv_d) {
   // [hi/lo][K/4][rows/8][8][4]: address(r, k) = (k/4)*rows*16 + (r/8)*128 + (r%8)*16 + (k%4)*4
@@ -209,7 +209,7 @@ k_gram_tf32x3(const float* __restrict__ x1, const float* __restrict__ x2, float*
 // ------------------------------------------------------------------------------------------
 constexpr int kDmmaBM = 32, kDmmaBN = 64, kDmmaBK = 16;
 
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_gram_dmma(const double* __restrict__ x1, const double* __restrict__ x2, double* __restrict__ out,
             int n1, int n2, int d, double inv_d) {
   __shared__ double sA[kDmmaBM][kDmmaBK + 1];

@@ -1,0 +1,18 @@
+// Explicit-instantiation plumbing: the heavy kernel families are compiled in their own
+// translation units (fused_f32.cu, fused_f64.cu, res_f32.cu, res_f64.cu) so that `make -j`
+// builds them in parallel; executor.cu only sees `extern template` declarations.
+#pragma once
+
+#include "fused_kernels.cuh"
+#include "res_kernels.cuh"
+
+#define NTK_FUSED_INSTANCES(KW, T)                                                                        \
+  KW template int fused_gram<T>(const FusedPlan&, Arena&, cudaStream_t, int64_t*, StageProfile*, const T*, \
+                                int, const T*, int, bool, int, int, int, bool, T*, T*, long long, bool);   \
+  KW template int fused_configure_device<T>();
+
+#define NTK_RES_INSTANCES(KW, T)                                                                         \
+  KW template int res_gram<T>(const ResPlan&, Arena&, cudaStream_t, int64_t*, const T*, int, const T*,    \
+                              int, bool, int, int, bool, T*, T*, long long, bool);                        \
+  KW template int diag_gram<T>(const DiagPlan&, Arena&, cudaStream_t, int64_t*, const T*, int, const T*, \
+                               int, bool, int, int, bool, T*, T*, long long, bool);
