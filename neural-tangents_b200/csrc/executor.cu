@@ -864,6 +864,7 @@ int ntk_context_create(int32_t device, size_t workspace_bytes, ntk_context_t** o
   c->ws_bytes = workspace_bytes;
   NTK_TRY(fused_configure_device<float>());
   NTK_TRY(fused_configure_device<double>());
+  NTK_TRY(stage_packed_configure());
   *out = c.release();
   return NTK_OK;
 }

@@ -989,9 +989,28 @@ int launch_stage_L(cudaStream_t stream, int64_t* launches, int L, int epi, const
   }
 }
 
+// Packed-FP32 (FFMA2) instance for fp32 at 32x32: stage_packed.cuh / stage_packed.cu.
+int launch_stage_packed(cudaStream_t stream, int64_t* launches, int S, int L, int from_x, int epi, bool ntk,
+                        const StageArgs<float>& a);
+int stage_packed_configure();
+
+inline bool packed_enabled() {
+  static const bool on = getenv("NTK_B200_NO_PACKED") == nullptr;
+  return on;
+}
+inline int launch_stage_packed_any(cudaStream_t, int64_t*, int, int, int, int, bool, const StageArgs<double>&) {
+  return fail(NTK_EINVAL, "packed stage kernel is fp32 only");
+}
+inline int launch_stage_packed_any(cudaStream_t stream, int64_t* launches, int S, int L, int from_x, int epi,
+                                   bool ntk, const StageArgs<float>& a) {
+  return launch_stage_packed(stream, launches, S, L, from_x, epi, ntk, a);
+}
+
 template <typename T, bool NTK>
 int launch_stage(cudaStream_t stream, int64_t* launches, int S, int L, int from_x, int C, int epi,
                  const StageArgs<T>& a) {
+  if (sizeof(T) == 4 && S == 32 && (!from_x || C == 3) && packed_enabled())
+    return launch_stage_packed_any(stream, launches, S, L, from_x, epi, NTK, a);
   if (from_x) {
     if (C != 3) return fail(NTK_EUNSUPPORTED, "fused FROM_X stages are instantiated for C == 3");
     if (S == 32) return launch_stage_L<T, 32, IN_FROM_X, NTK, 3>(stream, launches, L, epi, a);

@@ -1,0 +1,87 @@
+// Instantiations + launcher of the packed-FP32 stage kernel (stage_packed.cuh): fp32, 32x32.
+#include "stage_packed.cuh"
+
+namespace ntk {
+
+namespace {
+
+template <int S, int L, int IN, int EPI, bool NTK, int CIN, bool RC>
+int launch_p_impl(cudaStream_t stream, int64_t* launches, const StageArgs<float>& a) {
+  using G = PGeom<S>;
+  auto kern = k_stage_p<S, L, IN, EPI, NTK, CIN, RC>;
+  const size_t smem = stage_p_smem_bytes<S, L, IN, EPI, NTK, CIN>();
+  static thread_local bool configured = false;
+  if (!configured) {
+    NTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const long long blocks = (a.P + G::GROUPS - 1) / G::GROUPS;
+  (*launches)++;
+  kern<<<(unsigned)blocks, G::NT, smem, stream>>>(a);
+  NTK_CUDA(cudaGetLastError());
+  return NTK_OK;
+}
+
+template <int S, int L, int IN, bool NTK, int CIN>
+int launch_p_epi(cudaStream_t stream, int64_t* launches, int epi, const StageArgs<float>& a) {
+  if (!NTK && a.col_count != S) {  // self-pair pipeline (nngp only): partial column range
+    switch (epi) {
+      case EPI_STORE:
+        return launch_p_impl<S, L, IN, EPI_STORE, false, CIN, true>(stream, launches, a);
+      case EPI_POOL:
+        return launch_p_impl<S, L, IN, EPI_POOL, false, CIN, true>(stream, launches, a);
+      default:
+        return fail(NTK_EINVAL, "partial column range with a GAP epilogue");
+    }
+  }
+  switch (epi) {
+    case EPI_STORE:
+      return launch_p_impl<S, L, IN, EPI_STORE, NTK, CIN, false>(stream, launches, a);
+    case EPI_POOL:
+      return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false>(stream, launches, a);
+    default:
+      return launch_p_impl<S, L, IN, EPI_GAP, NTK, CIN, false>(stream, launches, a);
+  }
+}
+
+template <int S, int IN, bool NTK, int CIN>
+int launch_p_L(cudaStream_t stream, int64_t* launches, int L, int epi, const StageArgs<float>& a) {
+  switch (L) {
+    case 1:
+      return launch_p_epi<S, 1, IN, NTK, CIN>(stream, launches, epi, a);
+    case 2:
+      return launch_p_epi<S, 2, IN, NTK, CIN>(stream, launches, epi, a);
+    default:
+      return launch_p_epi<S, 3, IN, NTK, CIN>(stream, launches, epi, a);
+  }
+}
+
+}  // namespace
+
+int launch_stage_packed(cudaStream_t stream, int64_t* launches, int S, int L, int from_x, int epi, bool ntk,
+                        const StageArgs<float>& a) {
+  if (S != 32) return fail(NTK_EINVAL, "packed stage kernel is instantiated for S == 32");
+  if (from_x)
+    return ntk ? launch_p_L<32, IN_FROM_X, true, 3>(stream, launches, L, epi, a)
+               : launch_p_L<32, IN_FROM_X, false, 3>(stream, launches, L, epi, a);
+  return ntk ? launch_p_L<32, IN_LOAD, true, 1>(stream, launches, L, epi, a)
+             : launch_p_L<32, IN_LOAD, false, 1>(stream, launches, L, epi, a);
+}
+
+int stage_packed_configure() {
+  for (int S : {32, 16}) {
+    std::vector<float4> m((size_t)S * S);
+    for (int ch = 0; ch < S; ++ch)
+      for (int h = 0; h < S; ++h) {
+        const int h2 = (h + ch) % S;
+        const float vu = (h > 0 && h2 != 0) ? 1.f : 0.f, vd = (h < S - 1 && h2 != S - 1) ? 1.f : 0.f;
+        m[(size_t)ch * S + h] = make_float4(vu, vu, vd, vd);
+      }
+    const size_t bytes = m.size() * sizeof(float4);
+    if (S == 32) NTK_CUDA(cudaMemcpyToSymbol(c_vmaskp32, m.data(), bytes));
+    if (S == 16) NTK_CUDA(cudaMemcpyToSymbol(c_vmaskp16, m.data(), bytes));
+  }
+  return NTK_OK;
+}
+
+}  // namespace ntk
