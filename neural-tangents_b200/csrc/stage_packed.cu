@@ -5,11 +5,20 @@ namespace ntk {
 
 namespace {
 
-template <int S, int L, int IN, int EPI, bool NTK, int CIN, bool RC>
+inline int variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NTK_B200_PVAR");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+template <int S, int L, int IN, int EPI, bool NTK, int CIN, bool RC, int LAG = 1, int MINB = 2, bool Q2P = true>
 int launch_p_impl(cudaStream_t stream, int64_t* launches, const StageArgs<float>& a) {
   using G = PGeom<S>;
-  auto kern = k_stage_p<S, L, IN, EPI, NTK, CIN, RC>;
-  const size_t smem = stage_p_smem_bytes<S, L, IN, EPI, NTK, CIN>();
+  auto kern = k_stage_p<S, L, IN, EPI, NTK, CIN, RC, LAG, MINB, Q2P>;
+  const size_t smem = stage_p_smem_bytes<S, L, IN, EPI, NTK, CIN, Q2P>();
   static thread_local bool configured = false;
   if (!configured) {
     NTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -38,6 +47,12 @@ int launch_p_epi(cudaStream_t stream, int64_t* launches, int epi, const StageArg
     case EPI_STORE:
       return launch_p_impl<S, L, IN, EPI_STORE, NTK, CIN, false>(stream, launches, a);
     case EPI_POOL:
+      // Variants A/B-timed on B200 for the dominant kernel (L = 3, FROM_X, POOL, ntk; 9216 pairs):
+      //   LAG 1, 2 CTAs/SM, paired q2 (default) 37.87 ms | LAG 2: 37.73 | 3 CTAs/SM + planar q2: 37.29
+      //   LAG 2 + 3 CTAs (spills): 39.42 | planar q2 at 2 CTAs: 38.05.  All within 2 %: the kernel is bound
+      //   by register-file read bandwidth (profiles/microbench/rf_bandwidth.cu), not latency or occupancy.
+      if (L == 3 && IN == IN_FROM_X && NTK && variant() == 2)
+        return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false, 1, 3, false>(stream, launches, a);
       return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false>(stream, launches, a);
     default:
       return launch_p_impl<S, L, IN, EPI_GAP, NTK, CIN, false>(stream, launches, a);

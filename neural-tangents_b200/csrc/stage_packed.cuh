@@ -51,6 +51,12 @@ __device__ __forceinline__ float copysign_bits(float mag, float sgn) {
   return __uint_as_float((__float_as_uint(mag) & 0x7fffffffu) | (__float_as_uint(sgn) & 0x80000000u));
 }
 
+__device__ __forceinline__ float lds_f1(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
 __device__ __forceinline__ float2 lds_f2(unsigned addr) {
   float2 v;
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
@@ -123,18 +129,25 @@ __host__ __device__ __forceinline__ int perm8(int w) {
   return (w & ~7) + ((i & 3) << 1) + (i >> 2);
 }
 
-template <int S, int L, int IN, int EPI, bool NTK, int CIN>
+template <int S, int L, int IN, int EPI, bool NTK, int CIN, bool Q2P = true>
 size_t stage_p_smem_bytes() {
   using G = PGeom<S>;
   const int xs1 = IN == IN_FROM_X ? S * S * CIN : 0;
   const int xs2 = IN == IN_FROM_X ? S * S * 4 : 0;
-  const int q1 = L * S * S, q2 = 2 * L * S * S;
+  const int q1 = L * S * S, q2 = (Q2P ? 2 : 1) * L * S * S;
   const int stg = EPI == EPI_POOL ? 2 * (NTK ? 2 : 1) * S * (S + 1) : 0;
   return (size_t)G::GROUPS * (xs1 + xs2 + q1 + q2 + stg) * sizeof(float);
 }
 
-template <int S, int L, int IN, int EPI, bool NTK, int CIN, bool RC>
-__global__ void __launch_bounds__(PGeom<S>::NT)
+// Variant knobs (kept as template parameters so that they can be A/B-timed on the device):
+//   LAG   rows of lag between consecutive fused layers: 1 = a layer consumes the row its predecessor
+//         produced in the same step; 2 = the row of the previous step, so the L layer blocks of a step
+//         are independent (more ILP, more live registers)
+//   MINB  __launch_bounds__ min CTAs per SM (2 or 3)
+//   Q2P   q2 rows hold explicit (e, e+4) pairs (one LDS.64 per pair, 2x shared memory) or are planar
+//         (two LDS.32 per pair)
+template <int S, int L, int IN, int EPI, bool NTK, int CIN, bool RC, int LAG = 1, int MINB = 2, bool Q2P = true>
+__global__ void __launch_bounds__(PGeom<S>::NT, MINB)
 k_stage_p(const StageArgs<float> a) {
   using G = PGeom<S>;
   constexpr int WPT = 8, NP = 4;  // 4 pairs (i, i+4)
@@ -145,7 +158,7 @@ k_stage_p(const StageArgs<float> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int XS1 = IN == IN_FROM_X ? S * S * CIN : 0;
   constexpr int XS2 = IN == IN_FROM_X ? S * S * 4 : 0;
-  constexpr int Q1 = L * S * S, Q2 = 2 * L * S * S;
+  constexpr int Q1 = L * S * S, Q2 = (Q2P ? 2 : 1) * L * S * S;
   constexpr int STG = EPI == EPI_POOL ? 2 * (NTK ? 2 : 1) * S * SP : 0;
   constexpr int PER_GROUP = XS1 + XS2 + Q1 + Q2 + STG;
   static_assert((XS1 % 4) == 0 && (XS2 % 4) == 0 && (Q1 % 4) == 0, "16-byte alignment of the smem parts");
@@ -197,8 +210,12 @@ k_stage_p(const StageArgs<float> a) {
       const int w = e % S, row = e / S;
       q1A[row * S + perm8(w)] = fmaxf(__ldg(&g1[e].x), 1e-18f);
       const float nq = -fmaxf(__ldg(&g2[e].x), 1e-18f);
-      q2B[(row * S + w) * 2] = nq;
-      q2B[(row * S + ((w + S - 4) % S)) * 2 + 1] = nq;
+      if (Q2P) {
+        q2B[(row * S + w) * 2] = nq;
+        q2B[(row * S + ((w + S - 4) % S)) * 2 + 1] = nq;
+      } else {
+        q2B[row * S + w] = nq;
+      }
     }
   }
   if (TPP > 32)
@@ -297,13 +314,15 @@ k_stage_p(const StageArgs<float> a) {
       fetch(t + 1);
     }
 #pragma unroll
-    for (int l = 0; l < L; ++l) {
+    for (int li = 0; li < L; ++li) {
+      // LAG == 2: last layer first, so BK[l-1] still holds the previous step's row
+      const int l = LAG == 2 ? L - 1 - li : li;
       const int lm = l == 0 ? 0 : l - 1;
-      const int slot = (par + l) & 1;  // == (t - l) & 1, compile-time
+      const int slot = (par + (LAG == 1 ? l : 0)) & 1;  // == (t - LAG*l) & 1, compile-time
       const bool has_u = NTK && (l > 0 || IN == IN_LOAD);
 #define INK(j) (l == 0 ? PK[j] : BK[lm][j])
 #define INU(j) (l == 0 ? PU[j] : BU[lm][j])
-      int r_out = t - l - 1;
+      int r_out = t - LAG * l - 1;
       r_out = full_row(r_out < 0 ? 0 : (r_out > nrows - 1 ? nrows - 1 : r_out));
       const int ch = r_out / S, h = r_out % S;
       const int h2 = (h + ch) % S;
@@ -350,7 +369,7 @@ k_stage_p(const StageArgs<float> a) {
         const float4* q1r = reinterpret_cast<const float4*>(q1A + (l * S + h) * S + w0);
         const float4 qa01 = q1r[0], qa23 = q1r[1];
         const float2 q1p[NP] = {f2(qa01.x, qa01.y), f2(qa01.z, qa01.w), f2(qa23.x, qa23.y), f2(qa23.z, qa23.w)};
-        const unsigned q2row = q2base + (unsigned)((l * S + h2) * S * 8);
+        const unsigned q2row = q2base + (unsigned)((l * S + h2) * S * (Q2P ? 8 : 4));
         const float2 coef2 = f2s(a.lp[l].coef), hab2 = f2s(a.lp[l].hab2);
         const float bias = a.lp[l].bias;
         const bool has_bias = bias != 0.f;
@@ -363,7 +382,13 @@ k_stage_p(const StageArgs<float> a) {
             cu = __ffma2_rn(vD, RU[l][slot][j], tu[j]);
             if (has_bias) cu = __fadd2_rn(cu, f2s(bias));
           }
-          const float2 nq2 = lds_f2(q2row + (unsigned)off2[j] * 8u);
+          float2 nq2;
+          if (Q2P) {
+            nq2 = lds_f2(q2row + (unsigned)off2[j] * 8u);
+          } else {
+            nq2.x = lds_f1(q2row + (unsigned)off2[j] * 4u);
+            nq2.y = lds_f1(q2row + (unsigned)off2[j + 4] * 4u);
+          }
           act_pair<NTK>(ck, cu, q1p[j], nq2, coef2, hab2, BK[l][j], BU[l][j]);
         }
       }
@@ -371,7 +396,7 @@ k_stage_p(const StageArgs<float> a) {
 #undef INU
     }
     // ---- epilogue on the finished row of the last layer ---------------------------------------
-    const int r_fin = t - (L - 1) - 1;
+    const int r_fin = t - LAG * (L - 1) - 1;
     if (r_fin >= 0 && r_fin < nrows) {
       const int rf = full_row(r_fin);
       const int ch = rf / S, h = rf % S;
@@ -437,7 +462,7 @@ k_stage_p(const StageArgs<float> a) {
     }
   };
 
-  const int NSTEPS0 = nrows + (L - 1) + 1;
+  const int NSTEPS0 = nrows + LAG * (L - 1) + 1;
   const int NSTEPS = NSTEPS0 + (NSTEPS0 & 1);
   for (int t0 = 0; t0 < NSTEPS; t0 += 2) {
     step(t0, std::integral_constant<int, 0>{});
