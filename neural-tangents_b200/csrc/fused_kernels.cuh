@@ -50,7 +50,15 @@ struct FLayer {
   T half_ab;  // alpha_next * (a^2+b^2) / 2
   T hab2;     // half_ab - coef * pi/2
   T bias;     // b_std^2 of this layer's conv
+  // Erf(a, b, c) (elementwise.py:67-112), used when kind == ACT_ERF.  The q-map of such a layer
+  // holds D = 1 + 2 b^2 q and 1/sqrt(D) instead of (q, 1/sqrt q).
+  int kind;   // ACT_ABRELU | ACT_ERF
+  T e_in;     // 2 b^2
+  T eA;       // alpha_next * a^2 * 2/pi
+  T eT;       // alpha_next * a^2 b^2 * 4/pi
+  T eC;       // alpha_next * c^2
 };
+enum { ACT_ABRELU = 0, ACT_ERF = 1 };
 
 template <typename T>
 struct StageArgs {
@@ -246,6 +254,57 @@ __device__ __forceinline__ void act_point(double K, double Tn, double q1, double
   To = __dmul_rn(kd, Tn);
 }
 
+// Erf on one element.  With Kh = 2 b^2 K and D = 1 + 2 b^2 q:
+//   s = sqrt(D1 D2 - Kh^2)  (>= 1: the reference's `square_root`),  c = Kh / sqrt(D1 D2),
+//   K' = a^2 (2/pi) asin(c) + c_^2,   T' = a^2 b^2 (4/pi) T / s,
+// asin(c) = copysign(pi/2 - sqrt(1-c^2) G(|c|), c) with the same fit G as the ABRelu path.
+// The q-map kernels call this very function on (K = q, D, D), so a duplicate pair reproduces its
+// diagonal bit for bit.
+__device__ __forceinline__ float rsqrt_acc(float d, float& s) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  s = __fmul_rn(d, r);
+  return r;
+}
+__device__ __forceinline__ double rsqrt_acc(double x, double& s) {
+  // division-free (a DP divide is a subroutine call, which would put the whole kernel on the ABI
+  // register budget): rsqrt seed + coupled Newton steps for g ~ sqrt(x), h ~ 1/(2 sqrt(x))
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = __dmul_rn(x, y), h = __dmul_rn(0.5, y);
+  double r = __fma_rn(-g, h, 0.5);
+  g = __fma_rn(g, r, g);
+  h = __fma_rn(h, r, h);
+  r = __fma_rn(-g, h, 0.5);
+  g = __fma_rn(g, r, g);
+  h = __fma_rn(h, r, h);
+  r = __fma_rn(-g, h, 0.5);
+  s = __fma_rn(g, r, g);
+  return __dmul_rn(2.0, __fma_rn(h, r, h));
+}
+__device__ __forceinline__ float min1(float c) { return fminf(c, 1.f); }
+__device__ __forceinline__ double min1(double c) { return fmin(c, 1.0); }
+__device__ __forceinline__ float copysign_t(float a, float b) { return copysignf(a, b); }
+__device__ __forceinline__ double copysign_t(double a, double b) { return copysign(a, b); }
+
+template <typename T>
+__device__ __forceinline__ void erf_act_point(T K, T Tn, T D1, T rD1, T D2, T rD2, const FLayer<T>& lp,
+                                              T& Ko, T& To) {
+  const T Kh = mul_rn(lp.e_in, K);
+  const T p = mul_rn(D1, D2);
+  const T rb = mul_rn(rD1, rD2);
+  T d = sub_rn(p, mul_rn(Kh, Kh));
+  d = d > (T)0.25 ? d : (T)0.25;  // analytically >= 1
+  T s;
+  const T rs = rsqrt_acc(d, s);
+  const T sn = mul_rn(s, rb);
+  const T c = mul_rn(Kh, rb);
+  const T ac = min1(c < (T)0 ? -c : c);
+  const T u = fma_t(-sn, acos_over_sin(ac), (T)1.57079632679489661923);
+  Ko = fma_t(lp.eA, copysign_t(u, c), lp.eC);
+  To = mul_rn(mul_rn(lp.eT, rs), Tn);
+}
+
 // Vertical link masks per row r = ch*S + h of a pair (row-major march order):
 //   .x = vU: rows r-1 and r are linked (h > 0 and h' = (h+ch) mod S did not wrap),
 //   .y = vD: rows r and r+1 are linked.
@@ -316,10 +375,18 @@ __global__ void k_qmaps(const T* __restrict__ src, int src_mode, int C, T in_sca
       const T q = vsum3<T>(R[(h > 0 ? h - 1 : h) * S + w], R[e], R[(h < S - 1 ? h + 1 : h) * S + w], vU,
                            vD, lp[l].bias);
       typename Vec2<T>::type o;
-      o.x = q;
-      o.y = q > (T)0 ? rsqrt_t(q) : (T)0;
+      if (lp[l].kind == ACT_ERF) {
+        o.x = fma_t(lp[l].e_in, q, (T)1);
+        o.y = rsqrt_t(o.x);
+        T ko, to;
+        erf_act_point<T>(q, (T)0, o.x, o.y, o.x, o.y, lp[l], ko, to);
+        P[e] = ko;
+      } else {
+        o.x = q;
+        o.y = q > (T)0 ? rsqrt_t(q) : (T)0;
+        P[e] = mul_rn(kd_zero_angle(lp[l].coef, lp[l].half_ab, lp[l].hab2), q);  // theta == 0
+      }
       out[(long long)l * S * S + e] = o;
-      P[e] = mul_rn(kd_zero_angle(lp[l].coef, lp[l].half_ab, lp[l].hab2), q);  // theta == 0
     }
     __syncthreads();
   }
@@ -626,7 +693,10 @@ k_stage(const StageArgs<T> a) {
           }
           const V2 qa = q1r[i];
           const V2 qb = lds_v2<T>(q2row + off2[i]);
-          act_point(ck, ct, qa.x, qa.y, qb.x, qb.y, coef, half_ab, hab2, BK[l][i], BT[l][i]);
+          if (a.lp[l].kind == ACT_ERF)
+            erf_act_point<T>(ck, ct, qa.x, qa.y, qb.x, qb.y, a.lp[l], BK[l][i], BT[l][i]);
+          else
+            act_point(ck, ct, qa.x, qa.y, qb.x, qb.y, coef, half_ab, hab2, BK[l][i], BT[l][i]);
         }
       }
 #undef INK
@@ -787,6 +857,8 @@ __global__ void k_mirror(T* __restrict__ m, int n, long long ld) {
 struct FusedStage {
   int L = 0;
   double w2[kMaxFusedLayers], b2[kMaxFusedLayers], a[kMaxFusedLayers], b[kMaxFusedLayers];
+  double c[kMaxFusedLayers];          // Erf only
+  int kind[kMaxFusedLayers] = {0};    // ACT_ABRELU | ACT_ERF
   int epi = EPI_STORE;  // what follows this chunk
 };
 
@@ -811,7 +883,7 @@ inline FusedPlan plan_fused(const std::vector<ntk_op_t>& ops, int n_slots, int o
     return o.kind == NTK_OP_CONV && o.i[0] == 3 && o.i[1] == 3 && o.i[2] == 1 && o.i[3] == 1 &&
            o.i[4] == NTK_PAD_SAME;
   };
-  auto is_act = [](const ntk_op_t& o) { return o.kind == NTK_OP_ABRELU && o.i[0] == 0; };
+  auto is_act = [](const ntk_op_t& o) { return (o.kind == NTK_OP_ABRELU && o.i[0] == 0) || o.kind == NTK_OP_ERF; };
   auto is_pool = [](const ntk_op_t& o) {
     return o.kind == NTK_OP_AVGPOOL && o.i[0] == 2 && o.i[1] == 2 && o.i[2] == 2 && o.i[3] == 2 &&
            o.i[4] != NTK_PAD_CIRCULAR && !(o.i[4] == NTK_PAD_SAME && o.i[5]);
@@ -840,6 +912,8 @@ inline FusedPlan plan_fused(const std::vector<ntk_op_t>& ops, int n_slots, int o
         st.b2[l] = c.i[5] ? c.f[1] : 0.0;
         st.a[l] = act.f[0];
         st.b[l] = act.f[1];
+        st.c[l] = act.kind == NTK_OP_ERF ? act.f[2] : 0.0;
+        st.kind[l] = act.kind == NTK_OP_ERF ? ACT_ERF : ACT_ABRELU;
       }
       st.epi = EPI_STORE;
       plan.stages.push_back(st);
@@ -1009,7 +1083,9 @@ inline int launch_stage_packed_any(cudaStream_t stream, int64_t* launches, int S
 template <typename T, bool NTK>
 int launch_stage(cudaStream_t stream, int64_t* launches, int S, int L, int from_x, int C, int epi,
                  const StageArgs<T>& a) {
-  if (sizeof(T) == 4 && S == 32 && (!from_x || C == 3) && packed_enabled())
+  bool any_erf = false;
+  for (int l = 0; l < L; ++l) any_erf = any_erf || a.lp[l].kind == ACT_ERF;
+  if (sizeof(T) == 4 && S == 32 && (!from_x || C == 3) && packed_enabled() && !any_erf)
     return launch_stage_packed_any(stream, launches, S, L, from_x, epi, NTK, a);
   if (from_x) {
     if (C != 3) return fail(NTK_EUNSUPPORTED, "fused FROM_X stages are instantiated for C == 3");
@@ -1081,6 +1157,15 @@ void stage_constants(const FusedPlan& plan, size_t s, FLayer<T>* lp, double* nex
     lp[l].half_ab = (T)half_ab;
     lp[l].hab2 = (T)(half_ab - coef * 1.57079632679489661923);
     lp[l].bias = (T)st.b2[l];
+    {
+      const double an = via_epi ? 1.0 : alpha_next, pi = 3.14159265358979323846;
+      const double ea = st.a[l], eb = st.b[l], ec = st.c[l];
+      lp[l].kind = st.kind[l];
+      lp[l].e_in = (T)(2.0 * eb * eb);
+      lp[l].eA = (T)(an * ea * ea * 2.0 / pi);
+      lp[l].eT = (T)(an * ea * ea * eb * eb * 4.0 / pi);
+      lp[l].eC = (T)(an * ec * ec);
+    }
     if (l + 1 == st.L) *next_alpha_out = alpha_next;
   }
 }

@@ -11,6 +11,11 @@
                                 int, const T*, int, bool, int, int, int, bool, T*, T*, long long, bool);   \
   KW template int fused_configure_device<T>();
 
+// launch_res<T, NTK, ERF = true> (the Erf-capable residual kernels) lives in res_*_erf.cu
+#define NTK_RES_ERF_INSTANCES(KW, T)                                                                       \
+  KW template int launch_res<T, true, true>(cudaStream_t, int64_t*, int, bool, const ResArgs<T>&);         \
+  KW template int launch_res<T, false, true>(cudaStream_t, int64_t*, int, bool, const ResArgs<T>&);
+
 #define NTK_RES_INSTANCES(KW, T)                                                                         \
   KW template int res_gram<T>(const ResPlan&, Arena&, cudaStream_t, int64_t*, const T*, int, const T*,    \
                               int, bool, int, int, bool, T*, T*, long long, bool);                        \

@@ -75,7 +75,9 @@ struct ResGeom {
   static constexpr int LW = LPG / NWB;
 };
 
-template <typename T, int S, int IN, bool NTK, int CIN>
+// ERF: the network contains Erf activations (a runtime branch per activation row picks the closed
+// form); pure-ABRelu networks run the ERF = false instantiation, which carries no Erf code.
+template <typename T, int S, int IN, bool NTK, int CIN, bool ERF>
 __global__ void __launch_bounds__(ResGeom<S>::NT)
 k_res(const ResArgs<T> a) {
   using G = ResGeom<S>;
@@ -253,7 +255,10 @@ k_res(const ResArgs<T> a) {
       const V2 qa = q1r[i];
       const V2 qb = lds_v2<T>(q2row + off2[i]);
       T ko, to;
-      act_point(k[i], t[i], qa.x, qa.y, qb.x, qb.y, coef, half_ab, hab2, ko, to);
+      if (ERF && a.lp[u].kind == ACT_ERF)
+        erf_act_point<T>(k[i], t[i], qa.x, qa.y, qb.x, qb.y, a.lp[u], ko, to);
+      else
+        act_point(k[i], t[i], qa.x, qa.y, qb.x, qb.y, coef, half_ab, hab2, ko, to);
       k[i] = ko;
       t[i] = to;
     }
@@ -450,6 +455,8 @@ struct QOp {
   int stride;    // Q_CONV: 1 or 2
   int act_id;    // Q_ACT: q-map layer written
   double alpha, bias, kd0;
+  int akind = ACT_ABRELU;  // Q_ACT: ABRelu(a = alpha, b = bias) or Erf(a = alpha, b = bias, c = erf_c)
+  double erf_c = 0.0;
 };
 constexpr int kMaxQOps = 96;
 template <typename T>
@@ -460,7 +467,21 @@ struct QProg {
   short act_id[kMaxQOps];
   T alpha[kMaxQOps], bias[kMaxQOps], kd0[kMaxQOps];
   T coef[kMaxQOps], hab2[kMaxQOps];  // Q_ACT on cross pairs (k_diagnet)
+  signed char akind[kMaxQOps];       // Q_ACT: ACT_ABRELU | ACT_ERF
+  T e_in[kMaxQOps], eA[kMaxQOps], eT[kMaxQOps], eC[kMaxQOps];  // Erf constants (FLayer)
 };
+
+template <typename T>
+__device__ __forceinline__ FLayer<T> qprog_erf_layer(const QProg<T>& prog, int op) {
+  FLayer<T> f;
+  f.coef = f.half_ab = f.hab2 = f.bias = (T)0;
+  f.kind = ACT_ERF;
+  f.e_in = prog.e_in[op];
+  f.eA = prog.eA[op];
+  f.eT = prog.eT[op];
+  f.eC = prog.eC[op];
+  return f;
+}
 
 template <typename T>
 __global__ void k_qprog(const T* __restrict__ x, int S0, int C, T in_scale, const QProg<T>* __restrict__ prog_g,
@@ -512,10 +533,19 @@ __global__ void k_qprog(const T* __restrict__ x, int S0, int C, T in_scale, cons
       for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
         const T q = D[e];
         typename Vec2<T>::type o;
-        o.x = q;
-        o.y = q > (T)0 ? rsqrt_t(q) : (T)0;
+        if (prog.akind[op] == ACT_ERF) {
+          const FLayer<T> f = qprog_erf_layer(prog, op);
+          o.x = fma_t(f.e_in, q, (T)1);
+          o.y = rsqrt_t(o.x);
+          T ko, to;
+          erf_act_point<T>(q, (T)0, o.x, o.y, o.x, o.y, f, ko, to);
+          D[e] = ko;
+        } else {
+          o.x = q;
+          o.y = q > (T)0 ? rsqrt_t(q) : (T)0;
+          D[e] = mul_rn(prog.kd0[op], q);
+        }
         out[e] = o;
-        D[e] = mul_rn(prog.kd0[op], q);
       }
     } else if (kind == Q_COPY) {
       const int S = cur_S[sidx];
@@ -536,7 +566,9 @@ __global__ void k_qprog(const T* __restrict__ x, int S0, int C, T in_scale, cons
 // ---------------------------------------------------------------------------------------
 struct ResBlock {
   double w1, b1, w2, b2, ws, bs;  // W^2 and b^2 of conv1, conv2, shortcut conv
-  double a1, c1, a2, c2;          // ABRelu (a, b) in front of conv1 / conv2
+  double a1, c1, a2, c2;          // ABRelu (a, b) [Erf (a, b)] in front of conv1 / conv2
+  int k1 = ACT_ABRELU, k2 = ACT_ABRELU;
+  double g1 = 0, g2 = 0;          // Erf c
   int stride;                     // of conv1 (and of the shortcut conv)
   bool conv_shortcut;
 };
@@ -555,7 +587,7 @@ inline ResPlan plan_resnet(const std::vector<ntk_op_t>& ops, int out_slot) {
     return o.kind == NTK_OP_CONV && o.i[0] == 3 && o.i[1] == 3 && o.i[2] == stride && o.i[3] == stride &&
            o.i[4] == NTK_PAD_SAME;
   };
-  auto is_act = [](const ntk_op_t& o) { return o.kind == NTK_OP_ABRELU && o.i[0] == 0; };
+  auto is_act = [](const ntk_op_t& o) { return (o.kind == NTK_OP_ABRELU && o.i[0] == 0) || o.kind == NTK_OP_ERF; };
   if (n < 2 || !conv3(ops[0], 1) || ops[0].src != 0) return plan;
   plan.w0 = ops[0].f[0];
   plan.b0 = ops[0].i[5] ? ops[0].f[1] : 0.0;
@@ -571,6 +603,14 @@ inline ResPlan plan_resnet(const std::vector<ntk_op_t>& ops, int out_slot) {
     b.c1 = r1.f[1];
     b.a2 = r2.f[0];
     b.c2 = r2.f[1];
+    if (r1.kind == NTK_OP_ERF) {
+      b.k1 = ACT_ERF;
+      b.g1 = r1.f[2];
+    }
+    if (r2.kind == NTK_OP_ERF) {
+      b.k2 = ACT_ERF;
+      b.g2 = r2.f[2];
+    }
     b.w1 = c1.f[0];
     b.b1 = c1.i[5] ? c1.f[1] : 0.0;
     b.w2 = c2.f[0];
@@ -636,7 +676,7 @@ bool res_supported(const ResPlan& plan, int H, int W, int C) {
   return true;
 }
 
-template <typename T, bool NTK>
+template <typename T, bool NTK, bool ERF>
 int launch_res(cudaStream_t stream, int64_t* launches, int S, bool from_x, const ResArgs<T>& a) {
   (*launches)++;
   auto go = [&](auto kern, int nt, int groups, size_t smem) -> int {
@@ -664,8 +704,8 @@ int launch_res(cudaStream_t stream, int64_t* launches, int S, bool from_x, const
 #define NTK_RES_CASE(SS)                                                                              \
   if (S == SS) {                                                                                      \
     using G = ResGeom<SS>;                                                                            \
-    if (from_x) return go(k_res<T, SS, IN_FROM_X, NTK, 3>, G::NT, G::GROUPS, smem_for(SS, true));     \
-    return go(k_res<T, SS, IN_LOAD, NTK, 1>, G::NT, G::GROUPS, smem_for(SS, false));                  \
+    if (from_x) return go(k_res<T, SS, IN_FROM_X, NTK, 3, ERF>, G::NT, G::GROUPS, smem_for(SS, true)); \
+    return go(k_res<T, SS, IN_LOAD, NTK, 1, ERF>, G::NT, G::GROUPS, smem_for(SS, false));             \
   }
   NTK_RES_CASE(32)
   NTK_RES_CASE(16)
@@ -675,8 +715,9 @@ int launch_res(cudaStream_t stream, int64_t* launches, int S, bool from_x, const
 }
 
 template <typename T>
-FLayer<T> res_act_consts(double a, double b, double alpha_next, double bias) {
-  const double two_pi = 2.0 * 3.14159265358979323846;
+FLayer<T> res_act_consts(double a, double b, double alpha_next, double bias, int kind = ACT_ABRELU,
+                         double erf_c = 0.0) {
+  const double pi = 3.14159265358979323846, two_pi = 2.0 * pi;
   const double d = a - b;
   const double coef = alpha_next * d * d / two_pi, half_ab = alpha_next * (a * a + b * b) / 2.0;
   FLayer<T> f;
@@ -684,6 +725,11 @@ FLayer<T> res_act_consts(double a, double b, double alpha_next, double bias) {
   f.half_ab = (T)half_ab;
   f.hab2 = (T)(half_ab - coef * 1.57079632679489661923);
   f.bias = (T)bias;
+  f.kind = kind;
+  f.e_in = (T)(2.0 * b * b);
+  f.eA = (T)(alpha_next * a * a * 2.0 / pi);
+  f.eT = (T)(alpha_next * a * a * b * b * 4.0 / pi);
+  f.eC = (T)(alpha_next * erf_c * erf_c);
   return f;
 }
 
@@ -698,14 +744,22 @@ int res_gram(const ResPlan& plan, Arena& arena, cudaStream_t stream, int64_t* la
   const bool triangular = symmetric && !full_square && n1 == n2 && n1 > 1;
   const int ns = plan.n_strided & 0xff;
   const size_t nb = plan.blocks.size();
+  bool any_erf = false;
+  for (const ResBlock& B : plan.blocks) any_erf = any_erf || B.k1 == ACT_ERF || B.k2 == ACT_ERF;
   // ---- q-program --------------------------------------------------------------------------
   std::vector<long long> act_off;  // V2 offset of every activation's q-map inside a sample
   std::vector<int> act_S;
   QProg<T> qp{};
-  auto push = [&](int kind, int dst, int src, int stride, int act_id, double alpha, double bias, T kd0) {
+  auto push = [&](int kind, int dst, int src, int stride, int act_id, double alpha, double bias, T kd0,
+                  const FLayer<T>* f = nullptr) {
     const int i = qp.n++;
     qp.coef[i] = (T)0;
     qp.hab2[i] = (T)0;
+    qp.akind[i] = (signed char)(f ? f->kind : ACT_ABRELU);
+    qp.e_in[i] = f ? f->e_in : (T)0;
+    qp.eA[i] = f ? f->eA : (T)0;
+    qp.eT[i] = f ? f->eT : (T)0;
+    qp.eC[i] = f ? f->eC : (T)0;
     qp.kind[i] = kind;
     qp.dst[i] = (signed char)dst;
     qp.src[i] = (signed char)src;
@@ -723,19 +777,19 @@ int res_gram(const ResPlan& plan, Arena& arena, cudaStream_t stream, int64_t* la
     long long off = 0;
     for (size_t b = 0; b < nb; ++b) {
       const ResBlock& B = plan.blocks[b];
-      const FLayer<T> f1 = res_act_consts<T>(B.a1, B.c1, B.w1 / 9.0, B.b1);
-      const FLayer<T> f2 = res_act_consts<T>(B.a2, B.c2, B.w2 / 9.0, B.b2);
+      const FLayer<T> f1 = res_act_consts<T>(B.a1, B.c1, B.w1 / 9.0, B.b1, B.k1, B.g1);
+      const FLayer<T> f2 = res_act_consts<T>(B.a2, B.c2, B.w2 / 9.0, B.b2, B.k2, B.g2);
       push(Q_COPY, 1, 0, 1, 0, 1.0, 0.0, (T)0);
       act_off.push_back(off);
       act_S.push_back(S);
       off += (long long)S * S;
-      push(Q_ACT, 0, 0, 1, (int)act_off.size() - 1, 1.0, 0.0, host_kd0(f1.coef, f1.hab2));
+      push(Q_ACT, 0, 0, 1, (int)act_off.size() - 1, 1.0, 0.0, host_kd0(f1.coef, f1.hab2), &f1);
       push(Q_CONV, 0, 0, B.stride, 0, 1.0, B.b1, (T)0);
       S /= B.stride;
       act_off.push_back(off);
       act_S.push_back(S);
       off += (long long)S * S;
-      push(Q_ACT, 0, 0, 1, (int)act_off.size() - 1, 1.0, 0.0, host_kd0(f2.coef, f2.hab2));
+      push(Q_ACT, 0, 0, 1, (int)act_off.size() - 1, 1.0, 0.0, host_kd0(f2.coef, f2.hab2), &f2);
       push(Q_CONV, 0, 0, 1, 0, 1.0, B.b2, (T)0);
       if (B.conv_shortcut) push(Q_CONV, 1, 1, B.stride, 0, B.ws / 9.0, B.bs, (T)0);
       push(Q_ADD, 0, 1, 1, 0, 1.0, 0.0, (T)0);
@@ -815,8 +869,12 @@ int res_gram(const ResPlan& plan, Arena& arena, cudaStream_t stream, int64_t* la
       };
       auto tsize = [&](int s, int cw_) { return (size_t)(s / cw_) * (s / cw_) * s * s; };
       auto run = [&](int Sx, bool from_x, const ResArgs<T>& a) -> int {
-        if (want_ntk) return launch_res<T, true>(stream, launches, Sx, from_x, a);
-        return launch_res<T, false>(stream, launches, Sx, from_x, a);
+        if (any_erf) {
+          if (want_ntk) return launch_res<T, true, true>(stream, launches, Sx, from_x, a);
+          return launch_res<T, false, true>(stream, launches, Sx, from_x, a);
+        }
+        if (want_ntk) return launch_res<T, true, false>(stream, launches, Sx, from_x, a);
+        return launch_res<T, false, false>(stream, launches, Sx, from_x, a);
       };
       // stem
       int cur = 0;  // index of the buffer holding the current block input Z
@@ -837,8 +895,8 @@ int res_gram(const ResPlan& plan, Arena& arena, cudaStream_t stream, int64_t* la
       for (size_t b = 0; b < nb; ++b) {
         const ResBlock& B = plan.blocks[b];
         const bool last = b + 1 == nb;
-        const FLayer<T> f1 = res_act_consts<T>(B.a1, B.c1, B.w1 / 9.0, B.b1);
-        const FLayer<T> f2 = res_act_consts<T>(B.a2, B.c2, B.w2 / 9.0, B.b2);
+        const FLayer<T> f1 = res_act_consts<T>(B.a1, B.c1, B.w1 / 9.0, B.b1, B.k1, B.g1);
+        const FLayer<T> f2 = res_act_consts<T>(B.a2, B.c2, B.w2 / 9.0, B.b2, B.k2, B.g2);
         const int o1 = (cur + 1) % 3, o2 = (cur + 2) % 3;
         if (B.stride == 1) {
           ResArgs<T> a = base_args();
@@ -1044,7 +1102,10 @@ k_diagnet(const T* __restrict__ x1, const T* __restrict__ x2, int S0, int C, T i
         for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
           const V2 qa = a1[e], qb = a2[e];
           T ko, to;
-          act_point(DK[e], ht ? DT[e] : (T)0, qa.x, qa.y, qb.x, qb.y, prog.coef[op], (T)0, prog.hab2[op], ko, to);
+          if (prog.akind[op] == ACT_ERF)
+            erf_act_point<T>(DK[e], ht ? DT[e] : (T)0, qa.x, qa.y, qb.x, qb.y, qprog_erf_layer(prog, op), ko, to);
+          else
+            act_point(DK[e], ht ? DT[e] : (T)0, qa.x, qa.y, qb.x, qb.y, prog.coef[op], (T)0, prog.hab2[op], ko, to);
           DK[e] = ko;
           if (ht) DT[e] = to;
         }
@@ -1151,11 +1212,15 @@ inline DiagPlan plan_diag(const std::vector<ntk_op_t>& ops, const std::vector<in
       if (b < 0) return DiagPlan();
       plan.ops.push_back(QOp{Q_CONV, b, b, o.i[2], 0, o.f[0] / 9.0, o.i[5] ? o.f[1] : 0.0, 0.0});
       buf_of[o.dst] = b;
-    } else if (o.kind == NTK_OP_ABRELU) {
-      if (o.i[0]) return DiagPlan();
+    } else if (o.kind == NTK_OP_ABRELU || o.kind == NTK_OP_ERF) {
+      if (o.kind == NTK_OP_ABRELU && o.i[0]) return DiagPlan();
       const int b = dst_buf(o.src, src_dies);
       if (b < 0) return DiagPlan();
-      QOp q{Q_ACT, b, b, 1, plan.n_act++, o.f[0], o.f[1], 0.0};  // alpha/bias carry (a, b) of the ABRelu
+      QOp q{Q_ACT, b, b, 1, plan.n_act++, o.f[0], o.f[1], 0.0};  // alpha/bias carry (a, b) of the activation
+      if (o.kind == NTK_OP_ERF) {
+        q.akind = ACT_ERF;
+        q.erf_c = o.f[2];
+      }
       plan.ops.push_back(q);
       buf_of[o.dst] = b;
     } else if (o.kind == NTK_OP_FANINSUM) {
@@ -1208,13 +1273,20 @@ int diag_gram(const DiagPlan& plan, Arena& arena, cudaStream_t stream, int64_t* 
       qp.alpha[i] = (T)o.alpha;
       qp.bias[i] = (T)o.bias;
       qp.kd0[i] = qp.coef[i] = qp.hab2[i] = (T)0;
+      qp.akind[i] = ACT_ABRELU;
+      qp.e_in[i] = qp.eA[i] = qp.eT[i] = qp.eC[i] = (T)0;
       if (o.kind == Q_CONV) {
         Sb[o.dst] = Sb[o.src] / o.stride;
         if (Sb[o.dst] < 1) return fail(NTK_EINVAL, "Conv output would be empty");
       } else if (o.kind == Q_COPY) {
         Sb[o.dst] = Sb[o.src];
       } else if (o.kind == Q_ACT) {
-        const FLayer<T> f = res_act_consts<T>(o.alpha, o.bias, 1.0, 0.0);
+        const FLayer<T> f = res_act_consts<T>(o.alpha, o.bias, 1.0, 0.0, o.akind, o.erf_c);
+        qp.akind[i] = (signed char)f.kind;
+        qp.e_in[i] = f.e_in;
+        qp.eA[i] = f.eA;
+        qp.eT[i] = f.eT;
+        qp.eC[i] = f.eC;
         qp.coef[i] = f.coef;
         qp.hab2[i] = f.hab2;
         qp.kd0[i] = host_kd0(f.coef, f.hab2);

@@ -384,3 +384,72 @@ def test_pool_free_flatten_nets_diagonal_path(nt):
       sym = kernel_fn(x1, None, ('nngp', 'ntk'))
       np.testing.assert_array_equal(sym.ntk, sym.ntk.T)
       np.testing.assert_allclose(sym.nngp, O.kernel_fn(spec, x1, None, ('nngp',))[0], rtol=1e-4)
+
+
+ERF = ('erf', 1., 1., 0.)
+ERF2 = ('erf', 0.8, 1.3, 0.2)
+
+
+def test_erf_fused_stage_path(nt):
+  """Erf closed form (elementwise.py:67-112) inside the fused stage kernels: Myrtle-style stacks
+  with Erf (and mixed Erf / ABRelu) activations at 32x32 and 16x16, against the oracle and the
+  general per-op path; fp32 1e-4 / fp64 1e-10."""
+  from oracle import ntk_oracle as O
+  specs = {
+      'erf_myrtle': ('serial', [cases.conv(W=1.2, b=0.1), ERF, cases.conv(W=1.1, b=0.2), ERF2, pool(),
+                                cases.conv(), ERF, pool(), cases.conv(W=1.3, b=0.), ERF2, cases.conv(), ERF,
+                                ('gap',), ('dense', 1.1, 0.2)]),
+      'mixed': ('serial', [cases.conv(W=1.2, b=0.1), ERF2, cases.conv(), cases.RELU, cases.conv(), ERF, pool(),
+                           cases.conv(), cases.RELU, cases.conv(W=0.9, b=0.3), ERF2, ('gap',), ('dense', 1., 0.)]),
+  }
+  for name, spec in specs.items():
+    for size in (32, 16):
+      x1 = np.random.default_rng(141).standard_normal((3, size, size, 3)).astype(np.float32)
+      x2 = np.random.default_rng(142).standard_normal((2, size, size, 3)).astype(np.float32)
+      ref = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'))
+      _, _, kernel_fn = cases.build(spec, nt.stax)
+      for x64 in (False, True):
+        nt.config.update('enable_x64', x64)
+        out = kernel_fn(x1, x2, ('nngp', 'ntk'))
+        np.testing.assert_allclose(out.nngp, ref[0], rtol=RTOL[x64], err_msg=f'{name} {size} x64={x64}')
+        np.testing.assert_allclose(out.ntk, ref[1], rtol=RTOL[x64], err_msg=f'{name} {size} x64={x64}')
+        np.testing.assert_allclose(kernel_fn(x1, x2, 'nngp'), ref[0], rtol=RTOL[x64])
+        nt.config.update('disable_fusion', True)
+        gen = kernel_fn(x1, x2, ('nngp', 'ntk'))
+        nt.config.update('disable_fusion', False)
+        np.testing.assert_allclose(out.ntk, gen.ntk, rtol=RTOL[x64])
+      nt.config.update('enable_x64', False)
+      sym = kernel_fn(x1, None, ('nngp', 'ntk'))
+      refs = O.kernel_fn(spec, x1, None, ('nngp', 'ntk'))
+      # Erf has no sqrt singularity at duplicates: the diagonal holds to the plain tolerance
+      np.testing.assert_allclose(sym.nngp, refs[0], rtol=1e-4)
+      np.testing.assert_allclose(sym.ntk, refs[1], rtol=1e-4)
+
+
+@pytest.mark.parametrize('size', [16, 32])
+def test_erf_wide_resnet_and_diagonal_paths(nt, size):
+  """WideResNet with Erf (BASELINE config 5, Erf variant) through the column-sparse residual kernels,
+  and a pool-free Erf net ending in Flatten through the diagonal-column kernel."""
+  from oracle import ntk_oracle as O
+  wrn = ('serial', [cases.conv(W=1., b=0.1), cases.wrn_block(1, True, ERF), cases.wrn_block(1, False, ERF2),
+                    cases.wrn_block(2, True, ERF), cases.wrn_block(1, False, cases.RELU), ('gap',),
+                    ('dense', 1., 0.1)])
+  flat = ('serial', [cases.conv(W=1.3, b=0.1), ERF, cases.conv(s=(2, 2)), cases.wrn_block(1, False, ERF),
+                     ERF2, cases.conv(), cases.RELU, ('flatten',), ('dense', 1.1, 0.2)])
+  x1 = np.random.default_rng(151).standard_normal((3, size, size, 3)).astype(np.float32)
+  x2 = np.random.default_rng(152).standard_normal((2, size, size, 3)).astype(np.float32)
+  for name, spec in (('wrn', wrn), ('flat', flat)):
+    ref = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'))
+    refs = O.kernel_fn(spec, x1, None, ('nngp', 'ntk'))
+    _, _, kernel_fn = cases.build(spec, nt.stax)
+    for x64 in (False, True):
+      nt.config.update('enable_x64', x64)
+      out = kernel_fn(x1, x2, ('nngp', 'ntk'))
+      np.testing.assert_allclose(out.nngp, ref[0], rtol=RTOL[x64], err_msg=f'{name} x64={x64}')
+      np.testing.assert_allclose(out.ntk, ref[1], rtol=RTOL[x64], err_msg=f'{name} x64={x64}')
+      sym = kernel_fn(x1, None, ('nngp', 'ntk'))
+      off = ~np.eye(3, dtype=bool)
+      np.testing.assert_allclose(sym.nngp[off], refs[0][off], rtol=RTOL[x64])
+      np.testing.assert_allclose(sym.ntk[off], refs[1][off], rtol=RTOL[x64])
+      np.testing.assert_allclose(np.diag(sym.ntk), np.diag(refs[1]), rtol=RTOL_DUP[x64])
+    nt.config.update('enable_x64', False)
