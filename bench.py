@@ -42,6 +42,9 @@ WORKLOADS = {
     # README.md:399-416: the same 21 layers with Flatten on top (no pooling => only the diagonal
     # column is needed; the reference's diagonal_spatial path).  V100 fp32: 0.0046510 ms / entry.
     'readme21_flatten': (-1, 80 * 32 * 32, 0),
+    # Erf variants (BASELINE config 5 names Relu/Erf): same algorithmic traffic as their Relu twins
+    'wrn_erf': (-2, 46 * E32 + 42 * E16 + 38 * E8, 0),
+    'myrtle10_erf': (10, 8 * E32 + 12 * E16 + 12 * E8, 8 * E32 + 2 * E16),
 }
 PUBLISHED = {('readme21', 'f32'): 1e3 / 2.7001, ('readme21', 'f64'): 1e3 / 6.2058,
              ('readme21_flatten', 'f32'): 1e3 / 0.0046510, ('readme21_flatten', 'f64'): 1e3 / 0.010822}
@@ -53,9 +56,14 @@ def workload_spec(name):
     return ('serial', [cases.conv(W=1., b=None), cases.RELU] * 21 + [('gap',)])
   if name == 'readme21_flatten':
     return ('serial', [cases.conv(W=1., b=None), cases.RELU] * 21 + [('flatten',)])
-  if name == 'wrn':
+  if name == 'myrtle10_erf':
+    spec = cases.myrtle(10)
+    return ('serial', [('erf', 1., 1., 0.) if l == cases.RELU else l for l in spec[1]])
+  if name in ('wrn', 'wrn_erf'):
+    act = cases.RELU if name == 'wrn' else ('erf', 1., 1., 0.)
+
     def group(n, stride):
-      return [cases.wrn_block(stride, True)] + [cases.wrn_block(1, False) for _ in range(n - 1)]
+      return [cases.wrn_block(stride, True, act)] + [cases.wrn_block(1, False, act) for _ in range(n - 1)]
     # Conv defaults of the reference: W_std = 1, b_std = None (cases.wrn_block uses b = 0.1, which
     # exercises the bias path as well)
     return ('serial', [cases.conv(W=1., b=None)] + group(4, 1) + group(4, 2) + group(4, 2) +
@@ -155,21 +163,20 @@ class ClockSampler(threading.Thread):
 # CPU arm: the NumPy float64 oracle (port of the reference path) on all host cores
 # ---------------------------------------------------------------------------------------
 def _cpu_worker(job):
-  depth, seed, n_cols = job
+  name, seed, n_cols = job
   os.environ.setdefault('OMP_NUM_THREADS', '1')
   from oracle import ntk_oracle as O
-  import cases
-  spec = workload_spec({21: 'readme21', 0: 'wrn', -1: 'readme21_flatten', 5: 'myrtle5', 7: 'myrtle7', 10: 'myrtle10'}[depth])
+  spec = workload_spec(name)
   x1 = np.random.default_rng(1000 + seed).standard_normal((1, 32, 32, 3)).astype(np.float32)
   x2 = np.random.default_rng(1).standard_normal((n_cols, 32, 32, 3)).astype(np.float32)
   out = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'), dtype=np.float64)
   return float(out[0].sum() + out[1].sum())
 
 
-def cpu_port_step(pool, depth, cores, n_cols):
+def cpu_port_step(pool, name, cores, n_cols):
   """One bounded CPU step: `cores` workers, each one x1 row against `n_cols` x2 columns."""
   t0 = time.perf_counter()
-  res = pool.map(_cpu_worker, [(depth, s, n_cols) for s in range(cores)])
+  res = pool.map(_cpu_worker, [(name, s, n_cols) for s in range(cores)])
   dt = time.perf_counter() - t0
   assert all(np.isfinite(r) for r in res)
   return cores * n_cols, dt
@@ -184,15 +191,14 @@ def run_reference(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
-  depth = WORKLOADS[args.workload][0]
   cores = len(os.sched_getaffinity(0))
   pool = make_cpu_pool(cores)
   try:
     for _ in range(min(args.warmup, 1)):
-      cpu_port_step(pool, depth, cores, 1)
+      cpu_port_step(pool, args.workload, cores, 1)
     entries, t_tot = 0, 0.0
     for _ in range(args.steps):
-      n, dt = cpu_port_step(pool, depth, cores, args.ref_cols)
+      n, dt = cpu_port_step(pool, args.workload, cores, args.ref_cols)
       entries += n
       t_tot += dt
   finally:
@@ -364,7 +370,7 @@ def run_ours(args):
     roof['whole_net_frac'] = roof['whole_net_achieved'] / pk['hbm_gbs']
   else:
     achieved = b1 * b2 * args.steps * elems_net * sz / (ms_dev * 1e-3) / 1e9
-    roof.update({'kernel': ('k_res (column-sparse residual kernels, all launches of the step)' if depth == 0 else
+    roof.update({'kernel': ('k_res (column-sparse residual kernels, all launches of the step)' if depth in (0, -2) else
                             'k_diagnet (diagonal column only)' if depth == -1
                             else 'per-op path (all kernels of the step)'), 'achieved': achieved,
                  'frac': achieved / pk['hbm_gbs'], 'traffic': None})
@@ -390,8 +396,8 @@ def run_ours(args):
     cores = len(os.sched_getaffinity(0))
     pool = make_cpu_pool(cores)
     try:
-      cpu_port_step(pool, depth, cores, 1)
-      n, dt = cpu_port_step(pool, depth, cores, args.ref_cols)
+      cpu_port_step(pool, args.workload, cores, 1)
+      n, dt = cpu_port_step(pool, args.workload, cores, args.ref_cols)
     finally:
       pool.terminate()
     line['cpu_baseline'] = {

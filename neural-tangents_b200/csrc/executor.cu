@@ -15,6 +15,10 @@
 namespace ntk {
 NTK_FUSED_INSTANCES(extern, float)
 NTK_FUSED_INSTANCES(extern, double)
+NTK_FUSED_ERF_INSTANCES(extern, float)
+NTK_FUSED_ERF_INSTANCES(extern, double)
+NTK_RES_ERF_INSTANCES(extern, float)
+NTK_RES_ERF_INSTANCES(extern, double)
 NTK_RES_INSTANCES(extern, float)
 NTK_RES_INSTANCES(extern, double)
 }  // namespace ntk
@@ -862,8 +866,10 @@ int ntk_context_create(int32_t device, size_t workspace_bytes, ntk_context_t** o
   }
   NTK_CUDA(cudaMalloc((void**)&c->ws, workspace_bytes));
   c->ws_bytes = workspace_bytes;
-  NTK_TRY(fused_configure_device<float>());
-  NTK_TRY(fused_configure_device<double>());
+  NTK_TRY((fused_configure_device<float, false>()));
+  NTK_TRY((fused_configure_device<double, false>()));
+  NTK_TRY((fused_configure_device<float, true>()));
+  NTK_TRY((fused_configure_device<double, true>()));
   NTK_TRY(stage_packed_configure());
   *out = c.release();
   return NTK_OK;

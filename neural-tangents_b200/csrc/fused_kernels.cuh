@@ -288,9 +288,9 @@ __device__ __forceinline__ float copysign_t(float a, float b) { return copysignf
 __device__ __forceinline__ double copysign_t(double a, double b) { return copysign(a, b); }
 
 template <typename T>
-__device__ __forceinline__ void erf_act_point(T K, T Tn, T D1, T rD1, T D2, T rD2, const FLayer<T>& lp,
+__device__ __forceinline__ void erf_act_point(T K, T Tn, T D1, T rD1, T D2, T rD2, T e_in, T eA, T eT, T eC,
                                               T& Ko, T& To) {
-  const T Kh = mul_rn(lp.e_in, K);
+  const T Kh = mul_rn(e_in, K);
   const T p = mul_rn(D1, D2);
   const T rb = mul_rn(rD1, rD2);
   T d = sub_rn(p, mul_rn(Kh, Kh));
@@ -301,8 +301,8 @@ __device__ __forceinline__ void erf_act_point(T K, T Tn, T D1, T rD1, T D2, T rD
   const T c = mul_rn(Kh, rb);
   const T ac = min1(c < (T)0 ? -c : c);
   const T u = fma_t(-sn, acos_over_sin(ac), (T)1.57079632679489661923);
-  Ko = fma_t(lp.eA, copysign_t(u, c), lp.eC);
-  To = mul_rn(mul_rn(lp.eT, rs), Tn);
+  Ko = fma_t(eA, copysign_t(u, c), eC);
+  To = mul_rn(mul_rn(eT, rs), Tn);
 }
 
 // Vertical link masks per row r = ch*S + h of a pair (row-major march order):
@@ -379,7 +379,7 @@ __global__ void k_qmaps(const T* __restrict__ src, int src_mode, int C, T in_sca
         o.x = fma_t(lp[l].e_in, q, (T)1);
         o.y = rsqrt_t(o.x);
         T ko, to;
-        erf_act_point<T>(q, (T)0, o.x, o.y, o.x, o.y, lp[l], ko, to);
+        erf_act_point<T>(q, (T)0, o.x, o.y, o.x, o.y, lp[l].e_in, lp[l].eA, lp[l].eT, lp[l].eC, ko, to);
         P[e] = ko;
       } else {
         o.x = q;
@@ -414,7 +414,9 @@ struct StageGeom {
 // row sample x1[i] and its q-maps are staged once and shared (more resident warps per SM).
 // RC ("runtime columns"): march only the ch columns [col_start, col_start + col_count) -- used by
 // the self-pair pipeline; the cross-pair kernels keep compile-time trip counts.
-template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN, int SH, bool RC>
+// ERF: the stage may contain Erf layers (runtime branch per layer); ERF = false instantiations carry
+// no Erf code, so the ABRelu hot path is unchanged by it.
+template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN, int SH, bool RC, bool ERF>
 __global__ void __launch_bounds__(StageGeom<S, WPT, SH>::NT)
 k_stage(const StageArgs<T> a) {
   using G = StageGeom<S, WPT, SH>;
@@ -693,8 +695,9 @@ k_stage(const StageArgs<T> a) {
           }
           const V2 qa = q1r[i];
           const V2 qb = lds_v2<T>(q2row + off2[i]);
-          if (a.lp[l].kind == ACT_ERF)
-            erf_act_point<T>(ck, ct, qa.x, qa.y, qb.x, qb.y, a.lp[l], BK[l][i], BT[l][i]);
+          if (ERF && a.lp[l].kind == ACT_ERF)
+            erf_act_point<T>(ck, ct, qa.x, qa.y, qb.x, qb.y, a.lp[l].e_in, a.lp[l].eA, a.lp[l].eT, a.lp[l].eC,
+                             BK[l][i], BT[l][i]);
           else
             act_point(ck, ct, qa.x, qa.y, qb.x, qb.y, coef, half_ab, hab2, BK[l][i], BT[l][i]);
         }
@@ -987,10 +990,10 @@ size_t stage_smem_bytes() {
   return (size_t)G::GROUPS * (xs1 + xs2 + 2 * qm + stg) * sizeof(T);
 }
 
-template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN, int SH = 1, bool RC = false>
+template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN, bool ERF, int SH = 1, bool RC = false>
 int launch_stage_impl(cudaStream_t stream, int64_t* launches, const StageArgs<T>& a) {
   using G = StageGeom<S, WPT, SH>;
-  auto kern = k_stage<T, S, WPT, L, IN, EPI, NTK, CIN, SH, RC>;
+  auto kern = k_stage<T, S, WPT, L, IN, EPI, NTK, CIN, SH, RC, ERF>;
   const size_t smem = stage_smem_bytes<T, S, WPT, L, IN, EPI, NTK, CIN, SH>();
   static thread_local bool configured = false;
   if (!configured) {
@@ -1014,52 +1017,52 @@ inline int share_override() {
   return v;
 }
 
-template <typename T, int S, int L, int IN, bool NTK, int CIN>
+template <typename T, int S, int L, int IN, bool NTK, int CIN, bool ERF>
 int launch_stage_epi(cudaStream_t stream, int64_t* launches, int epi, const StageArgs<T>& a) {
   constexpr int WPT = StageCfg<T, S>::WPT;
   // Optional (NTK_B200_SHARE=3): three column samples share one row sample per CTA, i.e. 12
   // instead of 8 resident warps per SM at 32x32 fp32.  Measured on B200: no gain (the issue
   // rate stays ~73 %, profiles/README.md), so independent 128-thread CTAs are the default.
   constexpr int SHC = (sizeof(T) == 4 && S == 32) ? 3 : 1;
-  if (SHC > 1 && !a.self && !a.tri && a.n2 >= SHC && share_override() == 3) {
+  if (!ERF && SHC > 1 && !a.self && !a.tri && a.n2 >= SHC && share_override() == 3) {
     switch (epi) {
       case EPI_STORE:
-        return launch_stage_impl<T, S, WPT, L, IN, EPI_STORE, NTK, CIN, SHC>(stream, launches, a);
+        return launch_stage_impl<T, S, WPT, L, IN, EPI_STORE, NTK, CIN, ERF, SHC>(stream, launches, a);
       case EPI_POOL:
-        return launch_stage_impl<T, S, WPT, L, IN, EPI_POOL, NTK, CIN, SHC>(stream, launches, a);
+        return launch_stage_impl<T, S, WPT, L, IN, EPI_POOL, NTK, CIN, ERF, SHC>(stream, launches, a);
       default:
-        return launch_stage_impl<T, S, WPT, L, IN, EPI_GAP, NTK, CIN, SHC>(stream, launches, a);
+        return launch_stage_impl<T, S, WPT, L, IN, EPI_GAP, NTK, CIN, ERF, SHC>(stream, launches, a);
     }
   }
   if (!NTK && a.col_count != S) {  // self-pair pipeline (nngp only): partial column range
     switch (epi) {
       case EPI_STORE:
-        return launch_stage_impl<T, S, WPT, L, IN, EPI_STORE, false, CIN, 1, true>(stream, launches, a);
+        return launch_stage_impl<T, S, WPT, L, IN, EPI_STORE, false, CIN, ERF, 1, true>(stream, launches, a);
       case EPI_POOL:
-        return launch_stage_impl<T, S, WPT, L, IN, EPI_POOL, false, CIN, 1, true>(stream, launches, a);
+        return launch_stage_impl<T, S, WPT, L, IN, EPI_POOL, false, CIN, ERF, 1, true>(stream, launches, a);
       default:
         return fail(NTK_EINVAL, "partial column range with a GAP epilogue");
     }
   }
   switch (epi) {
     case EPI_STORE:
-      return launch_stage_impl<T, S, WPT, L, IN, EPI_STORE, NTK, CIN>(stream, launches, a);
+      return launch_stage_impl<T, S, WPT, L, IN, EPI_STORE, NTK, CIN, ERF>(stream, launches, a);
     case EPI_POOL:
-      return launch_stage_impl<T, S, WPT, L, IN, EPI_POOL, NTK, CIN>(stream, launches, a);
+      return launch_stage_impl<T, S, WPT, L, IN, EPI_POOL, NTK, CIN, ERF>(stream, launches, a);
     default:
-      return launch_stage_impl<T, S, WPT, L, IN, EPI_GAP, NTK, CIN>(stream, launches, a);
+      return launch_stage_impl<T, S, WPT, L, IN, EPI_GAP, NTK, CIN, ERF>(stream, launches, a);
   }
 }
 
-template <typename T, int S, int IN, bool NTK, int CIN>
+template <typename T, int S, int IN, bool NTK, int CIN, bool ERF>
 int launch_stage_L(cudaStream_t stream, int64_t* launches, int L, int epi, const StageArgs<T>& a) {
   switch (L) {
     case 1:
-      return launch_stage_epi<T, S, 1, IN, NTK, CIN>(stream, launches, epi, a);
+      return launch_stage_epi<T, S, 1, IN, NTK, CIN, ERF>(stream, launches, epi, a);
     case 2:
-      return launch_stage_epi<T, S, 2, IN, NTK, CIN>(stream, launches, epi, a);
+      return launch_stage_epi<T, S, 2, IN, NTK, CIN, ERF>(stream, launches, epi, a);
     default:
-      return launch_stage_epi<T, S, 3, IN, NTK, CIN>(stream, launches, epi, a);
+      return launch_stage_epi<T, S, 3, IN, NTK, CIN, ERF>(stream, launches, epi, a);
   }
 }
 
@@ -1080,22 +1083,31 @@ inline int launch_stage_packed_any(cudaStream_t stream, int64_t* launches, int S
   return launch_stage_packed(stream, launches, S, L, from_x, epi, ntk, a);
 }
 
+// The unpacked stage kernels: ERF = false (pure ABRelu) and ERF = true (Erf-capable) families are
+// instantiated in separate translation units (fused_*.cu / fused_*_erf.cu).
+template <typename T, bool NTK, bool ERF>
+int launch_stage_k(cudaStream_t stream, int64_t* launches, int S, int L, int from_x, int C, int epi,
+                   const StageArgs<T>& a) {
+  if (from_x) {
+    if (C != 3) return fail(NTK_EUNSUPPORTED, "fused FROM_X stages are instantiated for C == 3");
+    if (S == 32) return launch_stage_L<T, 32, IN_FROM_X, NTK, 3, ERF>(stream, launches, L, epi, a);
+    if (S == 16) return launch_stage_L<T, 16, IN_FROM_X, NTK, 3, ERF>(stream, launches, L, epi, a);
+    return launch_stage_L<T, 8, IN_FROM_X, NTK, 3, ERF>(stream, launches, L, epi, a);
+  }
+  if (S == 32) return launch_stage_L<T, 32, IN_LOAD, NTK, 1, ERF>(stream, launches, L, epi, a);
+  if (S == 16) return launch_stage_L<T, 16, IN_LOAD, NTK, 1, ERF>(stream, launches, L, epi, a);
+  return launch_stage_L<T, 8, IN_LOAD, NTK, 1, ERF>(stream, launches, L, epi, a);
+}
+
 template <typename T, bool NTK>
 int launch_stage(cudaStream_t stream, int64_t* launches, int S, int L, int from_x, int C, int epi,
                  const StageArgs<T>& a) {
   bool any_erf = false;
   for (int l = 0; l < L; ++l) any_erf = any_erf || a.lp[l].kind == ACT_ERF;
-  if (sizeof(T) == 4 && S == 32 && (!from_x || C == 3) && packed_enabled() && !any_erf)
+  if (any_erf) return launch_stage_k<T, NTK, true>(stream, launches, S, L, from_x, C, epi, a);
+  if (sizeof(T) == 4 && S == 32 && (!from_x || C == 3) && packed_enabled())
     return launch_stage_packed_any(stream, launches, S, L, from_x, epi, NTK, a);
-  if (from_x) {
-    if (C != 3) return fail(NTK_EUNSUPPORTED, "fused FROM_X stages are instantiated for C == 3");
-    if (S == 32) return launch_stage_L<T, 32, IN_FROM_X, NTK, 3>(stream, launches, L, epi, a);
-    if (S == 16) return launch_stage_L<T, 16, IN_FROM_X, NTK, 3>(stream, launches, L, epi, a);
-    return launch_stage_L<T, 8, IN_FROM_X, NTK, 3>(stream, launches, L, epi, a);
-  }
-  if (S == 32) return launch_stage_L<T, 32, IN_LOAD, NTK, 1>(stream, launches, L, epi, a);
-  if (S == 16) return launch_stage_L<T, 16, IN_LOAD, NTK, 1>(stream, launches, L, epi, a);
-  return launch_stage_L<T, 8, IN_LOAD, NTK, 1>(stream, launches, L, epi, a);
+  return launch_stage_k<T, NTK, false>(stream, launches, S, L, from_x, C, epi, a);
 }
 
 template <typename T>
@@ -1115,8 +1127,9 @@ int launch_qmaps(cudaStream_t stream, int64_t* launches, int S, const T* src, in
 }
 
 // Uploads the vertical link masks to the current device (once per context).  Templated on the
-// dtype so that each translation unit (fused_f32.cu / fused_f64.cu) uploads its own copy.
-template <typename T>
+// dtype and kernel family so that each translation unit (fused_f32.cu, fused_f32_erf.cu, ...)
+// uploads its own copy of the `static __constant__` tables.
+template <typename T, bool ERF>
 int fused_configure_device() {
   for (int S : {32, 16, 8}) {
     std::vector<float2> m((size_t)S * S);

@@ -6,10 +6,18 @@
 #include "fused_kernels.cuh"
 #include "res_kernels.cuh"
 
+// launch_stage_k<T, NTK, ERF = true> (Erf-capable unpacked stage kernels) lives in fused_*_erf.cu
+#define NTK_FUSED_ERF_INSTANCES(KW, T)                                                                     \
+  KW template int launch_stage_k<T, true, true>(cudaStream_t, int64_t*, int, int, int, int, int,           \
+                                                const StageArgs<T>&);                                      \
+  KW template int launch_stage_k<T, false, true>(cudaStream_t, int64_t*, int, int, int, int, int,          \
+                                                 const StageArgs<T>&);                                     \
+  KW template int fused_configure_device<T, true>();
+
 #define NTK_FUSED_INSTANCES(KW, T)                                                                        \
   KW template int fused_gram<T>(const FusedPlan&, Arena&, cudaStream_t, int64_t*, StageProfile*, const T*, \
                                 int, const T*, int, bool, int, int, int, bool, T*, T*, long long, bool);   \
-  KW template int fused_configure_device<T>();
+  KW template int fused_configure_device<T, false>();
 
 // launch_res<T, NTK, ERF = true> (the Erf-capable residual kernels) lives in res_*_erf.cu
 #define NTK_RES_ERF_INSTANCES(KW, T)                                                                       \

@@ -256,7 +256,7 @@ k_res(const ResArgs<T> a) {
       const V2 qb = lds_v2<T>(q2row + off2[i]);
       T ko, to;
       if (ERF && a.lp[u].kind == ACT_ERF)
-        erf_act_point<T>(k[i], t[i], qa.x, qa.y, qb.x, qb.y, a.lp[u], ko, to);
+        erf_act_point<T>(k[i], t[i], qa.x, qa.y, qb.x, qb.y, a.lp[u].e_in, a.lp[u].eA, a.lp[u].eT, a.lp[u].eC, ko, to);
       else
         act_point(k[i], t[i], qa.x, qa.y, qb.x, qb.y, coef, half_ab, hab2, ko, to);
       k[i] = ko;
@@ -538,7 +538,7 @@ __global__ void k_qprog(const T* __restrict__ x, int S0, int C, T in_scale, cons
           o.x = fma_t(f.e_in, q, (T)1);
           o.y = rsqrt_t(o.x);
           T ko, to;
-          erf_act_point<T>(q, (T)0, o.x, o.y, o.x, o.y, f, ko, to);
+          erf_act_point<T>(q, (T)0, o.x, o.y, o.x, o.y, f.e_in, f.eA, f.eT, f.eC, ko, to);
           D[e] = ko;
         } else {
           o.x = q;
@@ -1103,7 +1103,8 @@ k_diagnet(const T* __restrict__ x1, const T* __restrict__ x2, int S0, int C, T i
           const V2 qa = a1[e], qb = a2[e];
           T ko, to;
           if (prog.akind[op] == ACT_ERF)
-            erf_act_point<T>(DK[e], ht ? DT[e] : (T)0, qa.x, qa.y, qb.x, qb.y, qprog_erf_layer(prog, op), ko, to);
+            erf_act_point<T>(DK[e], ht ? DT[e] : (T)0, qa.x, qa.y, qb.x, qb.y, prog.e_in[op], prog.eA[op],
+                             prog.eT[op], prog.eC[op], ko, to);
           else
             act_point(DK[e], ht ? DT[e] : (T)0, qa.x, qa.y, qb.x, qb.y, prog.coef[op], (T)0, prog.hab2[op], ko, to);
           DK[e] = ko;
