@@ -1,4 +1,4 @@
-// Instantiations + launcher of the packed-FP32 stage kernel (stage_packed.cuh): fp32, 32x32.
+// Instantiations + launcher of the packed-FP32 stage kernel (stage_packed.cuh): fp32, 32x32 and 16x16.
 #include "stage_packed.cuh"
 
 namespace ntk {
@@ -75,12 +75,21 @@ int launch_p_L(cudaStream_t stream, int64_t* launches, int L, int epi, const Sta
 
 int launch_stage_packed(cudaStream_t stream, int64_t* launches, int S, int L, int from_x, int epi, bool ntk,
                         const StageArgs<float>& a) {
-  if (S != 32) return fail(NTK_EINVAL, "packed stage kernel is instantiated for S == 32");
-  if (from_x)
-    return ntk ? launch_p_L<32, IN_FROM_X, true, 3>(stream, launches, L, epi, a)
-               : launch_p_L<32, IN_FROM_X, false, 3>(stream, launches, L, epi, a);
-  return ntk ? launch_p_L<32, IN_LOAD, true, 1>(stream, launches, L, epi, a)
-             : launch_p_L<32, IN_LOAD, false, 1>(stream, launches, L, epi, a);
+  if (S == 32) {
+    if (from_x)
+      return ntk ? launch_p_L<32, IN_FROM_X, true, 3>(stream, launches, L, epi, a)
+                 : launch_p_L<32, IN_FROM_X, false, 3>(stream, launches, L, epi, a);
+    return ntk ? launch_p_L<32, IN_LOAD, true, 1>(stream, launches, L, epi, a)
+               : launch_p_L<32, IN_LOAD, false, 1>(stream, launches, L, epi, a);
+  }
+  if (S == 16) {
+    if (from_x)
+      return ntk ? launch_p_L<16, IN_FROM_X, true, 3>(stream, launches, L, epi, a)
+                 : launch_p_L<16, IN_FROM_X, false, 3>(stream, launches, L, epi, a);
+    return ntk ? launch_p_L<16, IN_LOAD, true, 1>(stream, launches, L, epi, a)
+               : launch_p_L<16, IN_LOAD, false, 1>(stream, launches, L, epi, a);
+  }
+  return fail(NTK_EINVAL, "packed stage kernel is instantiated for S == 32 and 16");
 }
 
 int stage_packed_configure() {
