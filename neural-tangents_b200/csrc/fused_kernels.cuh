@@ -195,51 +195,45 @@ __device__ __forceinline__ void act_point(float K, float Tn, float q1, float b1,
   To = __fmul_rn(kd, Tn);
 }
 
-// fp64: same structure with a degree-20 fit of G (|err| < 8e-16) and a Newton square root
+// fp64: same structure with a degree-16 fit of G (|err| < 7e-14) and a Newton square root
 // seeded by MUFU.RSQ64H -- about 45 DP instructions per element instead of ~120 for
 // sqrt + atan2.
 __device__ __forceinline__ double acos_over_sin(double c) {
-  // degree-20 fit of G on [0,1], evaluated with Estrin's scheme: the same 20 FMAs (+4 squarings) as
-  // Horner's rule but a dependent depth of 6 instead of 20 -- the fp64 stage kernel is bound by DFMA
-  // latency (ncu: 40 % of the warp samples are fixed-latency waits), not by DP throughput.
-  const double c2 = __dmul_rn(c, c), c4 = __dmul_rn(c2, c2), c8 = __dmul_rn(c4, c4), c16 = __dmul_rn(c8, c8);
-  const double b0 = __fma_rn(-0.9999999999998898, c, 1.5707963267948963);
-  const double b1 = __fma_rn(-0.6666666662100986, c, 0.7853981633879067);
-  const double b2 = __fma_rn(-0.5333330865934092, c, 0.5890486093468758);
-  const double b3 = __fma_rn(-0.45711379217247317, c, 0.49087069104128306);
-  const double b4 = __fma_rn(-0.40531257550488764, c, 0.4293159767563122);
-  const double b5 = __fma_rn(-0.35579825919378716, c, 0.3823450610436574);
-  const double b6 = __fma_rn(-0.2662737577356398, c, 0.31902721592859684);
-  const double b7 = __fma_rn(-0.12612943586868636, c, 0.19838900896440054);
-  const double b8 = __fma_rn(-0.02601071230644528, c, 0.06524925918867551);
-  const double b9 = __fma_rn(-0.0013425118048028357, c, 0.0074255005353718135);
-  const double b10 = 0.00011498440214312142;
-  const double d0 = __fma_rn(b1, c2, b0);
-  const double d1 = __fma_rn(b3, c2, b2);
-  const double d2 = __fma_rn(b5, c2, b4);
-  const double d3 = __fma_rn(b7, c2, b6);
-  const double d4 = __fma_rn(b9, c2, b8);
-  const double d5 = b10;
-  const double e0 = __fma_rn(d1, c4, d0);
-  const double e1 = __fma_rn(d3, c4, d2);
-  const double e2 = __fma_rn(d5, c4, d4);
-  const double f0 = __fma_rn(e1, c8, e0);
-  return __fma_rn(e2, c16, f0);
+  // degree-16 interpolant of G at the Chebyshev nodes of [0,1] (|err| < 7e-14, 3 decades below the
+  // 1e-10 budget after 10 layers), split into even and odd parts: two independent Horner chains in
+  // c^2 -- 16 FMAs + 1 multiply at a dependent depth of 10.  The fp64 stage kernel is bound by DFMA
+  // latency and DP issue, so both the shorter chains and the lower degree pay (ncu: profiles/).
+  const double y = __dmul_rn(c, c);
+  double e = 0.0006085619653744684;
+  e = __fma_rn(e, y, 0.026115987357625138);
+  e = __fma_rn(e, y, 0.1515026854745219);
+  e = __fma_rn(e, y, 0.32168777107072677);
+  e = __fma_rn(e, y, 0.42153491130233556);
+  e = __fma_rn(e, y, 0.49055899159932126);
+  e = __fma_rn(e, y, 0.5890456114068265);
+  e = __fma_rn(e, y, 0.7853981595839817);
+  e = __fma_rn(e, y, 1.5707963267948286);
+  double o = -0.005808597590519145;
+  o = __fma_rn(o, y, -0.07419324994425795);
+  o = __fma_rn(o, y, -0.24155677597211828);
+  o = __fma_rn(o, y, -0.3804374854745279);
+  o = __fma_rn(o, y, -0.45529076094959686);
+  o = __fma_rn(o, y, -0.5332956171404206);
+  o = __fma_rn(o, y, -0.6666665195234605);
+  o = __fma_rn(o, y, -0.9999999999606062);
+  return __fma_rn(c, o, e);
 }
 
 // sqrt(x) for x >= 0 to ~1 ulp: rsqrt seed + two coupled Newton steps (x == 0 -> ~1e-150).
 __device__ __forceinline__ double sqrt_fast(double x) {
   x = fmax(x, 1e-300);
   double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));  // ~2^-22 relative
   double g = __dmul_rn(x, y), h = __dmul_rn(0.5, y);
-  double r = __fma_rn(-g, h, 0.5);
+  double r = __fma_rn(-g, h, 0.5);  // coupled Newton step: errors ~1e-13
   g = __fma_rn(g, r, g);
   h = __fma_rn(h, r, h);
-  r = __fma_rn(-g, h, 0.5);
-  g = __fma_rn(g, r, g);
-  h = __fma_rn(h, r, h);
-  r = __fma_rn(-g, h, 0.5);
+  r = __fma_rn(-g, h, 0.5);         // final correction of g: below 1 ulp
   return __fma_rn(g, r, g);
 }
 
@@ -277,9 +271,6 @@ __device__ __forceinline__ double rsqrt_acc(double x, double& s) {
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   double g = __dmul_rn(x, y), h = __dmul_rn(0.5, y);
   double r = __fma_rn(-g, h, 0.5);
-  g = __fma_rn(g, r, g);
-  h = __fma_rn(h, r, h);
-  r = __fma_rn(-g, h, 0.5);
   g = __fma_rn(g, r, g);
   h = __fma_rn(h, r, h);
   r = __fma_rn(-g, h, 0.5);
