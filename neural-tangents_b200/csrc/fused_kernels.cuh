@@ -74,7 +74,7 @@ struct StageArgs {
   int n2;         // pair p -> (p / n2, p % n2), or (p, p) when self
   int self;
   int tri;        // pairs enumerate the upper triangle (j >= i) of an n2 x n2 block, row-major
-  int col_start;  // marched ch columns: (col_start + i) mod S, i < col_count  (S for all)
+  int col_start;  // RC: k -- the marched ch columns are 0..k and S-k..S-1 (col_count = 2k+1 of them)
   int col_count;
   T in_scale;     // FROM_X: alpha_1 / C folded into x1
   T epi_scale;    // POOL: alpha_next/16; GAP: 1/S^4; STORE: unused (folded in coef)
@@ -563,11 +563,18 @@ k_stage(const StageArgs<T> a) {
         RT[l][sl][i] = (T)0;
       }
 
-  // Rows marched: nrows = col_count * S; marched row r -> column ch = (col_start + r/S) mod S,
+  // Rows marched: nrows = col_count * S; marched row r -> column ch (see full_row below),
   // full row index rf = ch*S + h (position in the sheared tensor and in the mask table).
   const int nrows = RC ? a.col_count * S : NR;
-  const int col_start = RC ? a.col_start : 0;
-  auto full_row = [&](int r) { return RC ? (((col_start + r / S) % S) * S) + (r % S) : r; };
+  // RC: the marched columns are {0..k} then {S-k..S-1} (k = col_start), i.e. the needed columns in
+  // the SAME relative order as the full march, so the pooled outputs they feed are accumulated in the
+  // same order as in a cross-pair run and a duplicate pair reproduces the self-pair diagonal exactly.
+  const int col_k = RC ? a.col_start : 0;
+  auto full_row = [&](int r) {
+    if (!RC) return r;
+    const int c = r / S;
+    return (c <= col_k ? c : S - (a.col_count - c)) * S + (r % S);
+  };
 
   T gap_k = (T)0, gap_t = (T)0;
   const T* inK = IN == IN_LOAD ? a.inK + p * (long long)NR * S * S + (long long)w0 * S + cw : nullptr;
@@ -1266,7 +1273,7 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
         a.n2 = 1;
         a.self = 1;
         a.col_count = std::min(S, 2 * k_in[s] + 1);
-        a.col_start = a.col_count == S ? 0 : (S - k_in[s]) % S;
+        a.col_start = a.col_count == S ? 0 : k_in[s];
         a.in_scale = in_scale;
         a.epi_scale = (T)(next_alpha / 16.0);
         for (int l = 0; l < plan.stages[s].L; ++l) a.lp[l] = lp[l];

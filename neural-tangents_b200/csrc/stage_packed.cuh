@@ -251,8 +251,15 @@ k_stage_p(const StageArgs<float> a) {
       }
 
   const int nrows = RC ? a.col_count * S : NR;
-  const int col_start = RC ? a.col_start : 0;
-  auto full_row = [&](int r) { return RC ? (((col_start + r / S) % S) * S) + (r % S) : r; };
+  // RC: the marched columns are {0..k} then {S-k..S-1} (k = col_start), i.e. the needed columns in
+  // the SAME relative order as the full march, so the pooled outputs they feed are accumulated in the
+  // same order as in a cross-pair run and a duplicate pair reproduces the self-pair diagonal exactly.
+  const int col_k = RC ? a.col_start : 0;
+  auto full_row = [&](int r) {
+    if (!RC) return r;
+    const int c = r / S;
+    return (c <= col_k ? c : S - (a.col_count - c)) * S + (r % S);
+  };
 
   float2 gap_k = f2s(0.f), gap_u = f2s(0.f);
   const float* inK = IN == IN_LOAD ? a.inK + p * (long long)NR * S * S + (long long)w0 * S + cw : nullptr;

@@ -453,3 +453,26 @@ def test_erf_wide_resnet_and_diagonal_paths(nt, size):
       np.testing.assert_allclose(sym.ntk[off], refs[1][off], rtol=RTOL[x64])
       np.testing.assert_allclose(np.diag(sym.ntk), np.diag(refs[1]), rtol=RTOL_DUP[x64])
     nt.config.update('enable_x64', False)
+
+
+def test_duplicate_pairs_reproduce_self_diagonal(nt):
+  """Exact-duplicate pairs (the diagonal of K(x, x), or x2 holding copies of x1 rows) hit the
+  sqrt singularity of the arccos kernel: q1 q2 - K^2 must be exactly 0 on their diagonal, which needs
+  the self-pair (q-map) pipeline and the cross-pair kernels to agree bit for bit across pooled stage
+  boundaries (same arithmetic, same accumulation order).  With that the duplicates meet the ordinary
+  tolerance instead of the sqrt(eps) bound of SURVEY Appendix A."""
+  from oracle import ntk_oracle as O
+  x = np.random.default_rng(161).standard_normal((4, 32, 32, 3)).astype(np.float32)
+  d = np.eye(4, dtype=bool)
+  for spec in (cases.myrtle(10), cases.myrtle(5, 'gap')):
+    ref = O.kernel_fn(spec, x, None, ('nngp', 'ntk'))
+    _, _, kernel_fn = cases.build(spec, nt.stax)
+    for x64, tol in ((False, 1e-5), (True, 1e-11)):
+      nt.config.update('enable_x64', x64)
+      sym = kernel_fn(x, None, ('nngp', 'ntk'))
+      dup = kernel_fn(x, x.copy(), ('nngp', 'ntk'))
+      for out in (sym, dup):
+        np.testing.assert_allclose(out.nngp[d], ref[0][d], rtol=tol)
+        np.testing.assert_allclose(out.ntk[d], ref[1][d], rtol=tol)
+      np.testing.assert_array_equal(np.diag(sym.ntk), np.diag(dup.ntk))
+  nt.config.update('enable_x64', False)
