@@ -76,6 +76,7 @@ struct StageArgs {
   int tri;        // pairs enumerate the upper triangle (j >= i) of an n2 x n2 block, row-major
   int col_start;  // RC: k -- the marched ch columns are 0..k and S-k..S-1 (col_count = 2k+1 of them)
   int col_count;
+  int zero_out;   // POOL epilogue: the kernel zeroes its pair's output itself (no host memset)
   T in_scale;     // FROM_X: alpha_1 / C folded into x1
   T epi_scale;    // POOL: alpha_next/16; GAP: 1/S^4; STORE: unused (folded in coef)
   FLayer<T> lp[kMaxFusedLayers];
@@ -1365,8 +1366,15 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
           a.outK = nxt;
           a.outT = want_ntk ? nxt + (size_t)P * out_per : nullptr;
           a.epi_scale = (T)(next_alpha / 16.0);
-          if (epi == EPI_POOL)
-            NTK_CUDA(cudaMemsetAsync(nxt, 0, (size_t)P * out_per * sizeof(T) * (want_ntk ? 2 : 1), stream));
+          if (epi == EPI_POOL) {
+            // the packed kernels zero their own (pre-accumulation) output while other CTAs compute
+            // -- DRAM is idle in this kernel -- instead of a 4.8 GB memset in front of every launch
+            bool erf_stage = false;
+            for (int l = 0; l < plan.stages[s].L; ++l) erf_stage = erf_stage || plan.stages[s].kind[l] == ACT_ERF;
+            a.zero_out = (sizeof(T) == 4 && (S == 32 || S == 16) && C == 3 && packed_enabled() && !erf_stage) ? 1 : 0;
+            if (!a.zero_out)
+              NTK_CUDA(cudaMemsetAsync(nxt, 0, (size_t)P * out_per * sizeof(T) * (want_ntk ? 2 : 1), stream));
+          }
         }
         a.qm1 = qm1[s] + (size_t)r0 * plan.stages[s].L * S * S * 2;
         a.qm2 = qm2[s] + (size_t)c0 * plan.stages[s].L * S * S * 2;

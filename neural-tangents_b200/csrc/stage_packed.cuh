@@ -191,6 +191,16 @@ k_stage_p(const StageArgs<float> a) {
     sj = (int)(p % a.n2);
   }
 
+  // ---- POOL: zero this pair's output (accumulated into with red.global.add below) -----------
+  if (EPI == EPI_POOL && a.zero_out && live) {
+    constexpr int OUT4 = SO * SO * SO * SO / 4;
+    float4* zk = reinterpret_cast<float4*>(a.outK + p * (long long)(SO * SO * SO * SO));
+    for (int e = tg; e < OUT4; e += TPP) zk[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (NTK) {
+      float4* zt = reinterpret_cast<float4*>(a.outT + p * (long long)(SO * SO * SO * SO));
+      for (int e = tg; e < OUT4; e += TPP) zt[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   // ---- stage the two samples and their q-maps -------------------------------------------
   {
     if (IN == IN_FROM_X) {
