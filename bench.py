@@ -45,7 +45,20 @@ WORKLOADS = {
     # Erf variants (BASELINE config 5 names Relu/Erf): same algorithmic traffic as their Relu twins
     'wrn_erf': (-2, 46 * E32 + 42 * E16 + 38 * E8, 0),
     'myrtle10_erf': (10, 8 * E32 + 12 * E16 + 12 * E8, 8 * E32 + 2 * E16),
+    # BASELINE configs[0]: infinite FCN (Dense-Relu x3 + Dense), 784-d inputs (examples/infinite_fcn.py
+    # deepened x3).  Input Gram on the tensor cores (tcgen05 3xTF32 / DMMA fp64); the
+    # per-entry epilogue is O(1), so the "algorithmic traffic" is just x1, x2 and the two result matrices.
+    'fcn': (-4, 0, 0),
 }
+FCN_DIM = 784
+
+
+def input_shape(name, n):
+  return (n, FCN_DIM) if name == 'fcn' else (n, 32, 32, 3)
+
+
+def input_dims(name):
+  return (0, 0, FCN_DIM) if name == 'fcn' else (32, 32, 3)
 PUBLISHED = {('readme21', 'f32'): 1e3 / 2.7001, ('readme21', 'f64'): 1e3 / 6.2058,
              ('readme21_flatten', 'f32'): 1e3 / 0.0046510, ('readme21_flatten', 'f64'): 1e3 / 0.010822}
 
@@ -56,6 +69,8 @@ def workload_spec(name):
     return ('serial', [cases.conv(W=1., b=None), cases.RELU] * 21 + [('gap',)])
   if name == 'readme21_flatten':
     return ('serial', [cases.conv(W=1., b=None), cases.RELU] * 21 + [('flatten',)])
+  if name == 'fcn':
+    return cases.fcn(3, 2., 0.05)
   if name == 'myrtle10_erf':
     spec = cases.myrtle(10)
     return ('serial', [('erf', 1., 1., 0.) if l == cases.RELU else l for l in spec[1]])
@@ -69,6 +84,10 @@ def workload_spec(name):
     return ('serial', [cases.conv(W=1., b=None)] + group(4, 1) + group(4, 2) + group(4, 2) +
             [cases.pool((8, 8), (1, 1)), ('flatten',), ('dense', 1., 0.)])
   return cases.myrtle(WORKLOADS[name][0])
+
+
+def workload_label(name):
+  return f'{name}_{FCN_DIM}d_nngp+ntk' if name == 'fcn' else f'{name}_32x32x3_nngp+ntk'
 
 
 def stage_elements(depth, per_layer):
@@ -167,10 +186,12 @@ def _cpu_worker(job):
   os.environ.setdefault('OMP_NUM_THREADS', '1')
   from oracle import ntk_oracle as O
   spec = workload_spec(name)
-  x1 = np.random.default_rng(1000 + seed).standard_normal((1, 32, 32, 3)).astype(np.float32)
-  x2 = np.random.default_rng(1).standard_normal((n_cols, 32, 32, 3)).astype(np.float32)
+  if name == 'fcn':
+    n_cols *= 250   # an FCN entry costs ~1e-4 of a Myrtle-10 entry on the CPU
+  x1 = np.random.default_rng(1000 + seed).standard_normal(input_shape(name, 1 if name != 'fcn' else 250)).astype(np.float32)
+  x2 = np.random.default_rng(1).standard_normal(input_shape(name, n_cols)).astype(np.float32)
   out = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'), dtype=np.float64)
-  return float(out[0].sum() + out[1].sum())
+  return float(out[0].sum() + out[1].sum()), int(out[0].size)
 
 
 def cpu_port_step(pool, name, cores, n_cols):
@@ -178,8 +199,8 @@ def cpu_port_step(pool, name, cores, n_cols):
   t0 = time.perf_counter()
   res = pool.map(_cpu_worker, [(name, s, n_cols) for s in range(cores)])
   dt = time.perf_counter() - t0
-  assert all(np.isfinite(r) for r in res)
-  return cores * n_cols, dt
+  assert all(np.isfinite(r[0]) for r in res)
+  return sum(r[1] for r in res), dt
 
 
 def make_cpu_pool(cores):
@@ -211,7 +232,7 @@ def run_reference(args):
       'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
       'ms_per_step': 1e3 * t_tot / args.steps, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-      'config': {'workload': f'{args.workload}_32x32x3_nngp+ntk',
+      'config': {'workload': workload_label(args.workload),
                  'block': [cores, args.ref_cols]},
       'cpu_baseline': {'value': value, 'unit': 'entries/s', 'cores': cores, 'kind': 'port',
                        'sample': sample},
@@ -251,12 +272,15 @@ def run_ours(args):
   low = stax._lowered(stax._strip(kernel_fn._spec), False, False, True)
   b1, b2 = args.block
   # synthetic inputs: each rank owns a slab of x1 rows; x2 comes from rank 0
-  x1_h = np.random.default_rng(100 + rank).standard_normal((b1, 32, 32, 3)).astype(np_dt)
-  x2_h = np.random.default_rng(1).standard_normal((b2, 32, 32, 3)).astype(np_dt)
+  if args.workload == 'fcn' and args.block == [96, 96]:
+    b1 = b2 = 1000                                                  # BASELINE configs[0]: 1000 x 1000
+  H_, W_, C_ = input_dims(args.workload)
+  x1_h = np.random.default_rng(100 + rank).standard_normal(input_shape(args.workload, b1)).astype(np_dt)
+  x2_h = np.random.default_rng(1).standard_normal(input_shape(args.workload, b2)).astype(np_dt)
   ctx = _lib.get_context(local)
   stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
   x1_d = torch.from_numpy(x1_h).to(dev)
-  x2_d = torch.from_numpy(x2_h).to(dev) if rank == 0 else torch.empty((b2, 32, 32, 3), dtype=t_dt, device=dev)
+  x2_d = torch.from_numpy(x2_h).to(dev) if rank == 0 else torch.empty(input_shape(args.workload, b2), dtype=t_dt, device=dev)
   out_d = torch.empty((2, b1, b2), dtype=t_dt, device=dev)          # this rank's nngp / ntk slab
   gath_d = torch.empty((world, 2, b1, b2), dtype=t_dt, device=dev) if world > 1 else None
   flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
@@ -267,10 +291,10 @@ def run_ours(args):
     if world > 1:
       dist.broadcast(x2_d, src=0)                                   # x2 over NVLink
     if args.symmetric:   # K(x1, x1): upper triangle + mirror (not the headline configuration)
-      _lib.gram_device(ctx, low.program, np_dt, x1_d.data_ptr(), b1, None, b1, 32, 32, 3,
+      _lib.gram_device(ctx, low.program, np_dt, x1_d.data_ptr(), b1, None, b1, H_, W_, C_,
                        flags, out_d[0].data_ptr(), out_d[1].data_ptr(), b2)
       return
-    _lib.gram_device(ctx, low.program, np_dt, x1_d.data_ptr(), b1, x2_d.data_ptr(), b2, 32, 32, 3,
+    _lib.gram_device(ctx, low.program, np_dt, x1_d.data_ptr(), b1, x2_d.data_ptr(), b2, H_, W_, C_,
                      flags, out_d[0].data_ptr(), out_d[1].data_ptr(), b2)
     if world > 1:
       dist.all_gather_into_tensor(gath_d, out_d)                    # result slabs; no reduction
@@ -315,7 +339,8 @@ def run_ours(args):
   # end to end through the public API: HOST buffers in, HOST results out (nt.batch -> C-ABI)
   import math
   g_ = math.gcd(b1, b2)
-  e2e_bs = max(d for d in range(1, min(args.e2e_batch, g_) + 1) if g_ % d == 0)
+  e2e_cap = 500 if args.workload == 'fcn' else args.e2e_batch      # FCN entries are ~1e4 x cheaper: bigger blocks
+  e2e_bs = max(d for d in range(1, min(e2e_cap, g_) + 1) if g_ % d == 0)
   batched = nt.batch(kernel_fn, batch_size=e2e_bs, device_count=0)
   for _ in range(max(1, min(args.warmup, 2))):   # untimed warm-up of the host path (IO buffers)
     batched(x1_h, None if args.symmetric else x2_h, ('nngp', 'ntk'))
@@ -352,7 +377,9 @@ def run_ours(args):
     tpp = ncu_traffic_per_pair(args.workload, args.dtype)
     roof.update({
         'kernel': ('k_stage<S=32,L=3,FROM_X,STORE> (first 3 fused Conv+Relu layers)' if depth == 21 else
-                   'k_stage<S=32,L=%d,FROM_X,POOL> (fused Conv+Relu x%d + AvgPool)' % ((3, 3) if depth == 10 else (2, 2))),
+                   ('k_stage_p' if (not x64 and args.workload != 'myrtle10_erf') else 'k_stage') +
+                   '<S=32,L=%d,FROM_X,POOL> (fused Conv+%s x%d + AvgPool)' % (
+                       (3, 'Erf' if args.workload == 'myrtle10_erf' else 'Relu', 3) if depth == 10 else (2, 'Relu', 2))),
         'achieved': achieved, 'frac': achieved / pk['hbm_gbs'],
         'algorithmic_bytes_per_launch': alg_bytes_per_pair * st0_pairs // st0_n,
         'avg_launch_ms': st0_ms / st0_n, 'launches_timed': st0_n,
@@ -368,6 +395,16 @@ def run_ours(args):
                    'achieved': dom['algorithmic_GBps'], 'frac': dom['algorithmic_GBps'] / pk['hbm_gbs'],
                    'avg_launch_ms': dom['ms_per_launch'], 'traffic': None})
     roof['whole_net_frac'] = roof['whole_net_achieved'] / pk['hbm_gbs']
+  elif args.workload == 'fcn':
+    # HBM: read x1, x2 once, write nngp + ntk; tensor pipe: the 2 b1 b2 d input GEMM (x3 passes for 3xTF32)
+    bytes_step = (b1 + b2) * FCN_DIM * sz + 2 * b1 * b2 * sz
+    achieved = bytes_step * args.steps / (ms_dev * 1e-3) / 1e9
+    flops = 2.0 * b1 * b2 * FCN_DIM * (3 if not x64 else 1) * args.steps / (ms_dev * 1e-3)
+    roof.update({'kernel': 'k_gram_tf32x3 (tcgen05 kind::tf32, 3-pass split) + Dense/Relu chain' if not x64 else
+                           'k_gram_dmma (mma.sync f64) + Dense/Relu chain',
+                 'achieved': achieved, 'frac': achieved / pk['hbm_gbs'], 'traffic': None,
+                 'input_gemm_tflops_incl_split_passes': flops / 1e12,
+                 'note': 'whole step (GEMM + 7 elementwise launches); launch-latency bound at 1000 x 1000'})
   else:
     achieved = b1 * b2 * args.steps * elems_net * sz / (ms_dev * 1e-3) / 1e9
     roof.update({'kernel': ('k_res (column-sparse residual kernels, all launches of the step)' if depth in (0, -2) else
@@ -381,7 +418,7 @@ def run_ours(args):
       'vs_baseline': (value / world / PUBLISHED[(args.workload, args.dtype)]
                       if (args.workload, args.dtype) in PUBLISHED else None),
       'dtype': args.dtype, 'data': 'synthetic',
-      'config': {'workload': f'{args.workload}_32x32x3_nngp+ntk', 'block_per_gpu': [b1, b2],
+      'config': {'workload': workload_label(args.workload), 'block_per_gpu': [b1, b2],
                  'parallelism': f'x1-row partition over {world} rank(s), x2 broadcast, slabs all-gathered',
                  'l2': 'flushed (256 MiB write) between timed steps', 'fusion': ('per-layer stencil kernels' if args.per_layer else not args.no_fusion),
                  'symmetric_x2_none': bool(args.symmetric)},

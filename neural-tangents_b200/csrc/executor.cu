@@ -31,6 +31,7 @@ struct ntk_program {
   int n_slots = 0;
   int out_slot = 0;
   std::vector<int> last_use;  // per slot: index of the last op reading it (or n_ops if output)
+  FcnProg fcn{};              // Dense/ABRelu/Erf chain on [N, d] inputs (k_fcn_chain); n == 0 if not matched
   FusedPlan fused;            // fast-path plan (fused_kernels.cuh); empty if not matched
   FusedPlan per_layer;        // same kernels, one layer per launch (NTK_FLAG_PER_LAYER)
   ResPlan res;                // residual-network plan (res_kernels.cuh)
@@ -627,6 +628,63 @@ int ensure_io(ntk_context* ctx, int which, size_t bytes) {
   return NTK_OK;
 }
 
+// Recognises a serial chain of Dense / ABRelu (no do_stabilize) / Erf ops from slot 0 to the output.
+FcnProg plan_fcn(const std::vector<ntk_op_t>& ops, int out_slot) {
+  FcnProg f{};
+  const int n = (int)ops.size();
+  if (n == 0 || n > kMaxFcnOps || ops[0].kind != NTK_OP_DENSE) return FcnProg{};
+  bool gaussian = false;
+  for (int k = 0; k < n; ++k) {
+    const ntk_op_t& o = ops[k];
+    if (o.src != (k == 0 ? 0 : ops[k - 1].dst)) return FcnProg{};
+    if (o.kind == NTK_OP_DENSE) {
+      gaussian = true;
+    } else if ((o.kind == NTK_OP_ABRELU && o.i[0] == 0) || o.kind == NTK_OP_ERF) {
+      if (!gaussian) return FcnProg{};  // the per-op path reports the reference's error
+      gaussian = false;
+    } else {
+      return FcnProg{};
+    }
+    f.kind[k] = o.kind;
+    f.has_bias[k] = o.kind == NTK_OP_DENSE ? o.i[0] : 0;
+    f.f0[k] = o.f[0];
+    f.f1[k] = o.f[1];
+    f.f2[k] = o.f[2];
+  }
+  if (ops[n - 1].dst != out_slot) return FcnProg{};
+  f.n = n;
+  return f;
+}
+
+// [N, d] inputs + a Dense/ABRelu/Erf chain: input Gram on the tensor cores, then ONE elementwise launch.
+template <typename T>
+int fcn_gram(ntk_context* ctx, Env& env, const FcnProg& fp, const T* x1, int n1, const T* x2, int n2,
+             bool symmetric, int C, bool want_ntk, T* out_nngp, T* out_ntk, long long ld) {
+  Arena& arena = ctx->arena;
+  T* c1 = (T*)arena.alloc((size_t)n1 * sizeof(T));
+  T* c2 = symmetric ? c1 : (T*)arena.alloc((size_t)n2 * sizeof(T));
+  if (!c1 || !c2) return fail(NTK_ENOMEM, "workspace too small");
+  const T inv_c = (T)(1.0 / (double)C);
+  LAUNCH(env, k_rowdot<T>, grid_for((long long)n1 * 32), kThreads, 0, x1, x1, c1, (long long)n1, PairMap{1, 1}, C, inv_c);
+  if (!symmetric)
+    LAUNCH(env, k_rowdot<T>, grid_for((long long)n2 * 32), kThreads, 0, x2, x2, c2, (long long)n2, PairMap{1, 1}, C, inv_c);
+  int t1 = n1;
+  T* K0 = nullptr;
+  for (;;) {
+    K0 = (T*)arena.alloc((size_t)t1 * n2 * sizeof(T));
+    if (K0) break;
+    if (t1 <= 1) return fail(NTK_ENOMEM, "workspace too small for one row of the input Gram");
+    t1 = (t1 + 1) / 2;
+  }
+  for (int r0 = 0; r0 < n1; r0 += t1) {
+    const int a1 = std::min(t1, n1 - r0);
+    NTK_TRY((fcn_input_gram<T>(false, env.stream, &env.launches, x1 + (size_t)r0 * C, a1, x2, n2, C, K0)));
+    LAUNCH(env, k_fcn_chain<T>, grid_for((long long)a1 * n2), kThreads, 0, (const T*)K0, (const T*)(c1 + r0),
+           (const T*)c2, a1, n2, fp, out_nngp + (size_t)r0 * ld, want_ntk ? out_ntk + (size_t)r0 * ld : (T*)nullptr, ld);
+  }
+  return NTK_OK;
+}
+
 template <typename T>
 int gram_device_t(ntk_context* ctx, const ntk_program* prog, const T* x1, int n1, const T* x2,
                   int n2, int H, int W, int C, uint32_t flags, const OutPtrs& out) {
@@ -641,6 +699,15 @@ int gram_device_t(ntk_context* ctx, const ntk_program* prog, const T* x1, int n1
   env.ctx = ctx;
   env.arena = &ctx->arena;
   env.stream = ctx->stream;
+
+  // Fully-connected networks: tensor-core input Gram + one elementwise launch for the whole chain.
+  if (!(flags & NTK_FLAG_NO_FUSION) && prog->fcn.n > 0 && H == 0 && !out.cov1 && !out.cov2) {
+    ctx->arena.reset(ctx->ws, ctx->ws_bytes, false);
+    int st = fcn_gram<T>(ctx, env, prog->fcn, x1, n1, x2, n2, symmetric, C, want_ntk, (T*)out.nngp,
+                         (T*)out.ntk, out.ld);
+    ctx->launches += env.launches;
+    return st;
+  }
 
   // Fast path: fused diagonal-marching kernels (fused_kernels.cuh).
   if (!(flags & NTK_FLAG_NO_FUSION) && prog->fused.ok && H > 0 &&
@@ -775,6 +842,7 @@ int ntk_program_create(const ntk_op_t* ops, int32_t n_ops, int32_t n_slots, int3
   p->n_slots = n_slots;
   p->out_slot = out_slot;
   NTK_TRY(validate_program(*p));
+  p->fcn = plan_fcn(p->ops, p->out_slot);
   p->fused = plan_fused(p->ops, p->n_slots, p->out_slot);
   p->per_layer = plan_fused(p->ops, p->n_slots, p->out_slot, 1);
   p->res = plan_resnet(p->ops, p->out_slot);

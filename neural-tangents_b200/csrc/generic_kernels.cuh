@@ -377,6 +377,67 @@ __global__ void k_dense(T* __restrict__ K, T* __restrict__ Tt, long long n, T w2
   }
 }
 
+// ---- fully-connected networks in one launch -------------------------------------------------
+// For [N, d] inputs every op after the input Gram is elementwise on the [n1, n2] matrix and on the two
+// per-sample variance vectors, so the whole Dense / ABRelu / Erf chain (BASELINE configs[0])
+// runs per entry in registers: K0[i,j], cov1[i], cov2[j] -> nngp[i,j], ntk[i,j].  The arithmetic is that of
+// k_dense / k_act (same expressions, same order), so the result is bit-identical to the per-op path.
+constexpr int kMaxFcnOps = 48;
+struct FcnProg {
+  int n;
+  int kind[kMaxFcnOps];      // NTK_OP_DENSE | NTK_OP_ABRELU | NTK_OP_ERF
+  int has_bias[kMaxFcnOps];  // Dense
+  double f0[kMaxFcnOps], f1[kMaxFcnOps], f2[kMaxFcnOps];
+};
+
+template <typename T>
+__global__ void k_fcn_chain(const T* __restrict__ K0, const T* __restrict__ c1, const T* __restrict__ c2,
+                            int t1, int t2, const FcnProg prog, T* __restrict__ nngp, T* __restrict__ ntk,
+                            long long ld) {
+  const long long P = (long long)t1 * t2;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < P;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / t2), j = (int)(idx % t2);
+    T k = K0[idx], q1 = c1[i], q2 = c2[j], t = (T)0;
+    bool t_zero = true;
+    for (int o = 0; o < prog.n; ++o) {
+      if (prog.kind[o] == NTK_OP_DENSE) {  // linear.py:899-926
+        const T w2 = (T)prog.f0[o], b2 = (T)(prog.has_bias[o] ? prog.f1[o] : 0.0);
+        k = fma_t(w2, k, b2);
+        t = t_zero ? k : fma_t(w2, t, k);
+        t_zero = false;
+        q1 = fma_t(w2, q1, b2);
+        q2 = fma_t(w2, q2, b2);
+      } else if (prog.kind[o] == NTK_OP_ABRELU) {  // elementwise.py:444-455
+        const T a = (T)prog.f0[o], b = (T)prog.f1[o];
+        const T coef_s = (a - b) * (a - b) / ((T)2 * Consts<T>::pi());
+        const T half_ab = (a * a + b * b) / (T)2;
+        T ko, dot, d1, d2;
+        abrelu_point<T>(k, q1 * q2, coef_s, half_ab, ko, dot);
+        k = ko;
+        t *= dot;
+        abrelu_point<T>(q1, q1 * q1, coef_s, half_ab, d1, dot);
+        abrelu_point<T>(q2, q2 * q2, coef_s, half_ab, d2, dot);
+        q1 = d1;
+        q2 = d2;
+      } else {  // Erf: elementwise.py:84-93 + kernel.py:426-439
+        const T a = (T)prog.f0[o], b = (T)prog.f1[o];
+        const T bb = b * b, aa = a * a, cc = (T)(prog.f2[o] * prog.f2[o]);
+        T ko, dot, d1, d2;
+        erf_point<T>(k * bb, ((T)1 + (T)2 * bb * q1) * ((T)1 + (T)2 * bb * q2), ko, dot);
+        k = fma_t(aa, ko, cc);
+        t = aa * (bb * t * dot);
+        erf_point<T>(q1 * bb, ((T)1 + (T)2 * bb * q1) * ((T)1 + (T)2 * bb * q1), d1, dot);
+        erf_point<T>(q2 * bb, ((T)1 + (T)2 * bb * q2) * ((T)1 + (T)2 * bb * q2), d2, dot);
+        q1 = fma_t(aa, d1, cc);
+        q2 = fma_t(aa, d2, cc);
+      }
+    }
+    nngp[(long long)i * ld + j] = k;
+    if (ntk) ntk[(long long)i * ld + j] = t;
+  }
+}
+
 // ---- FanInSum: branching.py:87-93 ---------------------------------------------------
 template <typename T>
 __global__ void k_add(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
