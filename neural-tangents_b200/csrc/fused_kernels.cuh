@@ -1011,32 +1011,12 @@ int launch_stage_impl(cudaStream_t stream, int64_t* launches, const StageArgs<T>
   return NTK_OK;
 }
 
-inline int share_override() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("NTK_B200_SHARE");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
-
 template <typename T, int S, int L, int IN, bool NTK, int CIN, bool ERF>
 int launch_stage_epi(cudaStream_t stream, int64_t* launches, int epi, const StageArgs<T>& a) {
   constexpr int WPT = StageCfg<T, S>::WPT;
-  // Optional (NTK_B200_SHARE=3): three column samples share one row sample per CTA, i.e. 12
-  // instead of 8 resident warps per SM at 32x32 fp32.  Measured on B200: no gain (the issue
-  // rate stays ~73 %, profiles/README.md), so independent 128-thread CTAs are the default.
-  constexpr int SHC = (sizeof(T) == 4 && S == 32) ? 3 : 1;
-  if (!ERF && SHC > 1 && !a.self && !a.tri && a.n2 >= SHC && share_override() == 3) {
-    switch (epi) {
-      case EPI_STORE:
-        return launch_stage_impl<T, S, WPT, L, IN, EPI_STORE, NTK, CIN, ERF, SHC>(stream, launches, a);
-      case EPI_POOL:
-        return launch_stage_impl<T, S, WPT, L, IN, EPI_POOL, NTK, CIN, ERF, SHC>(stream, launches, a);
-      default:
-        return launch_stage_impl<T, S, WPT, L, IN, EPI_GAP, NTK, CIN, ERF, SHC>(stream, launches, a);
-    }
-  }
+  // (An SH = 3 variant -- three column samples sharing one row sample per CTA, 12 instead of 8 resident
+  // warps per SM -- was measured on B200 in round 1: no gain, the issue rate stayed at ~73 %.  The
+  // kernel keeps the SH template parameter; the variant is no longer instantiated.)
   if (!NTK && a.col_count != S) {  // self-pair pipeline (nngp only): partial column range
     switch (epi) {
       case EPI_STORE:
