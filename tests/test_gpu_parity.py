@@ -476,3 +476,33 @@ def test_duplicate_pairs_reproduce_self_diagonal(nt):
         np.testing.assert_allclose(out.ntk[d], ref[1][d], rtol=tol)
       np.testing.assert_array_equal(np.diag(sym.ntk), np.diag(dup.ntk))
   nt.config.update('enable_x64', False)
+
+
+def test_packed_and_scalar_stage_kernels_agree(nt, tmp_path):
+  """`k_stage_p` (packed FFMA2, U = T + K carry, MUFU.RSQ normalisation) and the scalar `k_stage` are two
+  implementations of the same stage; NTK_B200_NO_PACKED=1 (read at library load) selects the scalar one in a
+  child process.  They agree far inside the fp32 budget on Myrtle-10 and on a 16x16 stack."""
+  import os
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  code = (
+      "import sys, numpy as np\n"
+      f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests', 'golden')!r})\n"
+      "import cases, neural_tangents_b200 as nt\n"
+      "x1 = np.random.default_rng(171).standard_normal((5, 32, 32, 3)).astype(np.float32)\n"
+      "x2 = np.random.default_rng(172).standard_normal((4, 32, 32, 3)).astype(np.float32)\n"
+      "_, _, k = cases.build(cases.myrtle(10), nt.stax)\n"
+      "a = k(x1, x2, ('nngp', 'ntk')); s = k(x1, None, ('nngp', 'ntk'))\n"
+      "_, _, k16 = cases.build(cases.CASES['myrtle10_16px'][0], nt.stax)\n"
+      "b = k16(x1[:, ::2, ::2], x2[:, ::2, ::2], ('nngp', 'ntk'))\n"
+      "np.savez(sys.argv[1], a0=a.nngp, a1=a.ntk, s0=s.nngp, s1=s.ntk, b0=b.nngp, b1=b.ntk)\n")
+  outs = {}
+  for tag, env_extra in (('packed', {}), ('scalar', {'NTK_B200_NO_PACKED': '1'})):
+    path = str(tmp_path / f'{tag}.npz')
+    env = dict(os.environ, **env_extra)
+    env.pop('NTK_B200_NO_PACKED', None) if tag == 'packed' else None
+    subprocess.run([sys.executable, '-c', code, path], check=True, env=env, timeout=600)
+    outs[tag] = np.load(path)
+  for key in ('a0', 'a1', 's0', 's1', 'b0', 'b1'):
+    np.testing.assert_allclose(outs['packed'][key], outs['scalar'][key], rtol=3e-6, err_msg=key)
