@@ -6,8 +6,10 @@ Flatten/FanOut/FanInSum networks and the `nt.batch` Gram tiling.  All arithmetic
 runs in hand-written sm_100a CUDA behind the C-ABI of `include/ntk_b200.h`
 (`libntk_b200.so`); there is no CPU fallback.
 
-Public names mirror `neural_tangents/__init__.py:21-33`.
+Public names mirror `neural_tangents/__init__.py:21-33`; `predict` holds the closed-form inference that
+consumes the Gram matrices (`gp_inference`, `gradient_descent_mse_ensemble`).
 """
+from . import predict  # noqa: F401
 from . import stax  # noqa: F401
 from ._config import config  # noqa: F401
 from .batching import batch  # noqa: F401

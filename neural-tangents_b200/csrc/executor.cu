@@ -7,6 +7,7 @@
 // scatters the tile into the result matrices.  There is no CPU path.
 #include <algorithm>
 #include <memory>
+#include <type_traits>
 
 #include "common.cuh"
 #include "generic_kernels.cuh"
@@ -668,6 +669,29 @@ int fcn_gram(ntk_context* ctx, Env& env, const FcnProg& fp, const T* x1, int n1,
   LAUNCH(env, k_rowdot<T>, grid_for((long long)n1 * 32), kThreads, 0, x1, x1, c1, (long long)n1, PairMap{1, 1}, C, inv_c);
   if (!symmetric)
     LAUNCH(env, k_rowdot<T>, grid_for((long long)n2 * 32), kThreads, 0, x2, x2, c2, (long long)n2, PairMap{1, 1}, C, inv_c);
+  // fp32: split x into TF32 hi / lo parts once, then the pipelined tcgen05 GEMM (gemm_kernels.cuh)
+  static const bool no_tc = getenv("NTK_B200_NO_TC") != nullptr;
+  static const bool no_pipe = getenv("NTK_B200_NO_GEMM_PIPE") != nullptr;
+  float *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
+  const int d_pad = gram_pad_k(C);
+  bool pipe = false;
+  if constexpr (std::is_same<T, float>::value) {
+    if (C >= 16 && !no_tc && !no_pipe) {
+      b_hi = (float*)arena.alloc((size_t)n2 * d_pad * sizeof(float));
+      b_lo = (float*)arena.alloc((size_t)n2 * d_pad * sizeof(float));
+      a_hi = symmetric ? b_hi : (float*)arena.alloc((size_t)n1 * d_pad * sizeof(float));
+      a_lo = symmetric ? b_lo : (float*)arena.alloc((size_t)n1 * d_pad * sizeof(float));
+      if (b_hi && b_lo && a_hi && a_lo) {
+        pipe = true;
+        env.launches++;
+        NTK_TRY(launch_split_tf32(env.stream, x2, n2, C, b_hi, b_lo));
+        if (!symmetric) {
+          env.launches++;
+          NTK_TRY(launch_split_tf32(env.stream, x1, n1, C, a_hi, a_lo));
+        }
+      }
+    }
+  }
   int t1 = n1;
   T* K0 = nullptr;
   for (;;) {
@@ -678,7 +702,15 @@ int fcn_gram(ntk_context* ctx, Env& env, const FcnProg& fp, const T* x1, int n1,
   }
   for (int r0 = 0; r0 < n1; r0 += t1) {
     const int a1 = std::min(t1, n1 - r0);
-    NTK_TRY((fcn_input_gram<T>(false, env.stream, &env.launches, x1 + (size_t)r0 * C, a1, x2, n2, C, K0)));
+    if constexpr (std::is_same<T, float>::value) {
+      if (pipe) {
+        env.launches++;
+        NTK_TRY(launch_gram_tc_pipe(env.stream, a_hi + (size_t)r0 * d_pad, a_lo + (size_t)r0 * d_pad, a1, b_hi, b_lo,
+                                    n2, C, K0, (long long)n2));
+      }
+    }
+    if (!pipe)
+      NTK_TRY((fcn_input_gram<T>(false, env.stream, &env.launches, x1 + (size_t)r0 * C, a1, x2, n2, C, K0)));
     LAUNCH(env, k_fcn_chain<T>, grid_for((long long)a1 * n2), kThreads, 0, (const T*)K0, (const T*)(c1 + r0),
            (const T*)c2, a1, n2, fp, out_nngp + (size_t)r0 * ld, want_ntk ? out_ntk + (size_t)r0 * ld : (T*)nullptr, ld);
   }

@@ -34,10 +34,15 @@
 namespace ntk {
 
 constexpr int kMaxFusedLayers = 3;
-#ifndef NTK_LAG
-#define NTK_LAG 1
-#endif
-constexpr int LAG = NTK_LAG;  // rows of lag between consecutive fused layers (1 or 2)
+// Rows of lag between consecutive fused layers of k_stage.  1: a layer consumes the row its predecessor
+// produced in the same step (fewest live registers).  2: the row of the previous step, so the L layer blocks
+// of a step are independent.  Measured on B200 (Myrtle-10 stage 0): fp32 is bound by issue / register-file
+// bandwidth and gains nothing from the extra ILP; fp64 is bound by DFMA latency (31 % fixed-latency waits at
+// 8 warps per SM) and gains 12 % (134.2 -> 117.9 ms) at 216 registers.
+template <typename T>
+struct StageLag {
+  static constexpr int value = sizeof(T) == 8 ? 2 : 1;
+};
 
 enum { IN_FROM_X = 0, IN_LOAD = 1 };
 enum { EPI_STORE = 0, EPI_POOL = 1, EPI_GAP = 2 };
@@ -418,6 +423,7 @@ k_stage(const StageArgs<T> a) {
   using G = StageGeom<S, WPT, SH>;
   using V2 = typename Vec2<T>::type;
   constexpr int TPP = G::TPP, LPG = G::LPG, NWB = G::NWB, LW = G::LW, NR = G::NR;
+  constexpr int LAG = StageLag<T>::value;
   constexpr int SO = S / 2;
   constexpr int SP = S + 1;  // padded staging row
 

@@ -1,0 +1,258 @@
+"""Closed-form inference with the NNGP / NTK Gram matrices: the immediate caller of the hot path
+(SURVEY §8f row 1).  Mirrors `neural_tangents.predict.gp_inference` (`_src/predict.py:566-750`) and
+`gradient_descent_mse_ensemble` (`_src/predict.py:753-1100`) for the case the B200 path produces:
+`[n1, n2]` kernel matrices (outputs block-diagonal along the logit axis, `trace_axes=(-1,)`).
+
+The Gram matrices come from `kernel_fn` (libntk_b200.so on the GPU); the n x n factorisations
+here are host float64 linear algebra (Cholesky for t = None, one symmetric eigendecomposition
+for finite t), which is what the reference does with `jax.scipy.linalg` on its default device.
+Moving these solves onto the GPU next to the Gram slabs is the round-2 item of DESIGN.md.
+"""
+import collections
+from typing import Callable, Optional
+
+import numpy as np
+
+Gaussian = collections.namedtuple('Gaussian', 'mean covariance')   # `_src/predict.py:552-563`
+
+
+def _canonicalize_get(get):
+  """`utils.canonicalize_get` (`_src/utils/utils.py:139-155`) for the two names used here."""
+  if get is None:
+    return True, ('nngp', 'ntk')
+  if isinstance(get, str):
+    get, single = (get,), True
+  else:
+    get, single = tuple(get), False
+  get = tuple(g.lower() for g in get)
+  if not get:
+    raise ValueError('"get" must be non-empty.')
+  if len(set(get)) < len(get):
+    raise ValueError('All entries in "get" must be unique. Got {}'.format(get))
+  return (False if not single else None), get
+
+
+def _pack(get_arg, names, values):
+  """str -> the value, tuple / None -> a namedtuple over `names` (`utils.get_namedtuple`)."""
+  if isinstance(get_arg, str):
+    return values[0]
+  return collections.namedtuple('Gaussians', names)(*values)
+
+
+def _attr(k, name):
+  """An ndarray stands for whichever kernel is asked; otherwise read the field (`_get_attr`)."""
+  if k is None:
+    return None
+  if isinstance(k, np.ndarray):
+    return k
+  v = getattr(k, name, None)
+  if v is None:
+    raise ValueError(f'The kernel `{name}` is required but missing from {type(k).__name__}.')
+  return np.asarray(v)
+
+
+def _as_matrix(k, what):
+  k = np.asarray(k, dtype=np.float64)
+  if k.ndim != 2:
+    raise NotImplementedError(f'{what} must be an [n1, n2] matrix (got shape {k.shape}); kernels with spatial '
+                              'or `trace_axes=()` structure are outside the B200 hot path.')
+  return k
+
+
+def _regularize(a: np.ndarray, diag_reg: float, absolute: bool) -> np.ndarray:
+  """K + diag_reg * (mean of the diagonal unless absolute) * I   (`_add_diagonal_regularizer`)."""
+  n = a.shape[0]
+  scale = diag_reg if absolute else diag_reg * np.trace(a) / n
+  out = a.copy()
+  out[np.diag_indices(n)] += scale
+  return out
+
+
+class _CholSolver:
+  """Cached Cholesky factor of a regularised train-train matrix (`_get_cho_solve`)."""
+
+  def __init__(self, k_dd, diag_reg, absolute):
+    import scipy.linalg
+    self._sl = scipy.linalg
+    self.factor = scipy.linalg.cho_factor(_regularize(k_dd, diag_reg, absolute), lower=False)
+
+  def __call__(self, b):
+    return self._sl.cho_solve(self.factor, np.asarray(b, dtype=np.float64))
+
+
+def _check_targets(y_train, trace_axes):
+  y = np.asarray(y_train, dtype=np.float64)
+  if y.ndim != 2:
+    raise NotImplementedError('y_train must be [n_train, n_outputs].')
+  ta = tuple(a % y.ndim for a in (trace_axes if isinstance(trace_axes, (tuple, list)) else (trace_axes,)))
+  if ta != (1,):
+    raise NotImplementedError('only trace_axes=(-1,) (one kernel shared by all outputs) is supported.')
+  return y
+
+
+def gp_inference(k_train_train, y_train, diag_reg: float = 0., diag_reg_absolute_scale: bool = False,
+                 trace_axes=(-1,)) -> Callable:
+  """Posterior of the NNGP / NTK / NTKGP given train-train kernels (`_src/predict.py:566-750`).
+
+  Returns `predict_fn(get=None, k_test_train=None, k_test_test=None)`; `get` in 'nngp', 'ntk',
+  'ntkgp' or a tuple; a mean, or `Gaussian(mean, covariance)` when `k_test_test` is given.
+  """
+  y = _check_targets(y_train, trace_axes)
+  solvers, alphas = {}, {}
+
+  def solver(name):
+    if name not in solvers:
+      solvers[name] = _CholSolver(_as_matrix(_attr(k_train_train, name), 'k_train_train'), diag_reg,
+                                  diag_reg_absolute_scale)
+    return solvers[name]
+
+  def k_inv_y(name):
+    if name not in alphas:
+      alphas[name] = solver(name)(y)
+    return alphas[name]
+
+  def predict_fn(get=None, k_test_train=None, k_test_test=None):
+    _, names = _canonicalize_get(get)
+    values = []
+    for g in names:
+      if g not in ('nngp', 'ntk', 'ntkgp'):
+        raise ValueError(g)
+      k = 'ntk' if g == 'ntkgp' else g
+      k_dd = _as_matrix(_attr(k_train_train, k), 'k_train_train')
+      k_td = None if k_test_train is None else _as_matrix(_attr(k_test_train, k), 'k_test_train')
+      mean = y.copy() if k_td is None else k_td @ k_inv_y(k)
+      if k_test_test is None:
+        values.append(mean)
+        continue
+      if k_td is None:                      # train set: N(y_train, 0)
+        values.append(Gaussian(mean, np.zeros_like(k_dd)))
+        continue
+      if g == 'ntk' and (isinstance(k_train_train, np.ndarray) or isinstance(k_test_train, np.ndarray)):
+        raise ValueError('The NTK posterior covariance on the test set needs both the NTK and the NNGP '
+                         'train-train and test-train matrices (namedtuples with `nngp` and `ntk`).')
+      init = 'ntk' if g == 'ntkgp' else 'nngp'              # kernel of the wide net at initialisation
+      init_td = _as_matrix(_attr(k_test_train, init), 'k_test_train')
+      k_tt = _as_matrix(_attr(k_test_test, init), 'k_test_test')
+      kinv_init_dt = solver(k)(init_td.T)                      # K_k^-1 K_init(train, test)
+      if g in ('nngp', 'ntkgp'):
+        cov = k_tt - k_td @ kinv_init_dt
+      else:
+        # Theta_td Theta^-1 K_dd Theta^-1 Theta_dt - (Theta_td Theta^-1 K_dt + transpose) + K_tt
+        w = solver('ntk')(k_td.T)
+        nngp_dd = _as_matrix(_attr(k_train_train, 'nngp'), 'k_train_train')
+        cross = k_td @ kinv_init_dt
+        cov = w.T @ nngp_dd @ w - (cross + cross.T) + k_tt
+      values.append(Gaussian(mean, cov))
+    return _pack(get, names, values)
+
+  return predict_fn
+
+
+def gradient_descent_mse_ensemble(kernel_fn, x_train, y_train, learning_rate: float = 1., diag_reg: float = 0.,
+                                  diag_reg_absolute_scale: bool = False, trace_axes=(-1,),
+                                  **kernel_fn_train_train_kwargs) -> Callable:
+  """Mean and covariance of an infinite ensemble of infinitely wide networks trained on MSE with
+  continuous gradient descent for time `t` (`_src/predict.py:753-1100`).
+
+  Returns `predict_fn(t=None, x_test=None, get=None, compute_cov=False)`.  `t=None` is infinite
+  time (linear solves); finite `t` (scalar or array) works in the eigenbasis of the regularised
+  train-train matrix with the reference's time normalisation `t * learning_rate / y_train.size`.
+  """
+  y = _check_targets(y_train, trace_axes)
+  norm = float(y.size)
+  cache, eig, inf = {}, {}, {}
+
+  def k_train_train(names):
+    missing = tuple(n for n in names if n not in cache)
+    if missing:
+      res = kernel_fn(x_train, None, missing if len(missing) > 1 else missing[0], **kernel_fn_train_train_kwargs)
+      if len(missing) == 1:
+        cache[missing[0]] = np.asarray(res)
+      else:
+        for n in missing:
+          cache[n] = np.asarray(getattr(res, n))
+    K = collections.namedtuple('Kernel', names)
+    return K(*(cache[n] for n in names))
+
+  def eigenspace(name):
+    if name not in eig:
+      k_dd = _regularize(_as_matrix(getattr(k_train_train((name,)), name), 'k_train_train'), diag_reg,
+                         diag_reg_absolute_scale)
+      eig[name] = np.linalg.eigh(k_dd)
+    return eig[name]
+
+  def dependency(names, compute_cov):
+    for g in names:
+      if g not in ('nngp', 'ntk'):
+        raise NotImplementedError('Can only get either "nngp" or "ntk" predictions, got %s.' % g)
+    dep = ()
+    if 'nngp' in names or ('ntk' in names and compute_cov):
+      dep += ('nngp',)
+    if 'ntk' in names:
+      dep += ('ntk',)
+    return dep
+
+  def predict_fn(t=None, x_test=None, get=None, compute_cov: bool = False, **kernel_fn_test_test_kwargs):
+    _, names = _canonicalize_get(get)
+    dep = dependency(names, compute_cov)
+    k_dd = k_train_train(dep)
+    kw = dict(kernel_fn_train_train_kwargs)
+    kw.update(kernel_fn_test_test_kwargs)
+    if x_test is None:
+      k_td, nngp_tt = None, (True if compute_cov else None)
+    else:
+      res = kernel_fn(x_test, x_train, dep if len(dep) > 1 else dep[0], **kw)
+      K = collections.namedtuple('Kernel', dep)
+      k_td = K(*( [np.asarray(res)] if len(dep) == 1 else [np.asarray(getattr(res, n)) for n in dep]))
+      nngp_tt = np.asarray(kernel_fn(x_test, None, 'nngp', **kw)) if compute_cov else None
+
+    if t is None:                                             # infinite time
+      if dep not in inf:
+        inf[dep] = gp_inference(k_dd, y, diag_reg, diag_reg_absolute_scale, trace_axes)
+      # train set with compute_cov: any non-None k_test_test (the posterior there is N(y_train, 0))
+      k_tt = np.zeros((1, 1)) if nngp_tt is True else nngp_tt
+      return inf[dep](get=get if get is not None else names, k_test_train=k_td, k_test_test=k_tt)
+
+    t_arr = np.asarray(t, dtype=np.float64) * learning_rate
+    t_shape = t_arr.shape
+    ts = t_arr.reshape(-1)
+    values = []
+    for g in names:
+      evals, evecs = eigenspace(g)
+      lam = np.maximum(evals, 0.)
+      decay = np.exp(-np.outer(ts, lam) / norm)               # [T, n]  exp(-lambda t / |y|)
+      one_minus = -np.expm1(-np.outer(ts, lam) / norm)        # [T, n]  1 - exp(.)
+      vty = evecs.T @ y                                       # [n, out]
+      if k_td is None:
+        mean = np.einsum('ji,ti,ik->tjk', evecs, one_minus, vty)
+      else:
+        ktd = _as_matrix(getattr(k_td, g), 'k_test_train')
+        inv = one_minus / np.abs(evals)[None, :]              # (1 - exp)/|lambda|
+        mean = np.einsum('lj,ji,ti,ik->tlk', ktd, evecs, inv, vty)
+      mean = mean.reshape(t_shape + mean.shape[1:])
+      if nngp_tt is None:
+        values.append(mean)
+        continue
+      nngp_dd = _as_matrix(k_dd.nngp, 'k_train_train')
+      if k_td is None:
+        if g == 'nngp':
+          cov = np.einsum('ji,ti,ki->tjk', evecs, lam[None, :] * decay ** 2, evecs)
+        else:
+          e = np.einsum('mi,ti,ki->tmk', evecs, decay, evecs)
+          cov = np.einsum('tmk,kl,tnl->tmn', e, nngp_dd, e)
+      else:
+        ktt = _as_matrix(nngp_tt, 'k_test_test')[None]
+        if g == 'nngp':
+          inv2 = -np.expm1(-2. * np.outer(ts, lam) / norm) / np.abs(evals)[None, :]
+          cov = ktt - np.einsum('mj,ji,ti,ki,lk->tml', ktd, evecs, inv2, evecs, ktd)
+        else:
+          nngp_td = _as_matrix(k_td.nngp, 'k_test_train')
+          term1 = np.einsum('mi,ti,ki,lk->tml', evecs, inv, evecs, ktd)          # [T, n_train, n_test]
+          term2 = np.einsum('mj,ji,ti,ki,lk->tml', ktd, evecs, inv, evecs, nngp_td)
+          term2 = term2 + np.swapaxes(term2, 1, 2)
+          cov = np.einsum('tji,jk,tkl->til', term1, nngp_dd, term1) - term2 + ktt
+      cov = cov.reshape(t_shape + cov.shape[1:])
+      values.append(Gaussian(mean, cov))
+    return _pack(get, names, values)
+
+  return predict_fn

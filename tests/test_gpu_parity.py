@@ -506,3 +506,31 @@ def test_packed_and_scalar_stage_kernels_agree(nt, tmp_path):
     outs[tag] = np.load(path)
   for key in ('a0', 'a1', 's0', 's1', 'b0', 'b1'):
     np.testing.assert_allclose(outs['packed'][key], outs['scalar'][key], rtol=3e-6, err_msg=key)
+
+
+def test_predict_on_gpu_grams(nt):
+  """`nt.predict.gradient_descent_mse_ensemble` on Gram matrices produced by the CUDA path (Myrtle-5, batched):
+  interpolation of the training targets, agreement of t = None with a direct solve on the oracle's float64
+  kernels, positive semi-definite posterior covariance."""
+  from oracle import ntk_oracle as O
+  spec = cases.myrtle(5, 'gap')
+  _, _, kernel_fn = cases.build(spec, nt.stax)
+  rng = np.random.default_rng(181)
+  x_train = rng.standard_normal((12, 32, 32, 3)).astype(np.float32)
+  x_test = rng.standard_normal((4, 32, 32, 3)).astype(np.float32)
+  y_train = rng.standard_normal((12, 10))
+  nt.config.update('enable_x64', True)
+  batched = nt.batch(kernel_fn, batch_size=4, device_count=0)
+  fn = nt.predict.gradient_descent_mse_ensemble(batched, x_train, y_train, diag_reg=1e-6)
+  out = fn(t=None, x_test=x_test, get=('nngp', 'ntk'), compute_cov=True)
+  k_dd = O.kernel_fn(spec, x_train, None, ('nngp', 'ntk'))
+  k_td = O.kernel_fn(spec, x_test, x_train, ('nngp', 'ntk'))
+  for i, g in enumerate(('nngp', 'ntk')):
+    A = k_dd[i] + 1e-6 * np.trace(k_dd[i]) / 12 * np.eye(12)
+    np.testing.assert_allclose(getattr(out, g).mean, k_td[i] @ np.linalg.solve(A, y_train), rtol=1e-6, atol=1e-9)
+    c = getattr(out, g).covariance
+    assert np.linalg.eigvalsh((c + c.T) / 2).min() > -1e-9
+  np.testing.assert_allclose(fn(t=None, x_test=x_train, get='ntk'), y_train, rtol=1e-3, atol=1e-4)
+  near = fn(t=1e10, x_test=x_test, get='ntk')
+  np.testing.assert_allclose(near, out.ntk.mean, rtol=1e-5, atol=1e-8)
+  nt.config.update('enable_x64', False)
