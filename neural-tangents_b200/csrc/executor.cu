@@ -669,6 +669,14 @@ int fcn_gram(ntk_context* ctx, Env& env, const FcnProg& fp, const T* x1, int n1,
   LAUNCH(env, k_rowdot<T>, grid_for((long long)n1 * 32), kThreads, 0, x1, x1, c1, (long long)n1, PairMap{1, 1}, C, inv_c);
   if (!symmetric)
     LAUNCH(env, k_rowdot<T>, grid_for((long long)n2 * 32), kThreads, 0, x2, x2, c2, (long long)n2, PairMap{1, 1}, C, inv_c);
+  // per-sample variance chains (value in front of every activation): [n_act][n]
+  int n_act = 0;
+  for (int o = 0; o < fp.n; ++o) n_act += fp.kind[o] != NTK_OP_DENSE;
+  T* qs1 = (T*)arena.alloc((size_t)std::max(1, n_act) * n1 * sizeof(T));
+  T* qs2 = symmetric ? qs1 : (T*)arena.alloc((size_t)std::max(1, n_act) * n2 * sizeof(T));
+  if (!qs1 || !qs2) return fail(NTK_ENOMEM, "workspace too small");
+  LAUNCH(env, k_fcn_qchain<T>, grid_for(n1), kThreads, 0, (const T*)c1, n1, fp, qs1);
+  if (!symmetric) LAUNCH(env, k_fcn_qchain<T>, grid_for(n2), kThreads, 0, (const T*)c2, n2, fp, qs2);
   // fp32: split x into TF32 hi / lo parts once, then the pipelined tcgen05 GEMM (gemm_kernels.cuh)
   static const bool no_tc = getenv("NTK_B200_NO_TC") != nullptr;
   static const bool no_pipe = getenv("NTK_B200_NO_GEMM_PIPE") != nullptr;
@@ -711,8 +719,9 @@ int fcn_gram(ntk_context* ctx, Env& env, const FcnProg& fp, const T* x1, int n1,
     }
     if (!pipe)
       NTK_TRY((fcn_input_gram<T>(false, env.stream, &env.launches, x1 + (size_t)r0 * C, a1, x2, n2, C, K0)));
-    LAUNCH(env, k_fcn_chain<T>, grid_for((long long)a1 * n2), kThreads, 0, (const T*)K0, (const T*)(c1 + r0),
-           (const T*)c2, a1, n2, fp, out_nngp + (size_t)r0 * ld, want_ntk ? out_ntk + (size_t)r0 * ld : (T*)nullptr, ld);
+    LAUNCH(env, k_fcn_chain<T>, grid_for((long long)a1 * n2), kThreads, 0, (const T*)K0, (const T*)(qs1 + r0),
+           (const T*)qs2, a1, n2, (long long)n1, (long long)n2, fp, out_nngp + (size_t)r0 * ld,
+           want_ntk ? out_ntk + (size_t)r0 * ld : (T*)nullptr, ld);
   }
   return NTK_OK;
 }

@@ -380,7 +380,7 @@ __global__ void k_dense(T* __restrict__ K, T* __restrict__ Tt, long long n, T w2
 // ---- fully-connected networks in one launch -------------------------------------------------
 // For [N, d] inputs every op after the input Gram is elementwise on the [n1, n2] matrix and on the two
 // per-sample variance vectors, so the whole Dense / ABRelu / Erf chain (BASELINE configs[0])
-// runs per entry in registers: K0[i,j], cov1[i], cov2[j] -> nngp[i,j], ntk[i,j].  The arithmetic is that of
+// runs per entry in registers: K0[i,j], q-chains of samples i and j -> nngp[i,j], ntk[i,j].  The arithmetic is that of
 // k_dense / k_act (same expressions, same order), so the result is bit-identical to the per-op path.
 constexpr int kMaxFcnOps = 48;
 struct FcnProg {
@@ -390,47 +390,73 @@ struct FcnProg {
   double f0[kMaxFcnOps], f1[kMaxFcnOps], f2[kMaxFcnOps];
 };
 
+// Per-sample variance chain: q evolves on its own (Dense: w2 q + b2; activation: the closed form on (q, q, q)),
+// and its value IN FRONT of every activation is what the cross entries need.  qs: [n_act][n].
 template <typename T>
-__global__ void k_fcn_chain(const T* __restrict__ K0, const T* __restrict__ c1, const T* __restrict__ c2,
-                            int t1, int t2, const FcnProg prog, T* __restrict__ nngp, T* __restrict__ ntk,
-                            long long ld) {
+__global__ void k_fcn_qchain(const T* __restrict__ c, int n, const FcnProg prog, T* __restrict__ qs) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    T q = c[i];
+    int act = 0;
+    for (int o = 0; o < prog.n; ++o) {
+      if (prog.kind[o] == NTK_OP_DENSE) {
+        const T w2 = (T)prog.f0[o], b2 = (T)(prog.has_bias[o] ? prog.f1[o] : 0.0);
+        q = fma_t(w2, q, b2);
+      } else if (prog.kind[o] == NTK_OP_ABRELU) {
+        qs[(long long)act++ * n + i] = q;
+        const T a = (T)prog.f0[o], b = (T)prog.f1[o];
+        const T coef_s = (a - b) * (a - b) / ((T)2 * Consts<T>::pi());
+        const T half_ab = (a * a + b * b) / (T)2;
+        T d, dot;
+        abrelu_point<T>(q, q * q, coef_s, half_ab, d, dot);
+        q = d;
+      } else {
+        qs[(long long)act++ * n + i] = q;
+        const T a = (T)prog.f0[o], b = (T)prog.f1[o];
+        const T bb = b * b, aa = a * a, cc = (T)(prog.f2[o] * prog.f2[o]);
+        T d, dot;
+        erf_point<T>(q * bb, ((T)1 + (T)2 * bb * q) * ((T)1 + (T)2 * bb * q), d, dot);
+        q = fma_t(aa, d, cc);
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void k_fcn_chain(const T* __restrict__ K0, const T* __restrict__ qs1, const T* __restrict__ qs2,
+                            int t1, int t2, long long n1_all, long long n2_all, const FcnProg prog,
+                            T* __restrict__ nngp, T* __restrict__ ntk, long long ld) {
   const long long P = (long long)t1 * t2;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < P;
        idx += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(idx / t2), j = (int)(idx % t2);
-    T k = K0[idx], q1 = c1[i], q2 = c2[j], t = (T)0;
+    T k = K0[idx], t = (T)0;
     bool t_zero = true;
+    int act = 0;
     for (int o = 0; o < prog.n; ++o) {
       if (prog.kind[o] == NTK_OP_DENSE) {  // linear.py:899-926
         const T w2 = (T)prog.f0[o], b2 = (T)(prog.has_bias[o] ? prog.f1[o] : 0.0);
         k = fma_t(w2, k, b2);
         t = t_zero ? k : fma_t(w2, t, k);
         t_zero = false;
-        q1 = fma_t(w2, q1, b2);
-        q2 = fma_t(w2, q2, b2);
-      } else if (prog.kind[o] == NTK_OP_ABRELU) {  // elementwise.py:444-455
-        const T a = (T)prog.f0[o], b = (T)prog.f1[o];
-        const T coef_s = (a - b) * (a - b) / ((T)2 * Consts<T>::pi());
-        const T half_ab = (a * a + b * b) / (T)2;
-        T ko, dot, d1, d2;
-        abrelu_point<T>(k, q1 * q2, coef_s, half_ab, ko, dot);
-        k = ko;
-        t *= dot;
-        abrelu_point<T>(q1, q1 * q1, coef_s, half_ab, d1, dot);
-        abrelu_point<T>(q2, q2 * q2, coef_s, half_ab, d2, dot);
-        q1 = d1;
-        q2 = d2;
-      } else {  // Erf: elementwise.py:84-93 + kernel.py:426-439
-        const T a = (T)prog.f0[o], b = (T)prog.f1[o];
-        const T bb = b * b, aa = a * a, cc = (T)(prog.f2[o] * prog.f2[o]);
-        T ko, dot, d1, d2;
-        erf_point<T>(k * bb, ((T)1 + (T)2 * bb * q1) * ((T)1 + (T)2 * bb * q2), ko, dot);
-        k = fma_t(aa, ko, cc);
-        t = aa * (bb * t * dot);
-        erf_point<T>(q1 * bb, ((T)1 + (T)2 * bb * q1) * ((T)1 + (T)2 * bb * q1), d1, dot);
-        erf_point<T>(q2 * bb, ((T)1 + (T)2 * bb * q2) * ((T)1 + (T)2 * bb * q2), d2, dot);
-        q1 = fma_t(aa, d1, cc);
-        q2 = fma_t(aa, d2, cc);
+      } else {
+        const T q1 = qs1[act * n1_all + i], q2 = qs2[act * n2_all + j];
+        ++act;
+        if (prog.kind[o] == NTK_OP_ABRELU) {  // elementwise.py:444-455
+          const T a = (T)prog.f0[o], b = (T)prog.f1[o];
+          const T coef_s = (a - b) * (a - b) / ((T)2 * Consts<T>::pi());
+          const T half_ab = (a * a + b * b) / (T)2;
+          T ko, dot;
+          abrelu_point<T>(k, q1 * q2, coef_s, half_ab, ko, dot);
+          k = ko;
+          t *= dot;
+        } else {  // Erf: elementwise.py:84-93 + kernel.py:426-439
+          const T a = (T)prog.f0[o], b = (T)prog.f1[o];
+          const T bb = b * b, aa = a * a, cc = (T)(prog.f2[o] * prog.f2[o]);
+          T ko, dot;
+          erf_point<T>(k * bb, ((T)1 + (T)2 * bb * q1) * ((T)1 + (T)2 * bb * q2), ko, dot);
+          k = fma_t(aa, ko, cc);
+          t = aa * (bb * t * dot);
+        }
       }
     }
     nngp[(long long)i * ld + j] = k;

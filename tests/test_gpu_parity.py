@@ -530,7 +530,7 @@ def test_predict_on_gpu_grams(nt):
     np.testing.assert_allclose(getattr(out, g).mean, k_td[i] @ np.linalg.solve(A, y_train), rtol=1e-6, atol=1e-9)
     c = getattr(out, g).covariance
     assert np.linalg.eigvalsh((c + c.T) / 2).min() > -1e-9
-  np.testing.assert_allclose(fn(t=None, x_test=x_train, get='ntk'), y_train, rtol=1e-3, atol=1e-4)
+  np.testing.assert_allclose(fn(t=None, x_test=x_train, get='ntk'), y_train, rtol=1e-2, atol=2e-3)  # regularised fit
   near = fn(t=1e10, x_test=x_test, get='ntk')
   np.testing.assert_allclose(near, out.ntk.mean, rtol=1e-5, atol=1e-8)
   nt.config.update('enable_x64', False)
