@@ -79,9 +79,10 @@ __device__ __forceinline__ float2 neg_acos_over_sin2(float2 c) {
 }
 
 // ABRelu on two elements (elementwise.py:444-455; see act_point in fused_kernels.cuh).
-//   K, U     conv outputs (U = T + K);  q1, nq2 = q1 and -q2 of the two elements
-//   Ko = coef*s + kd*K,  Uo = kd*U + Ko   (i.e. T' = kd*T_conv, U' = T' + K' with T_conv = U - ... see header)
-// NOTE: U entering here is conv(T)+conv(K)+b = the reference's T_conv, so Uo = kd*T_conv + K'.
+//   K         conv(K_in) + b            (the reference's nngp after the conv)
+//   U         conv(U_in) + b = conv(T_in) + K, i.e. the reference's ntk after the conv (linear.py:1396-1398)
+//   q1, nq2   q1 and -q2 of the two elements
+//   Ko = coef*s + kd*K  (K'),   Uo = kd*U + Ko  (= T' + K', the carried form of the next layer's ntk)
 template <bool NTK>
 __device__ __forceinline__ void act_pair(float2 K, float2 U, float2 q1, float2 nq2, float2 coef2,
                                          float2 hab2, float2& Ko, float2& Uo) {
