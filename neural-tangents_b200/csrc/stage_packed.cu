@@ -49,7 +49,9 @@ int launch_p_epi(cudaStream_t stream, int64_t* launches, int epi, const StageArg
     case EPI_POOL:
       // Variants A/B-timed on B200 for the dominant kernel (L = 3, FROM_X, POOL, ntk; 9216 pairs):
       //   LAG 1, 2 CTAs/SM, paired q2 (default) 37.87 ms | LAG 2: 37.73 | 3 CTAs/SM + planar q2: 37.29
-      //   LAG 2 + 3 CTAs (spills): 39.42 | planar q2 at 2 CTAs: 38.05.  All within 2 %: the kernel is bound
+      //   LAG 2 + 3 CTAs (spills): 39.42 | planar q2 at 2 CTAs: 38.05 | pooled gather consumed one step later (its
+      //   LDS latency hidden, +18 registers): 0.5 % slower | K and U box-filter instructions interleaved to share
+      //   masks through the reuse cache: ptxas sets no .reuse, 0.9 % slower.  All within 2 %: the kernel is bound
       //   by register-file read bandwidth (profiles/microbench/rf_bandwidth.cu), not latency or occupancy.
       if (L == 3 && IN == IN_FROM_X && NTK && variant() == 2)
         return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false, 1, 3, false>(stream, launches, a);
