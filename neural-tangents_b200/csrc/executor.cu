@@ -980,6 +980,7 @@ int ntk_context_create(int32_t device, size_t workspace_bytes, ntk_context_t** o
   NTK_TRY((fused_configure_device<float, true>()));
   NTK_TRY((fused_configure_device<double, true>()));
   NTK_TRY(stage_packed_configure());
+  NTK_TRY(stage_packed_erf_configure());
   *out = c.release();
   return NTK_OK;
 }

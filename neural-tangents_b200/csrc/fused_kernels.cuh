@@ -1059,16 +1059,21 @@ int launch_stage_L(cudaStream_t stream, int64_t* launches, int L, int epi, const
 int launch_stage_packed(cudaStream_t stream, int64_t* launches, int S, int L, int from_x, int epi, bool ntk,
                         const StageArgs<float>& a);
 int stage_packed_configure();
+// the same kernels with the Erf closed form compiled in (stage_packed_erf.cu)
+int launch_stage_packed_erf(cudaStream_t stream, int64_t* launches, int S, int L, int from_x, int epi, bool ntk,
+                            const StageArgs<float>& a);
+int stage_packed_erf_configure();
 
 inline bool packed_enabled() {
   static const bool on = getenv("NTK_B200_NO_PACKED") == nullptr;
   return on;
 }
-inline int launch_stage_packed_any(cudaStream_t, int64_t*, int, int, int, int, bool, const StageArgs<double>&) {
+inline int launch_stage_packed_any(cudaStream_t, int64_t*, int, int, int, int, bool, bool, const StageArgs<double>&) {
   return fail(NTK_EINVAL, "packed stage kernel is fp32 only");
 }
 inline int launch_stage_packed_any(cudaStream_t stream, int64_t* launches, int S, int L, int from_x, int epi,
-                                   bool ntk, const StageArgs<float>& a) {
+                                   bool ntk, bool erf, const StageArgs<float>& a) {
+  if (erf) return launch_stage_packed_erf(stream, launches, S, L, from_x, epi, ntk, a);
   return launch_stage_packed(stream, launches, S, L, from_x, epi, ntk, a);
 }
 
@@ -1088,14 +1093,23 @@ int launch_stage_k(cudaStream_t stream, int64_t* launches, int S, int L, int fro
   return launch_stage_L<T, 8, IN_LOAD, NTK, 1, ERF>(stream, launches, L, epi, a);
 }
 
+// Which stages run on the packed kernels: fp32 at 32x32 / 16x16 whose activations are all ABRelu or all Erf.
+// (A stage that mixes them stays on the scalar kernel, whose Erf arithmetic is the one k_qmaps uses for the
+// diagonal: an ABRelu layer behind an Erf layer needs that bit-exact agreement on duplicate pairs.)
+template <typename T>
+bool stage_is_packed(int S, int C, int n_erf, int L) {
+  return sizeof(T) == 4 && (S == 32 || S == 16) && C == 3 && packed_enabled() && (n_erf == 0 || n_erf == L);
+}
+
 template <typename T, bool NTK>
 int launch_stage(cudaStream_t stream, int64_t* launches, int S, int L, int from_x, int C, int epi,
                  const StageArgs<T>& a) {
-  bool any_erf = false;
-  for (int l = 0; l < L; ++l) any_erf = any_erf || a.lp[l].kind == ACT_ERF;
+  int n_erf = 0;
+  for (int l = 0; l < L; ++l) n_erf += a.lp[l].kind == ACT_ERF;
+  const bool any_erf = n_erf > 0;
+  if (stage_is_packed<T>(S, from_x ? C : 3, n_erf, L))
+    return launch_stage_packed_any(stream, launches, S, L, from_x, epi, NTK, any_erf, a);
   if (any_erf) return launch_stage_k<T, NTK, true>(stream, launches, S, L, from_x, C, epi, a);
-  if (sizeof(T) == 4 && (S == 32 || S == 16) && (!from_x || C == 3) && packed_enabled())
-    return launch_stage_packed_any(stream, launches, S, L, from_x, epi, NTK, a);
   return launch_stage_k<T, NTK, false>(stream, launches, S, L, from_x, C, epi, a);
 }
 
@@ -1355,9 +1369,9 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
           if (epi == EPI_POOL) {
             // the packed kernels zero their own (pre-accumulation) output while other CTAs compute
             // -- DRAM is idle in this kernel -- instead of a 4.8 GB memset in front of every launch
-            bool erf_stage = false;
-            for (int l = 0; l < plan.stages[s].L; ++l) erf_stage = erf_stage || plan.stages[s].kind[l] == ACT_ERF;
-            a.zero_out = (sizeof(T) == 4 && (S == 32 || S == 16) && C == 3 && packed_enabled() && !erf_stage) ? 1 : 0;
+            int n_erf = 0;
+            for (int l = 0; l < plan.stages[s].L; ++l) n_erf += plan.stages[s].kind[l] == ACT_ERF;
+            a.zero_out = stage_is_packed<T>(S, s == 0 ? C : 3, n_erf, plan.stages[s].L) ? 1 : 0;
             if (!a.zero_out)
               NTK_CUDA(cudaMemsetAsync(nxt, 0, (size_t)P * out_per * sizeof(T) * (want_ntk ? 2 : 1), stream));
           }

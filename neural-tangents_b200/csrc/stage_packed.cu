@@ -1,5 +1,18 @@
 // Instantiations + launcher of the packed-FP32 stage kernel (stage_packed.cuh): fp32, 32x32 and 16x16.
+// Compiled twice: as is (pure-ABRelu stages) and from stage_packed_erf.cu with NTK_PACKED_ERF = 1 (Erf-capable
+// instantiations, their own copy of the constant tables).
 #include "stage_packed.cuh"
+
+#ifndef NTK_PACKED_ERF
+#define NTK_PACKED_ERF 0
+#endif
+#if NTK_PACKED_ERF
+#define NTK_PACKED_LAUNCH launch_stage_packed_erf
+#define NTK_PACKED_CONFIGURE stage_packed_erf_configure
+#else
+#define NTK_PACKED_LAUNCH launch_stage_packed
+#define NTK_PACKED_CONFIGURE stage_packed_configure
+#endif
 
 namespace ntk {
 
@@ -17,7 +30,7 @@ inline int variant() {
 template <int S, int L, int IN, int EPI, bool NTK, int CIN, bool RC, int LAG = 1, int MINB = 2, bool Q2P = true>
 int launch_p_impl(cudaStream_t stream, int64_t* launches, const StageArgs<float>& a) {
   using G = PGeom<S>;
-  auto kern = k_stage_p<S, L, IN, EPI, NTK, CIN, RC, LAG, MINB, Q2P>;
+  auto kern = k_stage_p<S, L, IN, EPI, NTK, CIN, RC, LAG, MINB, Q2P, NTK_PACKED_ERF != 0>;
   const size_t smem = stage_p_smem_bytes<S, L, IN, EPI, NTK, CIN, Q2P>();
   static thread_local bool configured = false;
   if (!configured) {
@@ -53,7 +66,7 @@ int launch_p_epi(cudaStream_t stream, int64_t* launches, int epi, const StageArg
       //   LDS latency hidden, +18 registers): 0.5 % slower | K and U box-filter instructions interleaved to share
       //   masks through the reuse cache: ptxas sets no .reuse, 0.9 % slower.  All within 2 %: the kernel is bound
       //   by register-file read bandwidth (profiles/microbench/rf_bandwidth.cu), not latency or occupancy.
-      if (L == 3 && IN == IN_FROM_X && NTK && variant() == 2)
+      if (!NTK_PACKED_ERF && L == 3 && IN == IN_FROM_X && NTK && variant() == 2)
         return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false, 1, 3, false>(stream, launches, a);
       return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false>(stream, launches, a);
     default:
@@ -75,8 +88,8 @@ int launch_p_L(cudaStream_t stream, int64_t* launches, int L, int epi, const Sta
 
 }  // namespace
 
-int launch_stage_packed(cudaStream_t stream, int64_t* launches, int S, int L, int from_x, int epi, bool ntk,
-                        const StageArgs<float>& a) {
+int NTK_PACKED_LAUNCH(cudaStream_t stream, int64_t* launches, int S, int L, int from_x, int epi, bool ntk,
+                      const StageArgs<float>& a) {
   if (S == 32) {
     if (from_x)
       return ntk ? launch_p_L<32, IN_FROM_X, true, 3>(stream, launches, L, epi, a)
@@ -94,7 +107,7 @@ int launch_stage_packed(cudaStream_t stream, int64_t* launches, int S, int L, in
   return fail(NTK_EINVAL, "packed stage kernel is instantiated for S == 32 and 16");
 }
 
-int stage_packed_configure() {
+int NTK_PACKED_CONFIGURE() {
   for (int S : {32, 16}) {
     std::vector<float4> m((size_t)S * S);
     for (int ch = 0; ch < S; ++ch)

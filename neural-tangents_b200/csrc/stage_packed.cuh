@@ -112,6 +112,37 @@ __device__ __forceinline__ void act_pair(float2 K, float2 U, float2 q1, float2 n
   if (NTK) Uo = __ffma2_rn(kd, U, Ko);
 }
 
+// Erf on two elements (elementwise.py:67-112; erf_act_point in fused_kernels.cuh).  The q-map of an Erf layer
+// holds D = 1 + 2 b^2 q, so q1 = D1 and nq2 = -D2 here; with Kh = 2 b^2 K:
+//   s = sqrt(D1 D2 - Kh^2) (>= 1),  c = Kh / sqrt(D1 D2),  K' = eA asin(c) + eC,  T' = eT T_conv / s,
+// asin(c) = copysign(pi/2 - sqrt(1-c^2) G(|c|), c) with the same fit as the ABRelu path; U' = T' + K'.
+template <bool NTK>
+__device__ __forceinline__ void act_pair_erf(float2 K, float2 U, float2 q1, float2 nq2, float e_in, float eA,
+                                             float eT, float eC, float2& Ko, float2& Uo) {
+  const float2 Kh = __fmul2_rn(f2s(e_in), K);
+  const float2 np = __fmul2_rn(q1, nq2);               // -(D1 D2)
+  const float2 d = __ffma2_rn(Kh, Kh, np);             // Kh^2 - D1 D2 <= -1: no cancellation to protect
+  float2 rb, rs;
+  rb.x = rsq_fast(fabsf(np.x));
+  rb.y = rsq_fast(fabsf(np.y));
+  rs.x = rsq_fast(fabsf(d.x));
+  rs.y = rsq_fast(fabsf(d.y));
+  float2 ad;
+  ad.x = fabsf(d.x);
+  ad.y = fabsf(d.y);
+  const float2 s = __fmul2_rn(ad, rs);
+  const float2 sn = __fmul2_rn(s, rb);
+  float2 ac;
+  ac.x = fminf(__fmul_rn(fabsf(Kh.x), rb.x), 1.f);
+  ac.y = fminf(__fmul_rn(fabsf(Kh.y), rb.y), 1.f);
+  const float2 u = __ffma2_rn(sn, neg_acos_over_sin2(ac), f2s(kHalfPiF));
+  float2 us;
+  us.x = copysign_bits(u.x, Kh.x);
+  us.y = copysign_bits(u.y, Kh.y);
+  Ko = __ffma2_rn(f2s(eA), us, f2s(eC));
+  if (NTK) Uo = __ffma2_rn(__fmul2_rn(f2s(eT), rs), U, Ko);
+}
+
 template <int S>
 struct PGeom {
   static constexpr int WPT = 8;
@@ -147,7 +178,9 @@ size_t stage_p_smem_bytes() {
 //   MINB  __launch_bounds__ min CTAs per SM (2 or 3)
 //   Q2P   q2 rows hold explicit (e, e+4) pairs (one LDS.64 per pair, 2x shared memory) or are planar
 //         (two LDS.32 per pair)
-template <int S, int L, int IN, int EPI, bool NTK, int CIN, bool RC, int LAG = 1, int MINB = 2, bool Q2P = true>
+//   ERF   the stage may contain Erf layers (runtime branch per layer); ERF = false carries no Erf code
+template <int S, int L, int IN, int EPI, bool NTK, int CIN, bool RC, int LAG = 1, int MINB = 2, bool Q2P = true,
+          bool ERF = false>
 __global__ void __launch_bounds__(PGeom<S>::NT, MINB)
 k_stage_p(const StageArgs<float> a) {
   using G = PGeom<S>;
@@ -407,7 +440,10 @@ k_stage_p(const StageArgs<float> a) {
             nq2.x = lds_f1(q2row + (unsigned)off2[j] * 4u);
             nq2.y = lds_f1(q2row + (unsigned)off2[j + 4] * 4u);
           }
-          act_pair<NTK>(ck, cu, q1p[j], nq2, coef2, hab2, BK[l][j], BU[l][j]);
+          if (ERF && a.lp[l].kind == ACT_ERF)
+            act_pair_erf<NTK>(ck, cu, q1p[j], nq2, a.lp[l].e_in, a.lp[l].eA, a.lp[l].eT, a.lp[l].eC, BK[l][j], BU[l][j]);
+          else
+            act_pair<NTK>(ck, cu, q1p[j], nq2, coef2, hab2, BK[l][j], BU[l][j]);
         }
       }
 #undef INK
