@@ -496,7 +496,10 @@ def test_packed_and_scalar_stage_kernels_agree(nt, tmp_path):
       "a = k(x1, x2, ('nngp', 'ntk')); s = k(x1, None, ('nngp', 'ntk'))\n"
       "_, _, k16 = cases.build(cases.CASES['myrtle10_16px'][0], nt.stax)\n"
       "b = k16(x1[:, ::2, ::2], x2[:, ::2, ::2], ('nngp', 'ntk'))\n"
-      "np.savez(sys.argv[1], a0=a.nngp, a1=a.ntk, s0=s.nngp, s1=s.ntk, b0=b.nngp, b1=b.ntk)\n")
+      "erf = ('serial', [('erf', 1., 1., 0.) if l == cases.RELU else l for l in cases.myrtle(10)[1]])\n"
+      "_, _, ke = cases.build(erf, nt.stax)\n"
+      "e = ke(x1, x2, ('nngp', 'ntk'))\n"
+      "np.savez(sys.argv[1], a0=a.nngp, a1=a.ntk, s0=s.nngp, s1=s.ntk, b0=b.nngp, b1=b.ntk, e0=e.nngp, e1=e.ntk)\n")
   outs = {}
   for tag, env_extra in (('packed', {}), ('scalar', {'NTK_B200_NO_PACKED': '1'})):
     path = str(tmp_path / f'{tag}.npz')
@@ -504,8 +507,12 @@ def test_packed_and_scalar_stage_kernels_agree(nt, tmp_path):
     env.pop('NTK_B200_NO_PACKED', None) if tag == 'packed' else None
     subprocess.run([sys.executable, '-c', code, path], check=True, env=env, timeout=600)
     outs[tag] = np.load(path)
-  for key in ('a0', 'a1', 's0', 's1', 'b0', 'b1'):
-    np.testing.assert_allclose(outs['packed'][key], outs['scalar'][key], rtol=3e-6, err_msg=key)
+  for key in ('a0', 'a1', 's0', 's1', 'b0', 'b1', 'e0', 'e1'):
+    # the cross entries of the bias-free Erf net are ~1e-5 of its diagonal scale (odd activation): compare
+    # them on the scale of the kernel (entries of K(x, x) are O(0.1)), not entry by entry
+    atol = 0. if key[0] != 'e' else 1e-7
+    np.testing.assert_allclose(outs['packed'][key], outs['scalar'][key], rtol=3e-6 if key[0] != 'e' else 1e-5,
+                               atol=atol, err_msg=key)
 
 
 def test_predict_on_gpu_grams(nt):
