@@ -238,7 +238,7 @@ def run_reference(args):
                        'sample': sample},
       'e2e': {'value': value, 'unit': 'entries/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
   }
-  print(json.dumps(line))
+  emit(line)
 
 
 # ---------------------------------------------------------------------------------------
@@ -440,9 +440,28 @@ def run_ours(args):
     line['cpu_baseline'] = {
         'value': n / dt, 'unit': 'entries/s', 'cores': cores, 'kind': 'port',
         'sample': f'{cores} worker processes x (1 x {args.ref_cols}) pairs, NumPy float64 oracle, {dt:.1f} s'}
-  print(json.dumps(line))
+  emit(line)
   if world > 1:
     dist.destroy_process_group()
+
+
+_JSON_OUT = None
+
+
+def claim_stdout():
+  """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner
+  to fd 1 when NCCL_DEBUG is set in the environment), so fd 1 is pointed at stderr for the rest of the
+  process and the JSON line goes to the saved descriptor."""
+  global _JSON_OUT
+  sys.stdout.flush()
+  _JSON_OUT = os.fdopen(os.dup(1), 'w')
+  os.dup2(2, 1)
+
+
+def emit(line):
+  out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+  out.write(json.dumps(line) + '\n')
+  out.flush()
 
 
 def main():
@@ -463,6 +482,7 @@ def main():
   ap.add_argument('--per-layer', action='store_true',
                   help='one Conv+Relu layer per kernel launch (one HBM round trip per layer)')
   args = ap.parse_args()
+  claim_stdout()
   if args.impl == 'reference':
     run_reference(args)
   else:
