@@ -116,3 +116,23 @@ def test_batch_stitching_with_foreign_kernel_fn():
   b = batching.batch(kernel_fn, batch_size=4, device_count=0)
   np.testing.assert_allclose(b(x1, x2), kernel_fn(x1, x2), rtol=1e-13, atol=1e-14)
   np.testing.assert_allclose(b(x1), kernel_fn(x1), rtol=1e-13, atol=1e-14)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+  """`bench.py --impl reference` (the CPU arm of the driver contract) prints exactly one JSON line on stdout with
+  the contract's keys; everything else (including library banners) goes to stderr."""
+  import json
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--workload', 'fcn',
+                        '--steps', '1', '--warmup', '0', '--ref-cols', '1'], capture_output=True, text=True,
+                       timeout=300, check=True).stdout
+  lines = [l for l in out.splitlines() if l.strip()]
+  assert len(lines) == 1
+  d = json.loads(lines[0])
+  for key in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better',
+              'scaling', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+    assert key in d, key
+  assert d['impl'] == 'reference' and d['cpu_baseline']['kind'] == 'port' and d['value'] > 0
+  assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
