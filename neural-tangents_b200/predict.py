@@ -1,6 +1,7 @@
 """Closed-form inference with the NNGP / NTK Gram matrices: the immediate caller of the hot path
-(SURVEY §8f row 1).  Mirrors `neural_tangents.predict.gp_inference` (`_src/predict.py:566-750`) and
-`gradient_descent_mse_ensemble` (`_src/predict.py:753-1100`) for the case the B200 path produces:
+(SURVEY §8f row 1).  Mirrors `neural_tangents.predict.gp_inference` (`_src/predict.py:566-750`),
+`gradient_descent_mse_ensemble` (`:753-1100`), `gradient_descent_mse` (`:71-279`) and `max_learning_rate`
+(`:1103-1150`) for the case the B200 path produces:
 `[n1, n2]` kernel matrices (outputs block-diagonal along the logit axis, `trace_axes=(-1,)`).
 
 The Gram matrices come from `kernel_fn` (libntk_b200.so on the GPU); the n x n factorisations
@@ -256,3 +257,74 @@ def gradient_descent_mse_ensemble(kernel_fn, x_train, y_train, learning_rate: fl
     return _pack(get, names, values)
 
   return predict_fn
+
+
+def gradient_descent_mse(k_train_train, y_train, learning_rate: float = 1., diag_reg: float = 0.,
+                         diag_reg_absolute_scale: bool = False, trace_axes=(-1,)) -> Callable:
+  """Function-space gradient descent on MSE for ONE network with kernel `k_train_train`
+  (`_src/predict.py:71-279`).
+
+  Returns `predict_fn(t=None, fx_train_0=0., fx_test_0=None, k_test_train=None)` giving the network outputs on
+  the train [and test] set at time[s] `t` from their values at t = 0:
+    f_train(t) = y + exp(-K t')(f_train(0) - y),   f_test(t) = f_test(0) + K_td K^-1 (I - exp(-K t'))(y - f_train(0)),
+  with t' = t * learning_rate / y_train.size and K the regularised train-train matrix.
+  """
+  y = _check_targets(y_train, trace_axes)
+  k_dd = _as_matrix(k_train_train, 'k_train_train')
+  norm = float(y.size)
+  state = {}
+
+  def solver():
+    if 'chol' not in state:
+      state['chol'] = _CholSolver(k_dd, diag_reg, diag_reg_absolute_scale)
+    return state['chol']
+
+  def eigenspace():
+    if 'eig' not in state:
+      state['eig'] = np.linalg.eigh(_regularize(k_dd, diag_reg, diag_reg_absolute_scale))
+    return state['eig']
+
+  def predict_fn(t=None, fx_train_0=0., fx_test_0=None, k_test_train=None):
+    if fx_train_0 is None and fx_test_0 is None:
+      raise ValueError('Both `fx_train_0` and `fx_test_0` are `None`, i.e. no predictions will be computed.')
+    if fx_test_0 is not None and k_test_train is None:
+      raise ValueError('To get predictions on the test set, please provide `k_test_train`.')
+    f0 = None if fx_train_0 is None else np.broadcast_to(np.asarray(fx_train_0, dtype=np.float64), y.shape)
+    ft0 = None if fx_test_0 is None else np.asarray(fx_test_0, dtype=np.float64)
+    k_td = None if k_test_train is None else _as_matrix(k_test_train, 'k_test_train')
+    resid = y if f0 is None else y - f0                      # y - f_train(0)
+
+    if t is None:                                             # infinite time
+      if ft0 is None:
+        return y.copy()
+      test = ft0 + k_td @ solver()(resid)
+      return test if f0 is None else (y.copy(), test)
+
+    t_arr = np.asarray(t, dtype=np.float64) * learning_rate
+    t_shape, ts = t_arr.shape, t_arr.reshape(-1)
+    evals, evecs = eigenspace()
+    lam = np.maximum(evals, 0.)
+    one_minus = -np.expm1(-np.outer(ts, lam) / norm)          # [T, n]
+    vtr = evecs.T @ resid                                     # [n, out]
+    out = []
+    if f0 is not None:
+      d_train = np.einsum('ji,ti,ik->tjk', evecs, one_minus, vtr)
+      out.append((f0[None] + d_train).reshape(t_shape + y.shape))
+    if ft0 is not None:
+      d_test = np.einsum('lj,ji,ti,ik->tlk', k_td, evecs, one_minus / np.abs(evals)[None, :], vtr)
+      out.append((ft0[None] + d_test).reshape(t_shape + d_test.shape[1:]))
+    return out[0] if len(out) == 1 else tuple(out)
+
+  return predict_fn
+
+
+def max_learning_rate(ntk_train_train, y_train_size: Optional[int] = None, momentum: float = 0.,
+                      eps: float = 1e-12) -> float:
+  """Largest stable learning rate of (momentum) gradient descent on MSE for an infinitely wide network
+  (`_src/predict.py:1103-1150`): 2 (1 + momentum) |y| / (lambda_max(NTK) + eps)."""
+  import scipy.linalg
+  k = _as_matrix(ntk_train_train, 'ntk_train_train')
+  n = k.shape[0]
+  factor = n if y_train_size is None else y_train_size
+  lam_max = scipy.linalg.eigvalsh(k, subset_by_index=(n - 1, n - 1))[-1]
+  return float(2. * (1. + momentum) * factor / (lam_max + eps))

@@ -135,3 +135,33 @@ def test_ensemble_train_set_and_get_conventions(data):
     fn(x_test=xt, get='ntkgp')
   with pytest.raises(ValueError):
     fn(x_test=xt, get=('ntk', 'ntk'))
+
+
+def test_gradient_descent_mse_and_max_learning_rate(data):
+  x, y, xt = data
+  rng = np.random.default_rng(3)
+  k_dd, k_td = kernel_fn(x, None, 'ntk'), kernel_fn(xt, x, 'ntk')
+  f0, ft0 = 0.1 * rng.standard_normal(y.shape), 0.1 * rng.standard_normal((len(xt), y.shape[1]))
+  fn = predict.gradient_descent_mse(k_dd, y, learning_rate=0.5, diag_reg=1e-5)
+  n = len(x)
+  A = k_dd + 1e-5 * np.trace(k_dd) / n * np.eye(n)
+  ts = np.array([0., 2., 300.])
+  tr, te = fn(ts, f0, ft0, k_td)
+  assert tr.shape == (3,) + y.shape and te.shape == (3,) + ft0.shape
+  for i, t in enumerate(ts):
+    E = scipy.linalg.expm(-A * t * 0.5 / y.size)
+    np.testing.assert_allclose(tr[i], y + E @ (f0 - y), rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(te[i], ft0 + k_td @ np.linalg.solve(A, (np.eye(n) - E) @ (y - f0)), rtol=1e-7, atol=1e-10)
+  np.testing.assert_allclose(tr[0], f0, atol=1e-12)                        # t = 0: nothing has moved
+  tr_inf, te_inf = fn(None, f0, ft0, k_td)
+  np.testing.assert_array_equal(tr_inf, y)
+  np.testing.assert_allclose(fn(1e13, f0, ft0, k_td)[1], te_inf, rtol=1e-6, atol=1e-9)
+  assert fn(5., None, ft0, k_td).shape == ft0.shape                        # test only, default f_train(0) = 0 path
+  assert fn(5.).shape == y.shape
+  with pytest.raises(ValueError):
+    fn(1., 0., ft0, None)
+  with pytest.raises(ValueError):
+    fn(1., None, None)
+  lam = np.linalg.eigvalsh(k_dd)[-1]
+  assert predict.max_learning_rate(k_dd, y.size, momentum=0.9) == pytest.approx(2 * 1.9 * y.size / (lam + 1e-12))
+  assert predict.max_learning_rate(k_dd) == pytest.approx(2 * n / (lam + 1e-12))
