@@ -265,3 +265,69 @@ def batch(kernel_fn: Callable, batch_size: int = 0, device_count: int = -1,
     batched_kernel_fn._spec = kernel_fn._spec
   batched_kernel_fn.device_count = device_count_eff
   return batched_kernel_fn
+
+
+# ---- restartable on-disk Gram ---------------------------------------------------
+def gram_to_disk(kernel_fn: Callable, x1: np.ndarray, x2, get, out_dir: str, block_rows: int = 512):
+  """Computes `kernel_fn(x1, x2, get)` slab by slab ([block_rows, n2] row slabs) into `out_dir` and can be
+  restarted: a slab whose file already exists is not recomputed.  Returns read-only `np.memmap`s of the
+  assembled `[n1, n2]` matrices (a single one for a `str` `get`, else a namedtuple over `get`).
+
+  The reference keeps every block in host memory until the final `jnp.stack` (`_src/batching.py:353-357,
+  370` -- twice the peak memory and nothing survives an interruption); for Grams that outgrow the host
+  (N >= 1e5) the slabs go to disk instead.  Files: `<name>.slab<row0>.npy` per finished slab (written
+  atomically), `<name>.npy` for the assembled matrix, `manifest.json` with the shapes.
+  """
+  import collections
+  import json
+  import os
+  names = (get,) if isinstance(get, str) else tuple(get)
+  if not names or not all(isinstance(n, str) for n in names):
+    raise ValueError('`get` must name the matrices to compute, e.g. ("nngp", "ntk").')
+  if block_rows <= 0:
+    raise ValueError('block_rows must be positive.')
+  os.makedirs(out_dir, exist_ok=True)
+  n1 = x1.shape[0]
+  n2 = n1 if x2 is None else x2.shape[0]
+  manifest = {'n1': int(n1), 'n2': int(n2), 'get': list(names), 'block_rows': int(block_rows)}
+  mpath = os.path.join(out_dir, 'manifest.json')
+  if os.path.exists(mpath):
+    old = json.load(open(mpath))
+    if any(old.get(k) != manifest[k] for k in ('n1', 'n2', 'get', 'block_rows')):
+      raise ValueError(f'{out_dir} holds a different computation ({old}); refusing to mix slabs.')
+  else:
+    with open(mpath, 'w') as f:
+      json.dump(manifest, f)
+  x2e = x1 if x2 is None else x2
+
+  def slab_path(name, r0):
+    return os.path.join(out_dir, f'{name}.slab{r0:09d}.npy')
+
+  for r0 in range(0, n1, block_rows):
+    r1 = min(n1, r0 + block_rows)
+    if all(os.path.exists(slab_path(n, r0)) for n in names):
+      continue                                                  # finished in an earlier run
+    res = kernel_fn(x1[r0:r1], x2e, names if len(names) > 1 else names[0])
+    vals = [res] if len(names) == 1 else [getattr(res, n) for n in names]
+    for n, v in zip(names, vals):
+      v = np.asarray(v)
+      if v.shape != (r1 - r0, n2):
+        raise ValueError(f'`{n}` of rows [{r0}, {r1}) has shape {v.shape}, expected {(r1 - r0, n2)}.')
+      tmp = slab_path(n, r0) + '.tmp.npy'
+      np.save(tmp, v)
+      os.replace(tmp, slab_path(n, r0))                         # atomic: a slab file is always complete
+
+  outs = []
+  for n in names:
+    first = np.load(slab_path(n, 0), mmap_mode='r')
+    full_path = os.path.join(out_dir, f'{n}.npy')
+    full = np.lib.format.open_memmap(full_path, mode='w+', dtype=first.dtype, shape=(n1, n2))
+    for r0 in range(0, n1, block_rows):
+      s = np.load(slab_path(n, r0), mmap_mode='r')
+      full[r0:r0 + s.shape[0]] = s
+    full.flush()
+    del full
+    outs.append(np.load(full_path, mmap_mode='r'))
+  if isinstance(get, str):
+    return outs[0]
+  return collections.namedtuple('AnalyticKernel', names)(*outs)
