@@ -133,6 +133,17 @@ int ntk_program_output_shape(const ntk_program_t* prog, int32_t H, int32_t W,
                              int32_t in_is_gaussian, int32_t* out_H, int32_t* out_W,
                              int32_t* out_is_gaussian);
 
+/* Which kernel family ntk_gram_* runs `prog` on for inputs [n, H, W, C] (H == W == 0: [n, C]) under `flags`
+ * (INTEGRATION.md §5).  Pure host logic -- no GPU needed -- so a caller (or a test) can see
+ * that a network is on a fused path rather than on the one-kernel-per-op path. */
+#define NTK_PATH_GENERIC 0 /* one kernel per op on the canonical layout            */
+#define NTK_PATH_FUSED 1   /* fused stage kernels (k_stage_p / k_stage)            */
+#define NTK_PATH_RES 2     /* column-sparse residual kernels (k_res)               */
+#define NTK_PATH_DIAG 3    /* diagonal-column kernel (k_diagnet)                   */
+#define NTK_PATH_FCN 4     /* tensor-core input Gram + k_fcn_chain                 */
+int ntk_program_path(const ntk_program_t* prog, int32_t dtype, int32_t H, int32_t W, int32_t C,
+                     uint32_t flags, int32_t* path);
+
 /* ---- contexts: one per (host thread, GPU) -------------------------------
  * Own a stream, a device workspace and pinned staging buffers; replace the
  * PjRt client/executable cache behind `jit`/`pmap` in `_src/batching.py:689-787`. */

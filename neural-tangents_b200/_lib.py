@@ -19,11 +19,13 @@ NTK_NONE, NTK_ZERO, NTK_TENSOR = 0, 1, 2
 FLAG_NTK, FLAG_NO_FUSION, FLAG_WANT_COV, FLAG_PER_LAYER, FLAG_FULL_SQUARE = 1, 2, 4, 8, 16
 
 E_INVAL, E_CUDA, E_NOMEM, E_NOTGAUSSIAN, E_UNSUPPORTED, E_SHAPE = -1, -2, -3, -4, -5, -6
+PATH_NAMES = ('generic', 'fused', 'res', 'diag', 'fcn')   # NTK_PATH_* of include/ntk_b200.h
 
 # every symbol include/ntk_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = (
     'ntk_abi_version', 'ntk_last_error', 'ntk_device_count', 'ntk_program_create',
-    'ntk_program_destroy', 'ntk_program_output_shape', 'ntk_context_create', 'ntk_context_destroy',
+    'ntk_program_destroy', 'ntk_program_output_shape', 'ntk_program_path', 'ntk_context_create',
+    'ntk_context_destroy',
     'ntk_context_synchronize', 'ntk_context_stream', 'ntk_context_launch_count',
     'ntk_context_set_profiling', 'ntk_context_profile', 'ntk_gram_host',
     'ntk_gram_device', 'ntk_apply_host', 'ntk_workspace_bytes', 'ntk_device_malloc',
@@ -74,6 +76,7 @@ def load():
     lib.ntk_program_destroy.argtypes = [vp]
     lib.ntk_program_destroy.restype = None
     lib.ntk_program_output_shape.argtypes = [vp, i32, i32, i32, P(i32), P(i32), P(i32)]
+    lib.ntk_program_path.argtypes = [vp, i32, i32, i32, i32, u32, P(i32)]
     lib.ntk_context_create.argtypes = [i32, sz, P(vp)]
     lib.ntk_context_destroy.argtypes = [vp]
     lib.ntk_context_destroy.restype = None
@@ -144,6 +147,12 @@ class Program:
     check(self._lib.ntk_program_output_shape(self._h, H, W, int(in_is_gaussian), ctypes.byref(oh), ctypes.byref(ow),
                                               ctypes.byref(og)))
     return oh.value, ow.value, bool(og.value)
+
+  def path(self, H, W, C, x64=False, flags=0):
+    """Kernel family `ntk_gram_*` runs this program on: 'generic', 'fused', 'res', 'diag' or 'fcn'."""
+    out = ctypes.c_int32()
+    check(self._lib.ntk_program_path(self._h, NTK_F64 if x64 else NTK_F32, H, W, C, flags, ctypes.byref(out)))
+    return PATH_NAMES[out.value]
 
   def __del__(self):
     try:

@@ -956,6 +956,26 @@ int ntk_program_output_shape(const ntk_program_t* prog, int32_t H, int32_t W,
   return NTK_OK;
 }
 
+// Mirrors the dispatch order of gram_device_t (above); keep the two in step.
+int ntk_program_path(const ntk_program_t* prog, int32_t dtype, int32_t H, int32_t W, int32_t C,
+                     uint32_t flags, int32_t* path) {
+  if (!prog || !path) return fail(NTK_EINVAL, "bad arguments");
+  if (dtype != NTK_F32 && dtype != NTK_F64) return fail(NTK_EINVAL, "unknown dtype %d", dtype);
+  const bool fusable = !(flags & NTK_FLAG_NO_FUSION) && !(flags & NTK_FLAG_WANT_COV);
+  *path = NTK_PATH_GENERIC;
+  if (!fusable) return NTK_OK;
+  if (prog->fcn.n > 0 && H == 0) {
+    *path = NTK_PATH_FCN;
+  } else if (prog->fused.ok && H > 0 && fused_supported<float>(prog->fused, H, W, C)) {
+    *path = NTK_PATH_FUSED;
+  } else if (prog->diag.ok && H > 0 && H == W && H <= 32) {
+    *path = NTK_PATH_DIAG;
+  } else if (prog->res.ok && H > 0 && res_supported<float>(prog->res, H, W, C)) {
+    *path = NTK_PATH_RES;
+  }
+  return NTK_OK;
+}
+
 int ntk_context_create(int32_t device, size_t workspace_bytes, ntk_context_t** out) {
   if (!out) return fail(NTK_EINVAL, "out is NULL");
   int n = 0;

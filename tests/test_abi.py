@@ -136,3 +136,39 @@ def test_bench_reference_arm_prints_one_json_line():
     assert key in d, key
   assert d['impl'] == 'reference' and d['cpu_baseline']['kind'] == 'port' and d['value'] > 0
   assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
+
+
+def test_kernel_family_selection_without_gpu(lib):
+  """`ntk_program_path`: which kernel family a network runs on (host logic of the planners).  Guards against a
+  BASELINE configuration silently dropping to the one-kernel-per-op path."""
+  import cases
+  from neural_tangents_b200 import stax
+
+  def path(spec, H, W, C, **kw):
+    _, _, kf = cases.build(spec, stax)
+    low = stax._lowered(stax._strip(kf._spec), False, False, H > 0)
+    return low.program.path(H, W, C, **kw)
+
+  erf = ('erf', 1., 1., 0.)
+  erf_myrtle = ('serial', [erf if l == cases.RELU else l for l in cases.myrtle(10)[1]])
+  for x64 in (False, True):
+    for depth in (5, 7, 10):                                                   # BASELINE configs 2-4
+      assert path(cases.myrtle(depth), 32, 32, 3, x64=x64) == 'fused'
+      assert path(cases.myrtle(depth, 'gap'), 32, 32, 3, x64=x64) == 'fused'
+    assert path(erf_myrtle, 32, 32, 3, x64=x64) == 'fused'                      # Erf closed form is fused too
+    two_stage_16 = ('serial', [cases.conv(), cases.RELU] * 3 + [cases.pool()] + [cases.conv(), cases.RELU] * 3 +
+                    [('gap',), ('dense', 1., 0.)])
+    assert path(two_stage_16, 16, 16, 3, x64=x64) == 'fused'                     # 16 -> 8
+    assert path(cases.CASES['myrtle10_16px'][0], 16, 16, 3, x64=x64) == 'generic'  # 16 -> 8 -> 4: no 4x4 stage kernel
+    assert path(cases.fcn(3), 0, 0, 784, x64=x64) == 'fcn'                      # configs[0]
+    assert path(cases.wrn(), 16, 16, 3, x64=x64) == 'res'                       # config 5 (Relu and Erf)
+    assert path(cases.wrn(erf), 32, 32, 3, x64=x64) == 'res'
+  flat = ('serial', [cases.conv(W=1., b=None), cases.RELU] * 21 + [('flatten',)])   # README.md:399-416
+  assert path(flat, 32, 32, 3) == 'diag'
+  assert path(('serial', [cases.conv(W=1., b=None), cases.RELU] * 21 + [('gap',)]), 32, 32, 3) == 'fused'
+  # outside the fused families: other image sizes / channel counts, VALID convs, forced per-op path, cov outputs
+  assert path(cases.myrtle(10), 28, 28, 1) == 'generic'
+  assert path(cases.CASES['erf_valid'][0], 6, 5, 2) == 'generic'
+  assert path(cases.myrtle(10), 32, 32, 3, flags=lib.FLAG_NO_FUSION) == 'generic'
+  assert path(cases.myrtle(10), 32, 32, 3, flags=lib.FLAG_WANT_COV) == 'generic'
+  assert path(cases.CASES['wrn_relu'][0], 8, 8, 3) == 'generic'                 # 8x8 with a stride-2 block: 4x4 maps
