@@ -27,10 +27,11 @@ inline int variant() {
   return v;
 }
 
-template <int S, int L, int IN, int EPI, bool NTK, int CIN, bool RC, int LAG = 1, int MINB = 2, bool Q2P = true>
+template <int S, int L, int IN, int EPI, bool NTK, int CIN, bool RC, int LAG = 1, int MINB = 2, bool Q2P = true,
+          int VAR = 0>
 int launch_p_impl(cudaStream_t stream, int64_t* launches, const StageArgs<float>& a) {
   using G = PGeom<S>;
-  auto kern = k_stage_p<S, L, IN, EPI, NTK, CIN, RC, LAG, MINB, Q2P, NTK_PACKED_ERF != 0>;
+  auto kern = k_stage_p<S, L, IN, EPI, NTK, CIN, RC, LAG, MINB, Q2P, NTK_PACKED_ERF != 0, VAR>;
   const size_t smem = stage_p_smem_bytes<S, L, IN, EPI, NTK, CIN, Q2P>();
   static thread_local bool configured = false;
   if (!configured) {
@@ -68,6 +69,21 @@ int launch_p_epi(cudaStream_t stream, int64_t* launches, int epi, const StageArg
       //   by register-file read bandwidth (profiles/microbench/rf_bandwidth.cu), not latency or occupancy.
       if (!NTK_PACKED_ERF && L == 3 && IN == IN_FROM_X && NTK && variant() == 2)
         return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false, 1, 3, false>(stream, launches, a);
+      // VAR bit 1 = bias-free convs (b_std = 0, every Myrtle config): the predicated bias adds are compiled out.
+      // Measured on B200 for the dominant kernel: 38.43 -> 37.07 ms per 9216 pairs, results bit-identical
+      // (profiles/check_variant.py), so it is the default whenever the stage has no bias; NTK_B200_PVAR=7 forces
+      // the general instantiation for A/B runs.
+      // VAR bit 0 = degree-7 fit of G (NTK_B200_PVAR=4, or 6 together with bit 1): a round-2 candidate, NOT measured
+      // (SASS: 68.0 / 65.4 register words per element-layer against 70.3 / 67.3); the self-pair runs keep the degree-8
+      // kernel, so it gives up the exact duplicate-pair diagonal.
+      if (!NTK_PACKED_ERF && L == 3 && IN == IN_FROM_X && NTK && S == 32) {
+        const bool no_bias = a.lp[0].bias == 0.f && a.lp[1].bias == 0.f && a.lp[2].bias == 0.f;
+        if (variant() == 4) return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false, 1, 2, true, 1>(stream, launches, a);
+        if (variant() == 6 && no_bias)
+          return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false, 1, 2, true, 3>(stream, launches, a);
+        if (variant() != 7 && no_bias)
+          return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false, 1, 2, true, 2>(stream, launches, a);
+      }
       return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false>(stream, launches, a);
     default:
       return launch_p_impl<S, L, IN, EPI_GAP, NTK, CIN, false>(stream, launches, a);

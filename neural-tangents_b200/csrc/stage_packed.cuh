@@ -78,12 +78,27 @@ __device__ __forceinline__ float2 neg_acos_over_sin2(float2 c) {
   return g;
 }
 
+// Degree-7 minimax fit of -G (|err| < 5.6e-7, the size of one fp32 rounding of G): one FFMA2 less per pair.
+// NOT the default -- kept for an A/B measurement (NTK_B200_PVAR=4): the degree-8 fit keeps the fp32 path at
+// 1.8e-7 of the float64 result.
+__device__ __forceinline__ float2 neg_acos_over_sin2_deg7(float2 c) {
+  float2 g = f2s(0.028090565068060184f);
+  g = __ffma2_rn(g, c, f2s(-0.14106766428166093f));
+  g = __ffma2_rn(g, c, f2s(0.33101607627600144f));
+  g = __ffma2_rn(g, c, f2s(-0.5139260110419339f));
+  g = __ffma2_rn(g, c, f2s(0.6503503954074816f));
+  g = __ffma2_rn(g, c, f2s(-0.7835891524309508f));
+  g = __ffma2_rn(g, c, f2s(0.9999221177978991f));
+  g = __ffma2_rn(g, c, f2s(-1.5707957734418327f));
+  return g;
+}
+
 // ABRelu on two elements (elementwise.py:444-455; see act_point in fused_kernels.cuh).
 //   K         conv(K_in) + b            (the reference's nngp after the conv)
 //   U         conv(U_in) + b = conv(T_in) + K, i.e. the reference's ntk after the conv (linear.py:1396-1398)
 //   q1, nq2   q1 and -q2 of the two elements
 //   Ko = coef*s + kd*K  (K'),   Uo = kd*U + Ko  (= T' + K', the carried form of the next layer's ntk)
-template <bool NTK>
+template <bool NTK, bool POLY7 = false>
 __device__ __forceinline__ void act_pair(float2 K, float2 U, float2 q1, float2 nq2, float2 coef2,
                                          float2 hab2, float2& Ko, float2& Uo) {
   const float2 np = __fmul2_rn(q1, nq2);                 // -(q1 q2), exact negation of the product
@@ -103,7 +118,7 @@ __device__ __forceinline__ void act_pair(float2 K, float2 U, float2 q1, float2 n
   float2 ac;
   ac.x = __fmul_rn(fabsf(K.x), rb.x);
   ac.y = __fmul_rn(fabsf(K.y), rb.y);
-  const float2 u = __ffma2_rn(sn, neg_acos_over_sin2(ac), f2s(kHalfPiF));
+  const float2 u = __ffma2_rn(sn, POLY7 ? neg_acos_over_sin2_deg7(ac) : neg_acos_over_sin2(ac), f2s(kHalfPiF));
   float2 us;
   us.x = copysign_bits(u.x, K.x);
   us.y = copysign_bits(u.y, K.y);
@@ -179,8 +194,11 @@ size_t stage_p_smem_bytes() {
 //   Q2P   q2 rows hold explicit (e, e+4) pairs (one LDS.64 per pair, 2x shared memory) or are planar
 //         (two LDS.32 per pair)
 //   ERF   the stage may contain Erf layers (runtime branch per layer); ERF = false carries no Erf code
+//   VAR   bit 1: the convs have no bias (the predicated bias adds are compiled out; bit-identical results, used by
+//         default for the dominant kernel when b_std = 0); bit 0: degree-7 fit of G, an unmeasured round-2
+//         candidate reachable only through NTK_B200_PVAR (stage_packed.cu)
 template <int S, int L, int IN, int EPI, bool NTK, int CIN, bool RC, int LAG = 1, int MINB = 2, bool Q2P = true,
-          bool ERF = false>
+          bool ERF = false, int VAR = 0>
 __global__ void __launch_bounds__(PGeom<S>::NT, MINB)
 k_stage_p(const StageArgs<float> a) {
   using G = PGeom<S>;
@@ -423,7 +441,7 @@ k_stage_p(const StageArgs<float> a) {
         const unsigned q2row = q2base + (unsigned)((l * S + h2) * S * (Q2P ? 8 : 4));
         const float2 coef2 = f2s(a.lp[l].coef), hab2 = f2s(a.lp[l].hab2);
         const float bias = a.lp[l].bias;
-        const bool has_bias = bias != 0.f;
+        const bool has_bias = !(VAR & 2) && bias != 0.f;
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
           float2 ck = __ffma2_rn(vD, RK[l][slot][j], tk[j]);
@@ -443,7 +461,7 @@ k_stage_p(const StageArgs<float> a) {
           if (ERF && a.lp[l].kind == ACT_ERF)
             act_pair_erf<NTK>(ck, cu, q1p[j], nq2, a.lp[l].e_in, a.lp[l].eA, a.lp[l].eT, a.lp[l].eC, BK[l][j], BU[l][j]);
           else
-            act_pair<NTK>(ck, cu, q1p[j], nq2, coef2, hab2, BK[l][j], BU[l][j]);
+            act_pair<NTK, (VAR & 1) != 0>(ck, cu, q1p[j], nq2, coef2, hab2, BK[l][j], BU[l][j]);
         }
       }
 #undef INK
