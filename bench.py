@@ -474,7 +474,8 @@ def main():
   ap.add_argument('--dtype', default='f32', choices=['f32', 'f64'])
   ap.add_argument('--block', type=int, nargs=2, default=[96, 96])
   ap.add_argument('--e2e-batch', type=int, default=32)
-  ap.add_argument('--ref-cols', type=int, default=4)
+  ap.add_argument('--ref-cols', type=int, default=12,
+                  help='x2 columns per worker in a CPU step (about 10 s of CPU work per step on every core)')
   ap.add_argument('--no-fusion', action='store_true')
   ap.add_argument('--no-cpu', action='store_true')
   ap.add_argument('--symmetric', action='store_true',
