@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NTK_B200_ABI_VERSION 1
+#define NTK_B200_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------ */
 #define NTK_OK 0
@@ -113,6 +113,12 @@ typedef struct ntk_state {
                                     launch: every layer makes one HBM round trip
                                     (the traffic model of the roofline)          */
 #define NTK_FLAG_WANT_COV 4u     /* also return cov1 / cov2                    */
+#define NTK_FLAG_UPPER_ONLY 32u  /* x2 != NULL and x1 is the SAME samples as x2[0:n1] (a row slab of a symmetric
+                                    Gram, columns starting at the slab's first row): entries (i, j < i) are not
+                                    needed and may be left unwritten.  The fused path enumerates only the upper
+                                    trapezoid; the other paths ignore the hint.  This is the building block of the
+                                    triangular multi-GPU schedule the reference leaves as a TODO
+                                    (`_src/batching.py:370`). */
 
 typedef struct ntk_program ntk_program_t;
 typedef struct ntk_context ntk_context_t;
@@ -196,11 +202,70 @@ int ntk_apply_host(ntk_context_t* ctx, const ntk_program_t* prog, int32_t dtype,
 int ntk_workspace_bytes(const ntk_program_t* prog, int32_t dtype, int32_t t1, int32_t t2, int32_t H,
                         int32_t W, int32_t C, uint32_t flags, size_t* bytes);
 
+/* ---- caller-stream entry (what an XLA custom call binds) -----------------------------------------
+ * Same as ntk_gram_device, but every kernel and copy is enqueued on `cuda_stream` (a cudaStream_t of the
+ * context's device, e.g. XLA's compute stream from ffi::PlatformStream) and the call returns without
+ * synchronising; results are valid once work enqueued on that stream before the call's return has run.
+ * The context's workspace is reused in stream order: when consecutive calls use different streams the new
+ * stream first waits (cudaStreamWaitEvent, on the device) for the previous call's work.
+ * Replaces the dispatch of the jitted `kernel_fn` executable, `_src/stax/requirements.py:939-953`,
+ * `_src/batching.py:725,760-776`. */
+int ntk_gram_device_on_stream(ntk_context_t* ctx, const ntk_program_t* prog, int32_t dtype, const void* x1,
+                              int32_t n1, const void* x2, int32_t n2, int32_t H, int32_t W, int32_t C,
+                              uint32_t flags, void* nngp, void* ntk, int64_t ld, void* cov1, void* cov2,
+                              void* cuda_stream);
+
+/* Kernel-in / Kernel-out on DEVICE pointers, asynchronous on `cuda_stream` (NULL = the context stream):
+ * composition `kernel_fn(kernel_fn_a(x1, x2))` without the host round trip of ntk_apply_host
+ * (`requirements.py:935-937`, `_src/utils/kernel.py:151-167`). */
+int ntk_apply_device(ntk_context_t* ctx, const ntk_program_t* prog, int32_t dtype, const ntk_state_t* in,
+                     ntk_state_t* out, void* cuda_stream);
+
+/* ---- multi-GPU: one process (or host thread) per GPU, NCCL over NVLink / NVSwitch -----------------
+ * The reference's device parallelism is `pmap` over x1 rows with x2 replicated and no collective
+ * (`_src/batching.py:505-644`).  Here each rank owns row blocks of the Gram matrix; x1 / x2 are broadcast
+ * once, result slabs are all-gathered, and there is no reduction.  libnccl is loaded with dlopen on the
+ * first ntk_comm_* call, so the library itself has no link-time NCCL dependency.
+ * All collectives are enqueued on the stream of the context the communicator was created with. */
+#define NTK_COMM_ID_BYTES 128
+typedef struct ntk_comm ntk_comm_t;
+/* rank 0 creates the id; the launcher hands it to every rank (file / env / TCP -- not the library's business) */
+int ntk_comm_unique_id(void* id_out /* NTK_COMM_ID_BYTES */);
+int ntk_comm_create(ntk_context_t* ctx, const void* id, int32_t rank, int32_t world, ntk_comm_t** out);
+void ntk_comm_destroy(ntk_comm_t* comm);
+int ntk_comm_rank(const ntk_comm_t* comm);
+int ntk_comm_world(const ntk_comm_t* comm);
+int ntk_comm_nccl_version(int* version);
+int ntk_comm_broadcast(ntk_comm_t* comm, void* dev_buf, size_t bytes, int32_t root);
+int ntk_comm_all_gather(ntk_comm_t* comm, const void* send_dev, void* recv_dev, size_t bytes_per_rank);
+
+/* Symmetric Gram assembled from gathered upper-trapezoid row slabs (NTK_FLAG_UPPER_ONLY):
+ *   out[i, j] = slabs[row_of[i], j]  (j >= i),   slabs[row_of[j], i]  (j < i)
+ * `slabs` is [rows, ld_slabs], `row_of` is int32[n] on the device, `out` is [n, ld_out]. */
+int ntk_sym_assemble(ntk_context_t* ctx, int32_t dtype, const void* slabs, int64_t ld_slabs,
+                     const int32_t* row_of, int32_t n, void* out, int64_t ld_out);
+
 /* ---- device memory helpers (so a host language needs no CUDA binding) ---- */
 int ntk_device_malloc(int32_t device, size_t bytes, void** ptr);
 int ntk_device_free(int32_t device, void* ptr);
 int ntk_memcpy_h2d(ntk_context_t* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int ntk_memcpy_d2h(ntk_context_t* ctx, void* dst_host, const void* src_dev, size_t bytes);
+int ntk_memset_async(ntk_context_t* ctx, void* dst_dev, int32_t value, size_t bytes);
+int ntk_context_device(const ntk_context_t* ctx);
+/* Page-locked host memory: ntk_gram_host moves pageable caller arrays through the context's pinned
+ * staging ring; arrays that already live in pinned memory (these) are DMA'd directly. */
+int ntk_host_alloc(size_t bytes, void** ptr);
+int ntk_host_free(void* ptr);
+/* CUDA events on the context stream (device-side timing for a host language without a CUDA binding). */
+int ntk_event_create(void** event);
+int ntk_event_record(ntk_context_t* ctx, void* event);
+int ntk_event_elapsed_ms(void* start, void* stop, float* ms); /* waits for `stop` */
+void ntk_event_destroy(void* event);
+/* A second stream on the context's device (tests of the caller-stream entry; bench timing streams). */
+int ntk_stream_create(int32_t device, void** cuda_stream);
+int ntk_stream_synchronize(void* cuda_stream);
+int ntk_stream_query(void* cuda_stream, int32_t* done); /* done = 1 when all enqueued work has finished */
+void ntk_stream_destroy(void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,8 @@ NTK_F32, NTK_F64 = 0, 1
 OP_DENSE, OP_CONV, OP_ABRELU, OP_ERF, OP_AVGPOOL, OP_GAP, OP_FLATTEN, OP_FANINSUM, OP_IDENTITY = range(1, 10)
 PAD = {'VALID': 0, 'SAME': 1, 'CIRCULAR': 2}
 NTK_NONE, NTK_ZERO, NTK_TENSOR = 0, 1, 2
-FLAG_NTK, FLAG_NO_FUSION, FLAG_WANT_COV, FLAG_PER_LAYER, FLAG_FULL_SQUARE = 1, 2, 4, 8, 16
+FLAG_NTK, FLAG_NO_FUSION, FLAG_WANT_COV, FLAG_PER_LAYER, FLAG_FULL_SQUARE, FLAG_UPPER_ONLY = 1, 2, 4, 8, 16, 32
+COMM_ID_BYTES = 128
 
 E_INVAL, E_CUDA, E_NOMEM, E_NOTGAUSSIAN, E_UNSUPPORTED, E_SHAPE = -1, -2, -3, -4, -5, -6
 PATH_NAMES = ('generic', 'fused', 'res', 'diag', 'fcn')   # NTK_PATH_* of include/ntk_b200.h
@@ -29,7 +30,13 @@ EXPORTED_SYMBOLS = (
     'ntk_context_synchronize', 'ntk_context_stream', 'ntk_context_launch_count',
     'ntk_context_set_profiling', 'ntk_context_profile', 'ntk_gram_host',
     'ntk_gram_device', 'ntk_apply_host', 'ntk_workspace_bytes', 'ntk_device_malloc',
-    'ntk_device_free', 'ntk_memcpy_h2d', 'ntk_memcpy_d2h')
+    'ntk_device_free', 'ntk_memcpy_h2d', 'ntk_memcpy_d2h',
+    # ABI version 2
+    'ntk_gram_device_on_stream', 'ntk_apply_device', 'ntk_comm_unique_id', 'ntk_comm_create',
+    'ntk_comm_destroy', 'ntk_comm_rank', 'ntk_comm_world', 'ntk_comm_nccl_version', 'ntk_comm_broadcast',
+    'ntk_comm_all_gather', 'ntk_sym_assemble', 'ntk_memset_async', 'ntk_context_device', 'ntk_host_alloc',
+    'ntk_host_free', 'ntk_event_create', 'ntk_event_record', 'ntk_event_elapsed_ms', 'ntk_event_destroy',
+    'ntk_stream_create', 'ntk_stream_synchronize', 'ntk_stream_query', 'ntk_stream_destroy')
 
 
 class NtkOp(ctypes.Structure):
@@ -55,6 +62,25 @@ _lib = None
 _lock = threading.Lock()
 
 
+def _prefer_bundled_nccl():
+  """libntk_b200.so resolves NCCL with dlopen on the first `ntk_comm_*` call (NTK_B200_NCCL_LIB, then
+  libnccl.so.2 on the loader path).  A process can hold only one libnccl.so.2 (the loader de-duplicates by
+  SONAME), so when the Python environment ships a newer NCCL wheel (`nvidia-nccl-cu12`, the one other
+  frameworks in the same process were built against) that copy is named explicitly."""
+  if os.environ.get('NTK_B200_NCCL_LIB'):
+    return
+  import importlib.util
+  try:
+    spec = importlib.util.find_spec('nvidia.nccl')
+  except (ImportError, ValueError):
+    spec = None
+  for base in (spec.submodule_search_locations if spec and spec.submodule_search_locations else []):
+    cand = os.path.join(base, 'lib', 'libnccl.so.2')
+    if os.path.exists(cand):
+      os.environ['NTK_B200_NCCL_LIB'] = cand
+      return
+
+
 def load():
   """Loads the shared library (once).  Raises if it has not been built."""
   global _lib
@@ -66,6 +92,7 @@ def load():
           f'{LIB_PATH} not found: build the CUDA library first '
           '(`python -c "import __graft_entry__ as g; g.build()"` or `make -C neural-tangents_b200/csrc`). '
           'neural_tangents_b200 has no CPU fallback.')
+    _prefer_bundled_nccl()
     lib = ctypes.CDLL(LIB_PATH)
     vp, i32, i64, u32, sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_size_t
     P = ctypes.POINTER
@@ -96,6 +123,32 @@ def load():
     lib.ntk_device_free.argtypes = [i32, vp]
     lib.ntk_memcpy_h2d.argtypes = [vp, vp, vp, sz]
     lib.ntk_memcpy_d2h.argtypes = [vp, vp, vp, sz]
+    lib.ntk_gram_device_on_stream.argtypes = gram_args + [vp]
+    lib.ntk_apply_device.argtypes = [vp, vp, i32, P(NtkState), P(NtkState), vp]
+    lib.ntk_comm_unique_id.argtypes = [vp]
+    lib.ntk_comm_create.argtypes = [vp, vp, i32, i32, P(vp)]
+    lib.ntk_comm_destroy.argtypes = [vp]
+    lib.ntk_comm_destroy.restype = None
+    lib.ntk_comm_rank.argtypes = [vp]
+    lib.ntk_comm_world.argtypes = [vp]
+    lib.ntk_comm_nccl_version.argtypes = [P(ctypes.c_int)]
+    lib.ntk_comm_broadcast.argtypes = [vp, vp, sz, i32]
+    lib.ntk_comm_all_gather.argtypes = [vp, vp, vp, sz]
+    lib.ntk_sym_assemble.argtypes = [vp, i32, vp, i64, vp, i32, vp, i64]
+    lib.ntk_memset_async.argtypes = [vp, vp, i32, sz]
+    lib.ntk_context_device.argtypes = [vp]
+    lib.ntk_host_alloc.argtypes = [sz, P(vp)]
+    lib.ntk_host_free.argtypes = [vp]
+    lib.ntk_event_create.argtypes = [P(vp)]
+    lib.ntk_event_record.argtypes = [vp, vp]
+    lib.ntk_event_elapsed_ms.argtypes = [vp, vp, P(ctypes.c_float)]
+    lib.ntk_event_destroy.argtypes = [vp]
+    lib.ntk_event_destroy.restype = None
+    lib.ntk_stream_create.argtypes = [i32, P(vp)]
+    lib.ntk_stream_synchronize.argtypes = [vp]
+    lib.ntk_stream_query.argtypes = [vp, P(i32)]
+    lib.ntk_stream_destroy.argtypes = [vp]
+    lib.ntk_stream_destroy.restype = None
     _lib = lib
     return lib
 
@@ -171,10 +224,35 @@ class Context:
     check(lib.ntk_context_create(device, workspace_bytes, ctypes.byref(self._h)))
     self._lib = lib
     self.device = device
+    # one context per GPU is shared by every host thread that computes on it (workspace, stream and staging
+    # buffers are per context): calls are serialised with this lock
+    self.lock = threading.RLock()
 
   @property
   def handle(self):
     return self._h
+
+  # ---- device memory / events through the C-ABI (a host language needs no CUDA binding) ----
+  def malloc(self, nbytes):
+    p = ctypes.c_void_p()
+    check(self._lib.ntk_device_malloc(self.device, max(int(nbytes), 1), ctypes.byref(p)))
+    return p.value
+
+  def free(self, ptr):
+    if ptr:
+      check(self._lib.ntk_device_free(self.device, ctypes.c_void_p(ptr)))
+
+  def h2d(self, dst_ptr, arr):
+    arr = np.ascontiguousarray(arr)
+    check(self._lib.ntk_memcpy_h2d(self._h, ctypes.c_void_p(dst_ptr), _ptr(arr), arr.nbytes))
+    return arr   # keep alive until the stream has consumed it (callers synchronise)
+
+  def d2h(self, arr, src_ptr):
+    check(self._lib.ntk_memcpy_d2h(self._h, _ptr(arr), ctypes.c_void_p(src_ptr), arr.nbytes))
+    return arr
+
+  def memset(self, ptr, value, nbytes):
+    check(self._lib.ntk_memset_async(self._h, ctypes.c_void_p(ptr), value, nbytes))
 
   def synchronize(self):
     check(self._lib.ntk_context_synchronize(self._h))
@@ -234,19 +312,82 @@ def device_count():
 
 
 def get_context(device=None):
-  """Per-(thread, device) cached context."""
+  """The context of GPU `device` (one per device, created on first use; callers hold `ctx.lock` while they
+  run on it).  `nt.batch(device_count=D)` spawns fresh host threads on every call: keying the cache by thread
+  would leak a workspace per call."""
   from ._config import config
   if device is None:
     device = getattr(_tls, 'device', None)
   if device is None:
     device = config.device
-  key = (threading.get_ident(), device)
   with _ctx_lock:
-    ctx = _contexts.get(key)
+    ctx = _contexts.get(device)
     if ctx is None:
       ctx = Context(device, config.workspace_bytes)
-      _contexts[key] = ctx
+      _contexts[device] = ctx
     return ctx
+
+
+def close_contexts():
+  """Destroys every cached context (frees the device workspaces)."""
+  with _ctx_lock:
+    for ctx in _contexts.values():
+      ctx.close()
+    _contexts.clear()
+
+
+# ---- page-locked host arrays -----------------------------------------------------------------------
+# Results of `gram_host` are allocated in pinned memory, so the device -> host copy is a direct DMA at PCIe
+# speed (pageable destinations go through the context's staging ring instead).  Blocks are recycled through a
+# small pool: cudaMallocHost / cudaFreeHost cost milliseconds and synchronise the device.
+_PIN_MIN, _PIN_MAX, _PIN_POOL_CAP = 1 << 16, 1 << 28, 1 << 30
+_pin_pool = {}          # rounded size -> [ptr, ...]
+_pin_pooled_bytes = 0
+_pin_lock = threading.Lock()
+
+
+def _pin_release(ptr, size):
+  global _pin_pooled_bytes
+  with _pin_lock:
+    if _pin_pooled_bytes + size <= _PIN_POOL_CAP:
+      _pin_pool.setdefault(size, []).append(ptr)
+      _pin_pooled_bytes += size
+      return
+  try:
+    load().ntk_host_free(ctypes.c_void_p(ptr))
+  except Exception:
+    pass
+
+
+def pinned_empty(shape, dtype):
+  """`np.empty(shape, dtype)` in page-locked memory (falls back to pageable memory for tiny / huge arrays)."""
+  global _pin_pooled_bytes
+  dtype = np.dtype(dtype)
+  nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+  if nbytes < _PIN_MIN or nbytes > _PIN_MAX:
+    return np.empty(shape, dtype)
+  size = 1 << (nbytes - 1).bit_length()
+  ptr = None
+  with _pin_lock:
+    free = _pin_pool.get(size)
+    if free:
+      ptr = free.pop()
+      _pin_pooled_bytes -= size
+  if ptr is None:
+    p = ctypes.c_void_p()
+    if load().ntk_host_alloc(size, ctypes.byref(p)) != 0 or not p.value:
+      return np.empty(shape, dtype)
+    ptr = p.value
+  buf = (ctypes.c_char * size).from_address(ptr)
+  import weakref
+  weakref.finalize(buf, _pin_release, ptr, size)   # `buf` is the base of every view of the array
+  return np.frombuffer(buf, dtype=dtype, count=nbytes // dtype.itemsize).reshape(shape)
+
+
+def pinned_copy(a):
+  out = pinned_empty(a.shape, a.dtype)
+  np.copyto(out, a)
+  return out
 
 
 def _ptr(a):
@@ -260,22 +401,29 @@ def gram_host(ctx, prog, x1, x2, H, W, C, flags, out_h, out_w, want_ntk, want_co
   n1 = x1.shape[0]
   n2 = n1 if x2 is None else x2.shape[0]
   sp = (out_h, out_h, out_w, out_w) if out_h > 0 else ()
-  nngp = np.empty((n1, n2) + sp, x1.dtype)
-  ntk = np.empty((n1, n2) + sp, x1.dtype) if want_ntk else None
+  nngp = pinned_empty((n1, n2) + sp, x1.dtype)
+  ntk = pinned_empty((n1, n2) + sp, x1.dtype) if want_ntk else None
   cov1 = np.empty((n1,) + sp, x1.dtype) if want_cov else None
   cov2 = np.empty((n2,) + sp, x1.dtype) if (want_cov and x2 is not None) else None
   f = flags | (FLAG_NTK if want_ntk else 0) | (FLAG_WANT_COV if want_cov else 0)
-  check(lib.ntk_gram_host(ctx.handle, prog.handle, dt, _ptr(x1), n1, _ptr(x2), n2, H, W, C, f,
-                          _ptr(nngp), _ptr(ntk), n2, _ptr(cov1), _ptr(cov2)))
+  with ctx.lock:
+    check(lib.ntk_gram_host(ctx.handle, prog.handle, dt, _ptr(x1), n1, _ptr(x2), n2, H, W, C, f,
+                            _ptr(nngp), _ptr(ntk), n2, _ptr(cov1), _ptr(cov2)))
   return dict(nngp=nngp, ntk=ntk, cov1=cov1, cov2=cov2)
 
 
-def gram_device(ctx, prog, dtype, x1_ptr, n1, x2_ptr, n2, H, W, C, flags, nngp_ptr, ntk_ptr, ld):
-  """Device-pointer entry (asynchronous on the context stream); pointers are ints."""
+def gram_device(ctx, prog, dtype, x1_ptr, n1, x2_ptr, n2, H, W, C, flags, nngp_ptr, ntk_ptr, ld, stream=None):
+  """Device-pointer entry; pointers are ints.  Asynchronous on the context stream, or on `stream` (a
+  cudaStream_t as an int: the caller-stream entry `ntk_gram_device_on_stream`)."""
   lib = load()
   f = flags | (FLAG_NTK if ntk_ptr else 0)
-  check(lib.ntk_gram_device(ctx.handle, prog.handle, dtype_code(dtype), x1_ptr, n1, x2_ptr, n2, H, W,
-                            C, f, nngp_ptr, ntk_ptr, ld, None, None))
+  with ctx.lock:
+    if stream is None:
+      check(lib.ntk_gram_device(ctx.handle, prog.handle, dtype_code(dtype), x1_ptr, n1, x2_ptr, n2, H, W,
+                                C, f, nngp_ptr, ntk_ptr, ld, None, None))
+    else:
+      check(lib.ntk_gram_device_on_stream(ctx.handle, prog.handle, dtype_code(dtype), x1_ptr, n1, x2_ptr, n2, H, W,
+                                          C, f, nngp_ptr, ntk_ptr, ld, None, None, ctypes.c_void_p(stream)))
 
 
 def apply_host(ctx, prog, dtype, nngp, ntk, cov1, cov2, H, W, ntk_mode, is_gaussian, out_h, out_w):
@@ -291,8 +439,97 @@ def apply_host(ctx, prog, dtype, nngp, ntk, cov1, cov2, H, W, ntk_mode, is_gauss
   sin = NtkState(_ptr(nngp), _ptr(ntk) if ntk_mode == NTK_TENSOR else None, _ptr(cov1), _ptr(cov2),
                  n1, n2, H, W, ntk_mode, int(is_gaussian))
   sout = NtkState(_ptr(o_nngp), _ptr(o_ntk), _ptr(o_cov1), _ptr(o_cov2), n1, n2, out_h, out_w, 0, 0)
-  check(lib.ntk_apply_host(ctx.handle, prog.handle, dt, ctypes.byref(sin), ctypes.byref(sout)))
+  with ctx.lock:
+    check(lib.ntk_apply_host(ctx.handle, prog.handle, dt, ctypes.byref(sin), ctypes.byref(sout)))
   if sout.ntk_mode == NTK_ZERO and o_ntk is not None:
     o_ntk = np.zeros((), dtype)
   return dict(nngp=o_nngp, ntk=o_ntk, cov1=o_cov1, cov2=o_cov2, ntk_mode=sout.ntk_mode,
               is_gaussian=bool(sout.is_gaussian))
+
+
+def apply_device(ctx, prog, dtype, n1, n2, H, W, ntk_mode, is_gaussian, in_ptrs, out_ptrs, out_h, out_w,
+                 stream=None):
+  """Kernel-in / Kernel-out on DEVICE pointers (ints; `in_ptrs` / `out_ptrs` = (nngp, ntk, cov1, cov2), 0 / None
+  for absent tensors).  Asynchronous on the context stream or on `stream`.  Returns (ntk_mode, is_gaussian)."""
+  lib = load()
+  v = lambda p: ctypes.c_void_p(p) if p else None
+  sin = NtkState(v(in_ptrs[0]), v(in_ptrs[1]) if ntk_mode == NTK_TENSOR else None, v(in_ptrs[2]), v(in_ptrs[3]),
+                 n1, n2, H, W, ntk_mode, int(is_gaussian))
+  sout = NtkState(v(out_ptrs[0]), v(out_ptrs[1]), v(out_ptrs[2]), v(out_ptrs[3]), n1, n2, out_h, out_w, 0, 0)
+  with ctx.lock:
+    check(lib.ntk_apply_device(ctx.handle, prog.handle, dtype_code(dtype), ctypes.byref(sin), ctypes.byref(sout),
+                               ctypes.c_void_p(stream) if stream else None))
+  return sout.ntk_mode, bool(sout.is_gaussian)
+
+
+class Event:
+  """CUDA event on a context stream (`ntk_event_*`)."""
+
+  def __init__(self):
+    self._lib = load()
+    self._h = ctypes.c_void_p()
+    check(self._lib.ntk_event_create(ctypes.byref(self._h)))
+
+  def record(self, ctx):
+    check(self._lib.ntk_event_record(ctx.handle, self._h))
+
+  def elapsed_ms(self, stop):
+    ms = ctypes.c_float()
+    check(self._lib.ntk_event_elapsed_ms(self._h, stop._h, ctypes.byref(ms)))
+    return ms.value
+
+  def __del__(self):
+    try:
+      self._lib.ntk_event_destroy(self._h)
+    except Exception:
+      pass
+
+
+class Comm:
+  """NCCL communicator bound to a context (`ntk_comm_*`): one rank per GPU."""
+
+  def __init__(self, ctx, unique_id: bytes, rank: int, world: int):
+    self._lib = load()
+    self.ctx = ctx
+    self._h = ctypes.c_void_p()
+    if len(unique_id) != COMM_ID_BYTES:
+      raise ValueError(f'unique id must be {COMM_ID_BYTES} bytes')
+    buf = ctypes.create_string_buffer(unique_id, COMM_ID_BYTES)
+    check(self._lib.ntk_comm_create(ctx.handle, buf, rank, world, ctypes.byref(self._h)))
+    self.rank, self.world = rank, world
+
+  @staticmethod
+  def unique_id() -> bytes:
+    buf = ctypes.create_string_buffer(COMM_ID_BYTES)
+    check(load().ntk_comm_unique_id(buf))
+    return buf.raw
+
+  @staticmethod
+  def nccl_version() -> int:
+    v = ctypes.c_int()
+    check(load().ntk_comm_nccl_version(ctypes.byref(v)))
+    return v.value
+
+  def broadcast(self, dev_ptr, nbytes, root=0):
+    check(self._lib.ntk_comm_broadcast(self._h, ctypes.c_void_p(dev_ptr), nbytes, root))
+
+  def all_gather(self, send_ptr, recv_ptr, nbytes_per_rank):
+    check(self._lib.ntk_comm_all_gather(self._h, ctypes.c_void_p(send_ptr), ctypes.c_void_p(recv_ptr),
+                                        nbytes_per_rank))
+
+  def close(self):
+    if self._h:
+      self._lib.ntk_comm_destroy(self._h)
+      self._h = ctypes.c_void_p()
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
+
+
+def sym_assemble(ctx, dtype, slabs_ptr, ld_slabs, row_of_ptr, n, out_ptr, ld_out):
+  with ctx.lock:
+    check(load().ntk_sym_assemble(ctx.handle, dtype_code(dtype), ctypes.c_void_p(slabs_ptr), ld_slabs,
+                                  ctypes.c_void_p(row_of_ptr), n, ctypes.c_void_p(out_ptr), ld_out))

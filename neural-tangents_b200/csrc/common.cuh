@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -44,6 +45,24 @@ inline int fail(int code, const char* fmt, ...) {
     int _s = (expr);           \
     if (_s != NTK_OK) return _s; \
   } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of (device, function): a host thread that
+// moves to another GPU must set it again there.  One process-wide table keyed by (device, function).
+inline int ensure_dynamic_smem(const void* func, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> done;  // largest size configured so far
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(NTK_ECUDA, "cudaGetDevice -> %s", cudaGetErrorString(e));
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = done.find({dev, func});
+  if (it != done.end() && it->second >= bytes) return NTK_OK;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess)
+    return fail(NTK_ECUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize = %zu) -> %s", bytes, cudaGetErrorString(e));
+  done[{dev, func}] = bytes;
+  return NTK_OK;
+}
 
 // ---- padding arithmetic (lax.padtype_to_pads) ----------
 struct AxisGeom {

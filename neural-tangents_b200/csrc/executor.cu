@@ -41,7 +41,17 @@ struct ntk_program {
 
 struct ntk_context {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // stream of the current call: own_stream unless a *_on_stream entry is running
+  cudaStream_t own_stream = nullptr;  // created (and destroyed) by the context
+  // Workspace reuse across calls on different streams is ordered on the device: every call records
+  // `order_ev` on the stream it used; a call on another stream makes that stream wait for it first.
+  cudaEvent_t order_ev = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool order_valid = false;
+  // pinned staging ring of ntk_gram_host (pageable caller arrays): 2 slots of kPinSlot bytes
+  char* pin = nullptr;
+  cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+  bool pin_busy[2] = {false, false};
   char* ws = nullptr;
   size_t ws_bytes = 0;
   int64_t launches = 0;
@@ -757,14 +767,13 @@ int gram_device_t(ntk_context* ctx, const ntk_program* prog, const T* x1, int n1
     const FusedPlan& plan = (flags & NTK_FLAG_PER_LAYER) ? prog->per_layer : prog->fused;
     int st = fused_gram<T>(plan, ctx->arena, ctx->stream, &env.launches, &ctx->prof, x1, n1, x2, n2,
                            symmetric, H, W, C, want_ntk, (T*)out.nngp, (T*)out.ntk, out.ld,
-                           (flags & NTK_FLAG_FULL_SQUARE) != 0);
+                           (flags & NTK_FLAG_FULL_SQUARE) != 0, (flags & NTK_FLAG_UPPER_ONLY) != 0);
     ctx->launches += env.launches;
     return st;
   }
 
   // Pool-free networks ending in Flatten: only the diagonal column matters (res_kernels.cuh).
-  if (!(flags & NTK_FLAG_NO_FUSION) && prog->diag.ok && H > 0 && H == W && H <= 32 && !out.cov1 &&
-      !out.cov2) {
+  if (!(flags & NTK_FLAG_NO_FUSION) && diag_supported<T>(prog->diag, H, W) && !out.cov1 && !out.cov2) {
     ctx->arena.reset(ctx->ws, ctx->ws_bytes, false);
     int st = diag_gram<T>(prog->diag, ctx->arena, ctx->stream, &env.launches, x1, n1, x2, n2, symmetric,
                           H, C, want_ntk, (T*)out.nngp, (T*)out.ntk, out.ld,
@@ -807,9 +816,10 @@ int gram_device_t(ntk_context* ctx, const ntk_program* prog, const T* x1, int n1
 
 }  // namespace
 
+// Kernel-in / Kernel-out (requirements.py:935-937).  `host`: `in`/`out` hold HOST pointers (copied through the
+// workspace, the call synchronises); otherwise DEVICE pointers (wrapped without a copy, asynchronous).
 template <typename T>
-static int apply_host_t(ntk_context* ctx, const ntk_program* prog, const ntk_state_t* in,
-                        ntk_state_t* out) {
+static int apply_t(ntk_context* ctx, const ntk_program* prog, const ntk_state_t* in, ntk_state_t* out, bool host) {
   const int t1 = in->n1, t2 = in->n2;
   const long long per_i = per_of(in->H, in->W);
   const long long P = (long long)t1 * t2;
@@ -821,11 +831,20 @@ static int apply_host_t(ntk_context* ctx, const ntk_program* prog, const ntk_sta
   std::vector<TState> slots(prog->n_slots);
   TState& s = slots[0];
   int st = NTK_OK;
-  auto up = [&](const void* host, long long n, Buf** dst) -> int {
-    Buf* b = env.alloc((size_t)n * sizeof(T), &st);
-    if (!b) return st;
-    NTK_CUDA(cudaMemcpyAsync(b->p, host, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-    *dst = b;
+  auto up = [&](const void* src, long long n, Buf** dst) -> int {
+    if (host) {
+      Buf* b = env.alloc((size_t)n * sizeof(T), &st);
+      if (!b) return st;
+      NTK_CUDA(cudaMemcpyAsync(b->p, src, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+      *dst = b;
+    } else {
+      // caller-owned device memory: two references, so in-place layer rules copy first (copy-on-write) and the
+      // arena never sees the pointer
+      env.bufs.emplace_back(new Buf());
+      env.bufs.back()->p = const_cast<void*>(src);
+      env.bufs.back()->refs = 2;
+      *dst = env.bufs.back().get();
+    }
     return NTK_OK;
   };
   NTK_TRY(up(in->nngp, P * per_i, &s.nngp));
@@ -841,9 +860,10 @@ static int apply_host_t(ntk_context* ctx, const ntk_program* prog, const ntk_sta
   TState& f = slots[prog->out_slot];
   if (!f.valid) return fail(NTK_EINVAL, "program left its output slot empty");
   const long long per_o = per_of(f.H, f.W);
-  auto down = [&](void* host, Buf* b, long long n) -> int {
-    if (host && b)
-      NTK_CUDA(cudaMemcpyAsync(host, b->p, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+  auto down = [&](void* dst, Buf* b, long long n) -> int {
+    if (dst && b && dst != b->p)
+      NTK_CUDA(cudaMemcpyAsync(dst, b->p, (size_t)n * sizeof(T),
+                               host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
     return NTK_OK;
   };
   NTK_TRY(down(out->nngp, f.nngp, P * per_o));
@@ -856,11 +876,113 @@ static int apply_host_t(ntk_context* ctx, const ntk_program* prog, const ntk_sta
   out->W = f.W;
   out->ntk_mode = f.ntk_mode;
   out->is_gaussian = f.gaussian ? 1 : 0;
-  NTK_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (host) NTK_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->launches += env.launches;
   return NTK_OK;
 }
 
+// Runs `body` with ctx->stream = `s` (NULL: the context's own stream).  No host synchronisation: workspace reuse
+// between consecutive calls on different streams is ordered with an event the new stream waits on.
+template <typename F>
+static int with_stream(ntk_context* ctx, void* cuda_stream, F body) {
+  NTK_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  if (ctx->order_valid && ctx->last_stream != s) NTK_CUDA(cudaStreamWaitEvent(s, ctx->order_ev, 0));
+  ctx->stream = s;
+  const int st = body();
+  ctx->stream = ctx->own_stream;
+  // even a failed call may have enqueued work that touches the workspace
+  cudaError_t e = cudaEventRecord(ctx->order_ev, s);
+  ctx->last_stream = s;
+  ctx->order_valid = e == cudaSuccess;
+  if (st == NTK_OK && e != cudaSuccess) return fail(NTK_ECUDA, "cudaEventRecord -> %s", cudaGetErrorString(e));
+  return st;
+}
+
+// out[i, j] = slabs[row_of[i], j] (j >= i) or slabs[row_of[j], i] (j < i)
+template <typename T>
+__global__ void k_sym_assemble(const T* __restrict__ slabs, long long ld_s, const int* __restrict__ row_of, int n,
+                               T* __restrict__ out, long long ld_o) {
+  const long long total = (long long)n * n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / n), j = (int)(idx % n);
+    const int a = j >= i ? i : j, b = j >= i ? j : i;
+    out[(long long)i * ld_o + j] = slabs[(long long)row_of[a] * ld_s + b];
+  }
+}
+
+constexpr size_t kPinSlot = (size_t)8 << 20;
+
+static bool is_pinned_host(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+static int ensure_pin(ntk_context* ctx) {
+  if (ctx->pin) return NTK_OK;
+  NTK_CUDA(cudaMallocHost((void**)&ctx->pin, 2 * kPinSlot));
+  for (int k = 0; k < 2; ++k) NTK_CUDA(cudaEventCreateWithFlags(&ctx->pin_ev[k], cudaEventDisableTiming));
+  return NTK_OK;
+}
+
+// Host -> device.  Page-locked sources are DMA'd directly; pageable ones go through the pinned ring in
+// kPinSlot chunks, so the CPU copy of chunk k+1 overlaps the DMA of chunk k.
+static int h2d_staged(ntk_context* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return NTK_OK;
+  if (is_pinned_host(src)) {
+    NTK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return NTK_OK;
+  }
+  NTK_TRY(ensure_pin(ctx));
+  int slot = 0;
+  for (size_t off = 0; off < bytes; off += kPinSlot, slot ^= 1) {
+    const size_t len = std::min(kPinSlot, bytes - off);
+    if (ctx->pin_busy[slot]) NTK_CUDA(cudaEventSynchronize(ctx->pin_ev[slot]));
+    memcpy(ctx->pin + slot * kPinSlot, (const char*)src + off, len);
+    NTK_CUDA(cudaMemcpyAsync((char*)dst + off, ctx->pin + slot * kPinSlot, len, cudaMemcpyHostToDevice, ctx->stream));
+    NTK_CUDA(cudaEventRecord(ctx->pin_ev[slot], ctx->stream));
+    ctx->pin_busy[slot] = true;
+  }
+  return NTK_OK;
+}
+
+// Device -> host, same scheme (two chunks in flight).  Returns with the data in `dst` for pageable destinations;
+// for page-locked ones the copy is only enqueued (the caller synchronises the stream).
+static int d2h_staged(ntk_context* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return NTK_OK;
+  if (is_pinned_host(dst)) {
+    NTK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return NTK_OK;
+  }
+  NTK_TRY(ensure_pin(ctx));
+  for (int k = 0; k < 2; ++k)
+    if (ctx->pin_busy[k]) {
+      NTK_CUDA(cudaEventSynchronize(ctx->pin_ev[k]));
+      ctx->pin_busy[k] = false;
+    }
+  const size_t n_chunks = (bytes + kPinSlot - 1) / kPinSlot;
+  auto issue = [&](size_t k) -> int {
+    const size_t off = k * kPinSlot, len = std::min(kPinSlot, bytes - off);
+    NTK_CUDA(cudaMemcpyAsync(ctx->pin + (k & 1) * kPinSlot, (const char*)src + off, len, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    NTK_CUDA(cudaEventRecord(ctx->pin_ev[k & 1], ctx->stream));
+    return NTK_OK;
+  };
+  NTK_TRY(issue(0));
+  if (n_chunks > 1) NTK_TRY(issue(1));
+  for (size_t k = 0; k < n_chunks; ++k) {
+    const size_t off = k * kPinSlot, len = std::min(kPinSlot, bytes - off);
+    NTK_CUDA(cudaEventSynchronize(ctx->pin_ev[k & 1]));
+    memcpy((char*)dst + off, ctx->pin + (k & 1) * kPinSlot, len);
+    if (k + 2 < n_chunks) NTK_TRY(issue(k + 2));
+  }
+  return NTK_OK;
+}
 
 // =================================== C ABI ===================================
 extern "C" {
@@ -968,7 +1090,7 @@ int ntk_program_path(const ntk_program_t* prog, int32_t dtype, int32_t H, int32_
     *path = NTK_PATH_FCN;
   } else if (prog->fused.ok && H > 0 && fused_supported<float>(prog->fused, H, W, C)) {
     *path = NTK_PATH_FUSED;
-  } else if (prog->diag.ok && H > 0 && H == W && H <= 32) {
+  } else if (dtype == NTK_F32 ? diag_supported<float>(prog->diag, H, W) : diag_supported<double>(prog->diag, H, W)) {
     *path = NTK_PATH_DIAG;
   } else if (prog->res.ok && H > 0 && res_supported<float>(prog->res, H, W, C)) {
     *path = NTK_PATH_RES;
@@ -987,7 +1109,9 @@ int ntk_context_create(int32_t device, size_t workspace_bytes, ntk_context_t** o
   NTK_CUDA(cudaSetDevice(device));
   std::unique_ptr<ntk_context> c(new ntk_context());
   c->device = device;
-  NTK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  NTK_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  NTK_CUDA(cudaEventCreateWithFlags(&c->order_ev, cudaEventDisableTiming));
   if (workspace_bytes == 0) {
     size_t free_b = 0, total_b = 0;
     NTK_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -1008,11 +1132,16 @@ int ntk_context_create(int32_t device, size_t workspace_bytes, ntk_context_t** o
 void ntk_context_destroy(ntk_context_t* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->own_stream);
+  if (ctx->order_valid) cudaEventSynchronize(ctx->order_ev);
   for (int k = 0; k < 6; ++k)
     if (ctx->io[k]) cudaFree(ctx->io[k]);
   if (ctx->ws) cudaFree(ctx->ws);
-  cudaStreamDestroy(ctx->stream);
+  if (ctx->pin) cudaFreeHost(ctx->pin);
+  for (int k = 0; k < 2; ++k)
+    if (ctx->pin_ev[k]) cudaEventDestroy(ctx->pin_ev[k]);
+  if (ctx->order_ev) cudaEventDestroy(ctx->order_ev);
+  cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
 
@@ -1070,23 +1199,30 @@ void* ntk_context_stream(ntk_context_t* ctx) { return ctx ? (void*)ctx->stream :
 
 int64_t ntk_context_launch_count(const ntk_context_t* ctx) { return ctx ? ctx->launches : 0; }
 
-int ntk_gram_device(ntk_context_t* ctx, const ntk_program_t* prog, int32_t dtype, const void* x1,
-                    int32_t n1, const void* x2, int32_t n2, int32_t H, int32_t W, int32_t C,
-                    uint32_t flags, void* nngp, void* ntk, int64_t ld, void* cov1, void* cov2) {
+int ntk_gram_device_on_stream(ntk_context_t* ctx, const ntk_program_t* prog, int32_t dtype, const void* x1,
+                              int32_t n1, const void* x2, int32_t n2, int32_t H, int32_t W, int32_t C,
+                              uint32_t flags, void* nngp, void* ntk, int64_t ld, void* cov1, void* cov2,
+                              void* cuda_stream) {
   if (!ctx || !prog || !x1 || n1 <= 0 || C <= 0 || (x2 && n2 <= 0))
     return fail(NTK_EINVAL, "bad arguments");
   if ((H > 0) != (W > 0) || H < 0) return fail(NTK_EINVAL, "bad spatial shape");
   if ((flags & NTK_FLAG_NTK) && !ntk) return fail(NTK_EINVAL, "NTK requested but ntk is NULL");
+  if (dtype != NTK_F32 && dtype != NTK_F64) return fail(NTK_EINVAL, "unknown dtype %d", dtype);
   OutPtrs o{nngp, (flags & NTK_FLAG_NTK) ? ntk : nullptr,
             (flags & NTK_FLAG_WANT_COV) ? cov1 : nullptr,
             (flags & NTK_FLAG_WANT_COV) ? cov2 : nullptr, ld};
-  if (dtype == NTK_F32)
-    return gram_device_t<float>(ctx, prog, (const float*)x1, n1, (const float*)x2, n2, H, W, C,
-                                flags, o);
-  if (dtype == NTK_F64)
-    return gram_device_t<double>(ctx, prog, (const double*)x1, n1, (const double*)x2, n2, H, W, C,
-                                 flags, o);
-  return fail(NTK_EINVAL, "unknown dtype %d", dtype);
+  return with_stream(ctx, cuda_stream, [&]() -> int {
+    if (dtype == NTK_F32)
+      return gram_device_t<float>(ctx, prog, (const float*)x1, n1, (const float*)x2, n2, H, W, C, flags, o);
+    return gram_device_t<double>(ctx, prog, (const double*)x1, n1, (const double*)x2, n2, H, W, C, flags, o);
+  });
+}
+
+int ntk_gram_device(ntk_context_t* ctx, const ntk_program_t* prog, int32_t dtype, const void* x1,
+                    int32_t n1, const void* x2, int32_t n2, int32_t H, int32_t W, int32_t C,
+                    uint32_t flags, void* nngp, void* ntk, int64_t ld, void* cov1, void* cov2) {
+  return ntk_gram_device_on_stream(ctx, prog, dtype, x1, n1, x2, n2, H, W, C, flags, nngp, ntk, ld, cov1, cov2,
+                                   nullptr);
 }
 
 int ntk_gram_host(ntk_context_t* ctx, const ntk_program_t* prog, int32_t dtype, const void* x1,
@@ -1112,15 +1248,18 @@ int ntk_gram_host(ntk_context_t* ctx, const ntk_program_t* prog, int32_t dtype, 
     NTK_TRY(ensure_io(ctx, 4, (size_t)n1 * per * sz));
     if (x2) NTK_TRY(ensure_io(ctx, 5, (size_t)n2 * per * sz));
   }
-  NTK_CUDA(cudaMemcpyAsync(ctx->io[0], x1, (size_t)n1 * row * sz, cudaMemcpyHostToDevice, ctx->stream));
-  if (x2)
-    NTK_CUDA(cudaMemcpyAsync(ctx->io[1], x2, (size_t)n2 * row * sz, cudaMemcpyHostToDevice, ctx->stream));
+  if (ctx->order_valid && ctx->last_stream != ctx->own_stream) {
+    NTK_CUDA(cudaStreamWaitEvent(ctx->own_stream, ctx->order_ev, 0));
+    ctx->last_stream = ctx->own_stream;
+  }
+  NTK_TRY(h2d_staged(ctx, ctx->io[0], x1, (size_t)n1 * row * sz));
+  if (x2) NTK_TRY(h2d_staged(ctx, ctx->io[1], x2, (size_t)n2 * row * sz));
   NTK_TRY(ntk_gram_device(ctx, prog, dtype, ctx->io[0], n1, x2 ? ctx->io[1] : nullptr, n2, H, W, C,
                           flags, ctx->io[2], want_ntk ? ctx->io[3] : nullptr, (int64_t)ldd,
                           want_cov ? ctx->io[4] : nullptr, (want_cov && x2) ? ctx->io[5] : nullptr));
   auto d2h = [&](void* dst, const void* src) -> int {
     if (oh > 0 || (size_t)ld == ldd) {
-      NTK_CUDA(cudaMemcpyAsync(dst, src, (size_t)n1 * ldd * per * sz, cudaMemcpyDeviceToHost, ctx->stream));
+      NTK_TRY(d2h_staged(ctx, dst, src, (size_t)n1 * ldd * per * sz));
     } else {
       NTK_CUDA(cudaMemcpy2DAsync(dst, (size_t)ld * sz, src, ldd * sz, (size_t)m2 * sz, (size_t)n1,
                                  cudaMemcpyDeviceToHost, ctx->stream));
@@ -1141,10 +1280,37 @@ int ntk_apply_host(ntk_context_t* ctx, const ntk_program_t* prog, int32_t dtype,
                    const ntk_state_t* in, ntk_state_t* out) {
   if (!ctx || !prog || !in || !out || !in->nngp || !in->cov1 || in->n1 <= 0 || in->n2 <= 0)
     return fail(NTK_EINVAL, "bad arguments");
-  NTK_CUDA(cudaSetDevice(ctx->device));
-  if (dtype == NTK_F32) return apply_host_t<float>(ctx, prog, in, out);
-  if (dtype == NTK_F64) return apply_host_t<double>(ctx, prog, in, out);
-  return fail(NTK_EINVAL, "unknown dtype %d", dtype);
+  if (dtype != NTK_F32 && dtype != NTK_F64) return fail(NTK_EINVAL, "unknown dtype %d", dtype);
+  return with_stream(ctx, nullptr, [&]() -> int {
+    return dtype == NTK_F32 ? apply_t<float>(ctx, prog, in, out, true) : apply_t<double>(ctx, prog, in, out, true);
+  });
+}
+
+int ntk_apply_device(ntk_context_t* ctx, const ntk_program_t* prog, int32_t dtype, const ntk_state_t* in,
+                     ntk_state_t* out, void* cuda_stream) {
+  if (!ctx || !prog || !in || !out || !in->nngp || !in->cov1 || in->n1 <= 0 || in->n2 <= 0)
+    return fail(NTK_EINVAL, "bad arguments");
+  if (dtype != NTK_F32 && dtype != NTK_F64) return fail(NTK_EINVAL, "unknown dtype %d", dtype);
+  return with_stream(ctx, cuda_stream, [&]() -> int {
+    return dtype == NTK_F32 ? apply_t<float>(ctx, prog, in, out, false) : apply_t<double>(ctx, prog, in, out, false);
+  });
+}
+
+int ntk_sym_assemble(ntk_context_t* ctx, int32_t dtype, const void* slabs, int64_t ld_slabs,
+                     const int32_t* row_of, int32_t n, void* out, int64_t ld_out) {
+  if (!ctx || !slabs || !row_of || !out || n <= 0) return fail(NTK_EINVAL, "bad arguments");
+  if (dtype != NTK_F32 && dtype != NTK_F64) return fail(NTK_EINVAL, "unknown dtype %d", dtype);
+  return with_stream(ctx, nullptr, [&]() -> int {
+    ctx->launches++;
+    if (dtype == NTK_F32)
+      k_sym_assemble<float><<<grid_for((long long)n * n), kThreads, 0, ctx->stream>>>(
+          (const float*)slabs, ld_slabs, row_of, n, (float*)out, ld_out);
+    else
+      k_sym_assemble<double><<<grid_for((long long)n * n), kThreads, 0, ctx->stream>>>(
+          (const double*)slabs, ld_slabs, row_of, n, (double*)out, ld_out);
+    NTK_CUDA(cudaGetLastError());
+    return NTK_OK;
+  });
 }
 
 int ntk_workspace_bytes(const ntk_program_t* prog, int32_t dtype, int32_t t1, int32_t t2, int32_t H,
@@ -1182,6 +1348,78 @@ int ntk_memcpy_d2h(ntk_context_t* ctx, void* dst_host, const void* src_dev, size
   NTK_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   NTK_CUDA(cudaStreamSynchronize(ctx->stream));
   return NTK_OK;
+}
+
+int ntk_memset_async(ntk_context_t* ctx, void* dst_dev, int32_t value, size_t bytes) {
+  if (!ctx) return fail(NTK_EINVAL, "ctx is NULL");
+  NTK_CUDA(cudaSetDevice(ctx->device));
+  NTK_CUDA(cudaMemsetAsync(dst_dev, value, bytes, ctx->stream));
+  return NTK_OK;
+}
+
+int ntk_context_device(const ntk_context_t* ctx) { return ctx ? ctx->device : -1; }
+
+int ntk_host_alloc(size_t bytes, void** ptr) {
+  if (!ptr) return fail(NTK_EINVAL, "ptr is NULL");
+  NTK_CUDA(cudaMallocHost(ptr, bytes));
+  return NTK_OK;
+}
+
+int ntk_host_free(void* ptr) {
+  NTK_CUDA(cudaFreeHost(ptr));
+  return NTK_OK;
+}
+
+int ntk_event_create(void** event) {
+  if (!event) return fail(NTK_EINVAL, "event is NULL");
+  cudaEvent_t e;
+  NTK_CUDA(cudaEventCreate(&e));
+  *event = (void*)e;
+  return NTK_OK;
+}
+
+int ntk_event_record(ntk_context_t* ctx, void* event) {
+  if (!ctx || !event) return fail(NTK_EINVAL, "bad arguments");
+  NTK_CUDA(cudaSetDevice(ctx->device));
+  NTK_CUDA(cudaEventRecord((cudaEvent_t)event, ctx->stream));
+  return NTK_OK;
+}
+
+int ntk_event_elapsed_ms(void* start, void* stop, float* ms) {
+  if (!start || !stop || !ms) return fail(NTK_EINVAL, "bad arguments");
+  NTK_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
+  NTK_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+  return NTK_OK;
+}
+
+void ntk_event_destroy(void* event) {
+  if (event) cudaEventDestroy((cudaEvent_t)event);
+}
+
+int ntk_stream_create(int32_t device, void** cuda_stream) {
+  if (!cuda_stream) return fail(NTK_EINVAL, "cuda_stream is NULL");
+  NTK_CUDA(cudaSetDevice(device));
+  cudaStream_t s;
+  NTK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *cuda_stream = (void*)s;
+  return NTK_OK;
+}
+
+int ntk_stream_synchronize(void* cuda_stream) {
+  NTK_CUDA(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+  return NTK_OK;
+}
+
+int ntk_stream_query(void* cuda_stream, int32_t* done) {
+  if (!done) return fail(NTK_EINVAL, "done is NULL");
+  cudaError_t e = cudaStreamQuery((cudaStream_t)cuda_stream);
+  if (e != cudaSuccess && e != cudaErrorNotReady) NTK_CUDA(e);
+  *done = e == cudaSuccess ? 1 : 0;
+  return NTK_OK;
+}
+
+void ntk_stream_destroy(void* cuda_stream) {
+  if (cuda_stream) cudaStreamDestroy((cudaStream_t)cuda_stream);
 }
 
 }  // extern "C"

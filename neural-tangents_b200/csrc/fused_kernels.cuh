@@ -1004,11 +1004,7 @@ int launch_stage_impl(cudaStream_t stream, int64_t* launches, const StageArgs<T>
   using G = StageGeom<S, WPT, SH>;
   auto kern = k_stage<T, S, WPT, L, IN, EPI, NTK, CIN, SH, RC, ERF>;
   const size_t smem = stage_smem_bytes<T, S, WPT, L, IN, EPI, NTK, CIN, SH>();
-  static thread_local bool configured = false;
-  if (!configured) {
-    NTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  NTK_TRY(ensure_dynamic_smem((const void*)kern, smem));
   long long blocks = (a.P + G::GROUPS - 1) / G::GROUPS;
   if (SH > 1) blocks = (a.P / a.n2) * ((a.n2 + SH - 1) / SH);
   (*launches)++;
@@ -1192,8 +1188,11 @@ template <typename T>
 int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t* launches,
                StageProfile* prof, const T* x1, int n1, const T* x2, int n2, bool symmetric, int S0,
                int /*W*/, int C, bool want_ntk, T* out_nngp, T* out_ntk, long long ld,
-               bool full_square = false) {
-  const bool triangular = symmetric && !full_square && n1 == n2 && n1 > 1;
+               bool full_square = false, bool upper = false) {
+  // `upper` (NTK_FLAG_UPPER_ONLY): x1 holds the same samples as x2[0:n1]; only entries (i, j >= i) are wanted.
+  upper = upper && !symmetric && n2 >= n1;
+  const bool triangular = (symmetric && !full_square && n1 == n2 && n1 > 1) || upper;
+  const bool share_q = symmetric || upper;  // the q-maps of x1 are (a prefix of) those of x2
   const size_t n_st = plan.stages.size() - 1;  // real stages (last entry is the tail marker)
   // ---- 1. q-maps for every stage and both sample sets (self-pair pipeline) --------------
   // qm[s][set]: [n][L][S][S][2]
@@ -1208,8 +1207,8 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
   }
   for (size_t s = 0; s < n_st; ++s) {
     const size_t per = (size_t)plan.stages[s].L * Ss[s] * Ss[s] * 2 * sizeof(T);
-    qm1[s] = (T*)arena.alloc(per * n1);
-    qm2[s] = symmetric ? qm1[s] : (T*)arena.alloc(per * n2);
+    qm2[s] = (T*)arena.alloc(per * n2);
+    qm1[s] = share_q ? qm2[s] : (T*)arena.alloc(per * n1);
     if (!qm1[s] || !qm2[s]) return fail(NTK_ENOMEM, "workspace too small for the q-maps");
   }
   const double alpha0 = plan.stages[0].w2[0] / 9.0;
@@ -1222,7 +1221,7 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
     k_in[s] = plan.stages[s].epi == EPI_POOL ? 2 * k_out + 1 : k_out;
     k_out = k_in[s];
   }
-  for (int set = 0; set < (symmetric ? 1 : 2); ++set) {
+  for (int set = share_q ? 1 : 0; set < 2; ++set) {
     const T* x = set == 0 ? x1 : x2;
     const int n = set == 0 ? n1 : n2;
     // self tensors are processed in chunks to bound the workspace
@@ -1428,7 +1427,7 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
       if (tri_tile) break;  // one triangular tile covers all columns of this row block
     }
   }
-  if (triangular) {
+  if (triangular && !upper) {
     (*launches)++;
     k_mirror<T><<<grid_for((long long)n1 * n1), kThreads, 0, stream>>>(out_nngp, n1, ld);
     NTK_CUDA(cudaGetLastError());

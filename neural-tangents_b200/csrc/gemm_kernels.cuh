@@ -393,11 +393,7 @@ inline int launch_gram_tc_pipe(cudaStream_t stream, const float* a_hi, const flo
                                const float* b_hi, const float* b_lo, int n2, int d, float* out, long long ld_out) {
   dim3 grid((n2 + kGemmBN - 1) / kGemmBN, (n1 + kGemmBM - 1) / kGemmBM);
   constexpr size_t smem = (size_t)kGemmStages * 4 * kGemmBM * kGemmBK * sizeof(float);  // 192 KB
-  static thread_local bool configured = false;
-  if (!configured) {
-    NTK_CUDA(cudaFuncSetAttribute(k_gram_tf32x3_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  NTK_TRY(ensure_dynamic_smem((const void*)k_gram_tf32x3_pipe, smem));
   k_gram_tf32x3_pipe<<<grid, 128, smem, stream>>>(a_hi, a_lo, b_hi, b_lo, out, n1, n2, gram_pad_k(d), ld_out,
                                                   (float)(1.0 / (double)d));
   NTK_CUDA(cudaGetLastError());
@@ -458,11 +454,7 @@ inline int launch_gram_tc(cudaStream_t stream, const float* x1, int n1, const fl
                           float* out) {
   dim3 grid((n2 + kGemmBN - 1) / kGemmBN, (n1 + kGemmBM - 1) / kGemmBM);
   constexpr size_t smem = 2 * (kGemmBM + kGemmBN) * kGemmBK * sizeof(float);  // 64 KB
-  static thread_local bool configured = false;
-  if (!configured) {
-    NTK_CUDA(cudaFuncSetAttribute(k_gram_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  NTK_TRY(ensure_dynamic_smem((const void*)k_gram_tf32x3, smem));
   k_gram_tf32x3<<<grid, 128, smem, stream>>>(x1, x2, out, n1, n2, d, (float)(1.0 / (double)d));
   NTK_CUDA(cudaGetLastError());
   return NTK_OK;

@@ -16,7 +16,7 @@
 
 #define NTK_FUSED_INSTANCES(KW, T)                                                                        \
   KW template int fused_gram<T>(const FusedPlan&, Arena&, cudaStream_t, int64_t*, StageProfile*, const T*, \
-                                int, const T*, int, bool, int, int, int, bool, T*, T*, long long, bool);   \
+                                int, const T*, int, bool, int, int, int, bool, T*, T*, long long, bool, bool); \
   KW template int fused_configure_device<T, false>();
 
 // launch_res<T, NTK, ERF = true> (the Erf-capable residual kernels) lives in res_*_erf.cu

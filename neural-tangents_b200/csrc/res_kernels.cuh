@@ -449,6 +449,9 @@ k_res(const ResArgs<T> a) {
 // recording (q, 1/sqrt q) in front of every activation.  One CTA per sample.
 // ---------------------------------------------------------------------------------------
 enum { Q_CONV = 0, Q_ACT = 1, Q_COPY = 2, Q_ADD = 3, Q_INPUT = 4 };
+// A 3x3 / stride-2 / SAME conv on a size-S axis (lax.padtype_to_pads): out = ceil(S/2), total padding
+// (out-1)*2 + 3 - S = 1 (S even: lo = 0, window centred at 2a+1) or 2 (S odd: lo = 1, centred at 2a).
+__host__ __device__ __forceinline__ int strided_center_offset(int S) { return (S & 1) ? 0 : 1; }
 struct QOp {
   int kind;
   int dst, src;  // image buffers 0..2
@@ -513,11 +516,12 @@ __global__ void k_qprog(const T* __restrict__ x, int S0, int C, T in_scale, cons
       }
       __syncthreads();
       const int st = prog.stride[op];
-      const int So = S / st;
+      const int So = (S + st - 1) / st;           // SAME: ceil(S / stride)
+      const int o2 = strided_center_offset(S);    // window centre of a stride-2 conv: 2a+1 (S even), 2a (S odd)
       T* D = img + d * S0 * S0;
       for (int e = threadIdx.x; e < So * So; e += blockDim.x) {
         const int a_ = e / So, b_ = e % So;
-        const int h = st == 2 ? 2 * a_ + 1 : a_, w = st == 2 ? 2 * b_ + 1 : b_;
+        const int h = st == 2 ? 2 * a_ + o2 : a_, w = st == 2 ? 2 * b_ + o2 : b_;
         const T vU = h > 0 ? (T)1 : (T)0, vD = h < S - 1 ? (T)1 : (T)0;
         const T box = fma_t(vD, scratch[(h < S - 1 ? h + 1 : h) * S + w],
                             fma_t(vU, scratch[(h > 0 ? h - 1 : h) * S + w], scratch[h * S + w]));
@@ -680,17 +684,7 @@ template <typename T, bool NTK, bool ERF>
 int launch_res(cudaStream_t stream, int64_t* launches, int S, bool from_x, const ResArgs<T>& a) {
   (*launches)++;
   auto go = [&](auto kern, int nt, int groups, size_t smem) -> int {
-    static thread_local const void* configured[16] = {nullptr};
-    bool done = false;
-    for (auto c : configured) done = done || c == (const void*)kern;
-    if (!done) {
-      NTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      for (auto& c : configured)
-        if (!c) {
-          c = (const void*)kern;
-          break;
-        }
-    }
+    NTK_TRY(ensure_dynamic_smem((const void*)kern, smem));
     const long long blocks = (a.P + groups - 1) / groups;
     kern<<<(unsigned)blocks, nt, smem, stream>>>(a);
     NTK_CUDA(cudaGetLastError());
@@ -1077,10 +1071,11 @@ k_diagnet(const T* __restrict__ x1, const T* __restrict__ x2, int S0, int C, T i
         }
         __syncthreads();
         const int st = prog.stride[op];
-        const int So = S / st;
+        const int So = (S + st - 1) / st;
+        const int o2 = strided_center_offset(S);
         for (int e = threadIdx.x; e < So * So; e += blockDim.x) {
           const int a_ = e / So, b_ = e % So;
-          const int h = st == 2 ? 2 * a_ + 1 : a_, w = st == 2 ? 2 * b_ + 1 : b_;
+          const int h = st == 2 ? 2 * a_ + o2 : a_, w = st == 2 ? 2 * b_ + o2 : b_;
           const T vU = h > 0 ? (T)1 : (T)0, vD = h < S - 1 ? (T)1 : (T)0;
           const int eu = (h > 0 ? h - 1 : h) * S + w, ed = (h < S - 1 ? h + 1 : h) * S + w;
           const T k = fma_t(fma_t(vD, scK[ed], fma_t(vU, scK[eu], scK[h * S + w])), prog.alpha[op],
@@ -1253,6 +1248,12 @@ inline DiagPlan plan_diag(const std::vector<ntk_op_t>& ops, const std::vector<in
   return plan;
 }
 
+// The diagonal-column kernels keep 8 (k_diagnet) / 4 (k_qprog) S0 x S0 images in shared memory.
+template <typename T>
+bool diag_supported(const DiagPlan& plan, int H, int W) {
+  return plan.ok && H > 0 && H == W && (size_t)8 * H * H * sizeof(T) <= (size_t)200 * 1024;
+}
+
 template <typename T>
 int diag_gram(const DiagPlan& plan, Arena& arena, cudaStream_t stream, int64_t* launches, const T* x1,
               int n1, const T* x2, int n2, bool symmetric, int S0, int C, bool want_ntk, T* out_nngp,
@@ -1277,7 +1278,7 @@ int diag_gram(const DiagPlan& plan, Arena& arena, cudaStream_t stream, int64_t* 
       qp.akind[i] = ACT_ABRELU;
       qp.e_in[i] = qp.eA[i] = qp.eT[i] = qp.eC[i] = (T)0;
       if (o.kind == Q_CONV) {
-        Sb[o.dst] = Sb[o.src] / o.stride;
+        Sb[o.dst] = (Sb[o.src] + o.stride - 1) / o.stride;  // SAME: ceil
         if (Sb[o.dst] < 1) return fail(NTK_EINVAL, "Conv output would be empty");
       } else if (o.kind == Q_COPY) {
         Sb[o.dst] = Sb[o.src];
@@ -1312,6 +1313,7 @@ int diag_gram(const DiagPlan& plan, Arena& arena, cudaStream_t stream, int64_t* 
   NTK_CUDA(cudaMemcpyAsync(off_d, act_off.data(), act_off.size() * sizeof(long long), cudaMemcpyHostToDevice, stream));
   NTK_CUDA(cudaStreamSynchronize(stream));
   const T in_scale = (T)(1.0 / (double)C);
+  NTK_TRY(ensure_dynamic_smem((const void*)k_qprog<T>, (size_t)4 * S0 * S0 * sizeof(T)));
   for (int set = 0; set < (symmetric ? 1 : 2); ++set) {
     (*launches)++;
     k_qprog<T><<<set == 0 ? n1 : n2, 256, (size_t)4 * S0 * S0 * sizeof(T), stream>>>(
@@ -1323,19 +1325,11 @@ int diag_gram(const DiagPlan& plan, Arena& arena, cudaStream_t stream, int64_t* 
   const int grid = (int)std::min<long long>(P, (long long)kNumSMs * 32);
   (*launches)++;
   if (want_ntk) {
-    static thread_local bool cfg = false;
-    if (!cfg) {
-      NTK_CUDA(cudaFuncSetAttribute(k_diagnet<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * 32 * 8));
-      cfg = true;
-    }
+    NTK_TRY(ensure_dynamic_smem((const void*)k_diagnet<T, true>, smem));
     k_diagnet<T, true><<<grid, 128, smem, stream>>>(x1, x2, S0, C, in_scale, qp_d, qm_stride, off_d, qm1, qm2,
                                                    P, n2, triangular ? 1 : 0, resK, resT);
   } else {
-    static thread_local bool cfg = false;
-    if (!cfg) {
-      NTK_CUDA(cudaFuncSetAttribute(k_diagnet<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * 32 * 8));
-      cfg = true;
-    }
+    NTK_TRY(ensure_dynamic_smem((const void*)k_diagnet<T, false>, smem));
     k_diagnet<T, false><<<grid, 128, smem, stream>>>(x1, x2, S0, C, in_scale, qp_d, qm_stride, off_d, qm1, qm2,
                                                     P, n2, triangular ? 1 : 0, resK, resT);
   }

@@ -33,11 +33,7 @@ int launch_p_impl(cudaStream_t stream, int64_t* launches, const StageArgs<float>
   using G = PGeom<S>;
   auto kern = k_stage_p<S, L, IN, EPI, NTK, CIN, RC, LAG, MINB, Q2P, NTK_PACKED_ERF != 0, VAR>;
   const size_t smem = stage_p_smem_bytes<S, L, IN, EPI, NTK, CIN, Q2P>();
-  static thread_local bool configured = false;
-  if (!configured) {
-    NTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  NTK_TRY(ensure_dynamic_smem((const void*)kern, smem));
   const long long blocks = (a.P + G::GROUPS - 1) / G::GROUPS;
   (*launches)++;
   kern<<<(unsigned)blocks, G::NT, smem, stream>>>(a);

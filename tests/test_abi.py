@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(lib):
   for name in declared:
     assert hasattr(cdll, name), f'{name} declared in include/ntk_b200.h but not exported'
   assert set(declared) == set(lib.EXPORTED_SYMBOLS)
-  assert cdll.ntk_abi_version() == 1
+  assert cdll.ntk_abi_version() == 2
 
 
 def test_struct_layout_matches_header(lib):
@@ -172,3 +172,41 @@ def test_kernel_family_selection_without_gpu(lib):
   assert path(cases.myrtle(10), 32, 32, 3, flags=lib.FLAG_NO_FUSION) == 'generic'
   assert path(cases.myrtle(10), 32, 32, 3, flags=lib.FLAG_WANT_COV) == 'generic'
   assert path(cases.CASES['wrn_relu'][0], 8, 8, 3) == 'generic'                 # 8x8 with a stride-2 block: 4x4 maps
+
+
+def test_comm_entry_points_without_gpu(lib):
+  """libnccl is resolved with dlopen on first use (no link-time dependency); without a GPU the communicator
+  cannot be created, but the version query and argument checks work."""
+  cdll = lib.load()
+  v = ctypes.c_int()
+  rc = cdll.ntk_comm_nccl_version(ctypes.byref(v))
+  if rc == 0:
+    assert v.value >= 21800
+  else:
+    assert rc == lib.E_UNSUPPORTED and b'NCCL' in cdll.ntk_last_error()
+  out = ctypes.c_void_p()
+  assert cdll.ntk_comm_create(None, None, 0, 1, ctypes.byref(out)) == lib.E_INVAL
+  assert cdll.ntk_comm_rank(None) == -1 and cdll.ntk_comm_world(None) == -1
+  assert cdll.ntk_context_device(None) == -1
+  assert cdll.ntk_gram_device_on_stream(None, None, 0, None, 1, None, 1, 0, 0, 1, 0, None, None, 1, None, None,
+                                        None) == lib.E_INVAL
+  assert cdll.ntk_apply_device(None, None, 0, None, None, None) == lib.E_INVAL
+  assert cdll.ntk_sym_assemble(None, 0, None, 0, None, 0, None, 0) == lib.E_INVAL
+  # pinned allocations fall back to pageable NumPy memory when there is no CUDA device
+  a = lib.pinned_empty((512, 512), np.float32)
+  assert a.shape == (512, 512) and a.flags['C_CONTIGUOUS'] and a.flags['WRITEABLE']
+
+
+def test_diag_path_selection_covers_odd_sizes(lib):
+  """Pool-free Flatten nets take the diagonal-column path at any square size whose images fit shared memory
+  (odd sizes included: SAME stride-2 geometry is handled in the kernels), else the per-op path."""
+  import cases
+  from neural_tangents_b200 import stax
+  spec = ('serial', [cases.conv(), cases.RELU, cases.conv(s=(2, 2)), cases.RELU, ('flatten',), ('dense', 1., 0.)])
+  _, _, kf = cases.build(spec, stax)
+  low = stax._lowered(stax._strip(kf._spec), False, False, True)
+  for size in (7, 15, 28, 32, 64):
+    assert low.program.path(size, size, 1) == 'diag'
+  assert low.program.path(64, 64, 1, x64=True) == 'generic'     # 8 x 64 x 64 doubles do not fit
+  assert low.program.path(96, 96, 1) == 'generic'
+  assert low.program.path(28, 14, 1) == 'generic'

@@ -1,0 +1,315 @@
+"""GPU tests of the round-2 boundary: the NCCL communicator inside libntk_b200.so and the torch-free
+`distributed.gram` (contiguous rows for x2 given, folded-cyclic triangular schedule for x2=None), the
+NTK_FLAG_UPPER_ONLY trapezoid, the caller-stream entry, device-side Kernel-in/Kernel-out, pinned host
+memory, and the diagonal-column path at odd sizes.  World-size-2 cases need two GPUs and skip otherwise."""
+import ctypes
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RTOL = {False: 1e-4, True: 1e-10}
+RTOL_DUP = {False: 2e-3, True: 2e-7}
+
+
+@pytest.fixture(scope='module')
+def nt():
+  import __graft_entry__ as g
+  g.build()
+  import neural_tangents_b200 as nt
+  yield nt
+  nt.config.update('enable_x64', False)
+  nt.config.update('disable_fusion', False)
+
+
+def _check_sym(v, ref, x64):
+  off = ~np.eye(v.shape[0], dtype=bool)
+  np.testing.assert_allclose(v[off], ref[off], rtol=RTOL[x64])
+  np.testing.assert_allclose(np.diag(v), np.diag(ref), rtol=RTOL_DUP[x64])
+  np.testing.assert_array_equal(v, v.T)
+
+
+def test_distributed_gram_world1_nccl(nt):
+  """The product multi-GPU path on a 1-rank NCCL communicator: device broadcast, per-block
+  `ntk_gram_device`, all-gather, `ntk_sym_assemble`, all through the C-ABI, against the oracle."""
+  from neural_tangents_b200 import _lib, distributed as D
+  from oracle import ntk_oracle as O
+  assert _lib.Comm.nccl_version() >= 21800
+  spec = cases.myrtle(5)
+  _, _, kernel_fn = cases.build(spec, nt.stax)
+  x1 = np.random.default_rng(3).standard_normal((7, 32, 32, 3)).astype(np.float32)
+  x2 = np.random.default_rng(4).standard_normal((5, 32, 32, 3)).astype(np.float32)
+  be = D.init(rank=0, world=1, local_rank=0, unique_id=_lib.Comm.unique_id())
+  try:
+    ref = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'))
+    sref = O.kernel_fn(spec, x1, None, ('nngp', 'ntk'))
+    for x64 in (False, True):
+      nt.config.update('enable_x64', x64)
+      out = D.gram(kernel_fn, x1, x2, ('nngp', 'ntk'))
+      np.testing.assert_allclose(out.nngp, ref[0], rtol=RTOL[x64])
+      np.testing.assert_allclose(out.ntk, ref[1], rtol=RTOL[x64])
+      for block in (None, 3):                       # one trapezoid / ragged trapezoids 3 + 3 + 1
+        sym = D.gram(kernel_fn, x1, None, ('nngp', 'ntk'), block_rows=block)
+        _check_sym(sym.nngp, sref[0], x64)
+        _check_sym(sym.ntk, sref[1], x64)
+      only = D.gram(kernel_fn, x1, x2, 'ntk')
+      np.testing.assert_allclose(only, ref[1], rtol=RTOL[x64])
+      dev = D.gram(kernel_fn, x1, x2, 'nngp', to_host=False)       # stays in HBM
+      assert isinstance(dev, D.DeviceArray) and dev.shape == (7, 5)
+      np.testing.assert_allclose(be.download(dev), ref[0], rtol=RTOL[x64])
+  finally:
+    nt.config.update('enable_x64', False)
+    D.shutdown()
+
+
+_WORLD2 = textwrap.dedent('''
+    import os, sys
+    import numpy as np
+    sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests', 'golden'))
+    import neural_tangents_b200 as nt
+    from neural_tangents_b200 import distributed as D
+    from oracle import ntk_oracle as O
+    import cases
+    rank = int(os.environ['RANK'])
+    be = D.init()
+    assert be.world == 2 and be.ctx.device == rank
+    spec = cases.myrtle(5)
+    _, _, kernel_fn = cases.build(spec, nt.stax)
+    x1 = np.random.default_rng(3).standard_normal((8, 32, 32, 3)).astype(np.float32)
+    x2 = np.random.default_rng(4).standard_normal((5, 32, 32, 3)).astype(np.float32)
+    ref = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'))
+    sref = O.kernel_fn(spec, x1, None, ('nngp', 'ntk'))
+    out = D.gram(kernel_fn, x1 if rank == 0 else None, x2 if rank == 0 else None, ('nngp', 'ntk'))
+    np.testing.assert_allclose(out.nngp, ref[0], rtol=1e-4)
+    np.testing.assert_allclose(out.ntk, ref[1], rtol=1e-4)
+    for block in (None, 1, 3):
+      sym = D.gram(kernel_fn, x1 if rank == 0 else None, None, ('nngp', 'ntk'), block_rows=block)
+      off = ~np.eye(8, dtype=bool)
+      np.testing.assert_allclose(sym.ntk[off], sref[1][off], rtol=1e-4)
+      np.testing.assert_allclose(np.diag(sym.ntk), np.diag(sref[1]), rtol=2e-3)
+      np.testing.assert_allclose(sym.nngp, sref[0], rtol=1e-4)
+    D.shutdown()
+    print('RANK_OK', rank)
+''')
+
+
+def test_distributed_gram_world2_nccl(nt, tmp_path):
+  """Two ranks, two GPUs, NCCL over NVLink: inputs only on rank 0, results identical to the oracle on both."""
+  from neural_tangents_b200 import _lib
+  if _lib.device_count() < 2:
+    pytest.skip('needs two GPUs')
+  s = socket.socket()
+  s.bind(('127.0.0.1', 0))
+  port = s.getsockname()[1]
+  s.close()
+  script = tmp_path / 'w2.py'
+  script.write_text(_WORLD2.format(root=ROOT))
+  procs = []
+  for r in range(2):
+    env = dict(os.environ, RANK=str(r), WORLD_SIZE='2', LOCAL_RANK=str(r), MASTER_ADDR='127.0.0.1',
+               MASTER_PORT=str(port), NTK_B200_RENDEZVOUS_DIR=str(tmp_path))
+    procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                  stderr=subprocess.STDOUT, text=True))
+  outs = [p.communicate(timeout=900)[0] for p in procs]
+  for r, (p, o) in enumerate(zip(procs, outs)):
+    assert p.returncode == 0 and f'RANK_OK {r}' in o, o[-3000:]
+
+
+def test_upper_only_trapezoid(nt):
+  """NTK_FLAG_UPPER_ONLY: rows [r0, r1) of a symmetric Gram against columns [r0, n): entries j >= i match the
+  full computation bit for bit, entries j < i are left untouched."""
+  from neural_tangents_b200 import _lib, stax
+  spec = cases.myrtle(5)
+  _, _, kernel_fn = cases.build(spec, stax)
+  n, r0, r1 = 9, 2, 6
+  x = np.random.default_rng(8).standard_normal((n, 32, 32, 3)).astype(np.float32)
+  full = kernel_fn(x, x.copy(), ('nngp', 'ntk'))          # cross-pair path on all n x n entries
+  ctx = _lib.get_context()
+  low = stax._lowered(stax._strip(kernel_fn._spec), False, False, True)
+  dx = ctx.malloc(x.nbytes)
+  ctx.h2d(dx, x)
+  nb = (r1 - r0) * (n - r0) * 4
+  dk, dt_ = ctx.malloc(nb), ctx.malloc(nb)
+  ctx.memset(dk, 0xff, nb)                                  # NaN pattern
+  ctx.memset(dt_, 0xff, nb)
+  row = 32 * 32 * 3 * 4
+  _lib.gram_device(ctx, low.program, np.float32, dx + r0 * row, r1 - r0, dx + r0 * row, n - r0, 32, 32, 3,
+                   _lib.FLAG_UPPER_ONLY, dk, dt_, n - r0)
+  k = ctx.d2h(np.empty((r1 - r0, n - r0), np.float32), dk)
+  t = ctx.d2h(np.empty((r1 - r0, n - r0), np.float32), dt_)
+  for ptr in (dx, dk, dt_):
+    ctx.free(ptr)
+  iu = np.triu(np.ones((r1 - r0, n - r0), bool))
+  np.testing.assert_array_equal(k[iu], full.nngp[r0:r1, r0:][iu])
+  np.testing.assert_array_equal(t[iu], full.ntk[r0:r1, r0:][iu])
+  assert np.isnan(k[~iu]).all() and np.isnan(t[~iu]).all()
+
+
+def test_caller_stream_entry_is_asynchronous(nt):
+  """`ntk_gram_device_on_stream` enqueues on a foreign stream and returns before the work has finished; the
+  result equals the context-stream result bit for bit.  A following call on the context stream is ordered
+  behind it on the device (shared workspace), with no host synchronisation in between."""
+  from neural_tangents_b200 import _lib, stax
+  lib = _lib.load()
+  spec = cases.myrtle(10)
+  _, _, kernel_fn = cases.build(spec, stax)
+  low = stax._lowered(stax._strip(kernel_fn._spec), False, False, True)
+  n1, n2 = 48, 48
+  x1 = np.random.default_rng(1).standard_normal((n1, 32, 32, 3)).astype(np.float32)
+  x2 = np.random.default_rng(2).standard_normal((n2, 32, 32, 3)).astype(np.float32)
+  ref = kernel_fn(x1, x2, ('nngp', 'ntk'))
+  ctx = _lib.get_context()
+  stream = ctypes.c_void_p()
+  _lib.check(lib.ntk_stream_create(ctx.device, ctypes.byref(stream)))
+  d1, d2 = ctx.malloc(x1.nbytes), ctx.malloc(x2.nbytes)
+  ctx.h2d(d1, x1)
+  ctx.h2d(d2, x2)
+  ctx.synchronize()
+  outs = [ctx.malloc(n1 * n2 * 4) for _ in range(4)]
+  _lib.gram_device(ctx, low.program, np.float32, d1, n1, d2, n2, 32, 32, 3, 0, outs[0], outs[1], n2,
+                   stream=stream.value)
+  done = ctypes.c_int32(-1)
+  _lib.check(lib.ntk_stream_query(stream, ctypes.byref(done)))
+  assert done.value == 0, 'the call blocked until the GPU work was finished'      # ~10 ms of kernels enqueued
+  # second call on the context's own stream: must wait for the first on the device (same workspace)
+  _lib.gram_device(ctx, low.program, np.float32, d1, n1, d2, n2, 32, 32, 3, 0, outs[2], outs[3], n2)
+  _lib.check(lib.ntk_stream_synchronize(stream))
+  ctx.synchronize()
+  got = [ctx.d2h(np.empty((n1, n2), np.float32), p) for p in outs]
+  np.testing.assert_array_equal(got[0], ref.nngp)
+  np.testing.assert_array_equal(got[1], ref.ntk)
+  np.testing.assert_array_equal(got[2], ref.nngp)
+  np.testing.assert_array_equal(got[3], ref.ntk)
+  for p in outs + [d1, d2]:
+    ctx.free(p)
+  lib.ntk_stream_destroy(stream)
+
+
+@pytest.mark.parametrize('x64', [False, True])
+def test_apply_device_matches_apply_host(nt, x64):
+  """Kernel-in / Kernel-out on device pointers (`ntk_apply_device`) == the host-pointer entry; the caller's
+  input tensors are not modified (copy-on-write inside the executor)."""
+  from neural_tangents_b200 import _lib, stax
+  nt.config.update('enable_x64', x64)
+  dt = np.float64 if x64 else np.float32
+  rng = np.random.default_rng(5)
+  x1 = rng.standard_normal((2, 6, 6, 2)).astype(np.float32)
+  x2 = rng.standard_normal((3, 6, 6, 2)).astype(np.float32)
+  a = stax.serial(stax.Conv(1, (3, 3), padding='SAME', W_std=1.2, b_std=0.1), stax.Relu())
+  b = stax.serial(stax.Conv(1, (3, 3), padding='SAME', W_std=1.0, b_std=0.3), stax.Relu(), stax.GlobalAvgPool(),
+                  stax.Dense(1, 1.1, 0.2))
+  k_mid = a[2](x1, x2)
+  want = b[2](k_mid)                                           # host path
+  ctx = _lib.get_context()
+  rev = bool(k_mid.is_reversed)
+  can = lambda m, nb: np.ascontiguousarray(stax._from_ref_layout(np.asarray(m, dt), rev, nb))
+  ins = [can(k_mid.nngp, 2), can(k_mid.ntk, 2), can(k_mid.cov1, 1), can(k_mid.cov2, 1)]
+  d_in = []
+  for arr in ins:
+    p = ctx.malloc(arr.nbytes)
+    ctx.h2d(p, arr)
+    d_in.append(p)
+  low = stax._lowered(stax._strip(b[2]._spec), rev, True, True)
+  isz = np.dtype(dt).itemsize
+  d_out = [ctx.malloc(2 * 3 * isz), ctx.malloc(2 * 3 * isz), ctx.malloc(2 * isz), ctx.malloc(3 * isz)]
+  mode, gauss = _lib.apply_device(ctx, low.program, dt, 2, 3, 6, 6, _lib.NTK_TENSOR, k_mid.is_gaussian, d_in, d_out,
+                                  0, 0)
+  ctx.synchronize()
+  assert mode == _lib.NTK_TENSOR and gauss
+  got = [ctx.d2h(np.empty(s, dt), p) for s, p in zip([(2, 3), (2, 3), (2,), (3,)], d_out)]
+  np.testing.assert_array_equal(got[0], want.nngp)
+  np.testing.assert_array_equal(got[1], want.ntk)
+  np.testing.assert_array_equal(got[2], want.cov1)
+  np.testing.assert_array_equal(got[3], want.cov2)
+  for arr, p in zip(ins, d_in):
+    np.testing.assert_array_equal(ctx.d2h(np.empty_like(arr), p), arr)   # inputs untouched
+  for p in d_in + d_out:
+    ctx.free(p)
+  nt.config.update('enable_x64', False)
+
+
+def test_pinned_results_and_pageable_staging(nt):
+  """Results come back in page-locked memory (direct DMA); pageable inputs larger than one staging slot go
+  through the pinned ring; both give the same numbers as pinned inputs."""
+  from neural_tangents_b200 import _lib, stax
+  lib = _lib.load()
+  _, _, kernel_fn = cases.build(cases.fcn(3, 2., 0.05), stax)
+  n, d = 3000, 784                                             # 9.4 MB per input > the 8 MB slot
+  x1 = np.random.default_rng(0).standard_normal((n, d)).astype(np.float32)
+  x2 = np.random.default_rng(1).standard_normal((n, d)).astype(np.float32)
+  out = kernel_fn(x1, x2, ('nngp', 'ntk'))
+  p1, p2 = _lib.pinned_copy(x1), _lib.pinned_copy(x2)
+  out_p = kernel_fn(p1, p2, ('nngp', 'ntk'))
+  np.testing.assert_array_equal(out.nngp, out_p.nngp)
+  np.testing.assert_array_equal(out.ntk, out_p.ntk)
+
+  class Attr(ctypes.Structure):
+    _fields_ = [('type', ctypes.c_int), ('device', ctypes.c_int), ('dptr', ctypes.c_void_p),
+                ('hptr', ctypes.c_void_p)]
+  try:
+    rt = ctypes.CDLL('libcudart.so.12')
+  except OSError:
+    rt = None
+  for arr, pinned in ((out.nngp, True), (p1, True), (x1, False)):
+    if rt is None:
+      break
+    at = Attr()
+    rc = rt.cudaPointerGetAttributes(ctypes.byref(at), ctypes.c_void_p(arr.ctypes.data))
+    assert rc == 0
+    assert (at.type == 1) == pinned, (at.type, pinned)         # cudaMemoryTypeHost == 1
+  from oracle import ntk_oracle as O
+  ref = O.kernel_fn(cases.fcn(3, 2., 0.05), x1[:64], x2[:64], ('nngp', 'ntk'))
+  np.testing.assert_allclose(out.ntk[:64, :64], ref[1], rtol=1e-4)
+
+
+def test_diagonal_path_odd_and_mnist_sizes(nt):
+  """Pool-free Flatten nets with stride-2 convs at odd resolutions (SAME: out = ceil(S/2), window centred at
+  2a) and at 28x28 (28 -> 14 -> 7 -> 4): the diagonal-column kernels against the oracle and the per-op path."""
+  from oracle import ntk_oracle as O
+  spec = ('serial', [cases.conv(W=1.3, b=0.1), cases.RELU, cases.conv(s=(2, 2), W=1.2, b=0.05), cases.RELU,
+                     cases.conv(s=(2, 2)), ('abrelu', 0.1, 1., False), cases.conv(s=(2, 2)), cases.RELU,
+                     ('flatten',), ('dense', 1., 0.1)])
+  _, _, kernel_fn = cases.build(spec, nt.stax)
+  for size, C in ((7, 3), (15, 2), (28, 1), (9, 3)):
+    x1 = np.random.default_rng(21).standard_normal((3, size, size, C)).astype(np.float32)
+    x2 = np.random.default_rng(22).standard_normal((4, size, size, C)).astype(np.float32)
+    ref = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'))
+    low = nt.stax._lowered(nt.stax._strip(kernel_fn._spec), False, False, True)
+    assert low.program.path(size, size, C) == 'diag'
+    for x64 in (False, True):
+      nt.config.update('enable_x64', x64)
+      out = kernel_fn(x1, x2, ('nngp', 'ntk'))
+      np.testing.assert_allclose(out.nngp, ref[0], rtol=RTOL[x64], err_msg=f'{size}')
+      np.testing.assert_allclose(out.ntk, ref[1], rtol=RTOL[x64], err_msg=f'{size}')
+      nt.config.update('disable_fusion', True)
+      gen = kernel_fn(x1, x2, ('nngp', 'ntk'))
+      nt.config.update('disable_fusion', False)
+      np.testing.assert_allclose(out.ntk, gen.ntk, rtol=RTOL[x64] * 0.1)
+  nt.config.update('enable_x64', False)
+
+
+def test_batch_device_count_one_context_per_device(nt):
+  """`batch(device_count=D)` spawns fresh host threads per call; contexts are cached per device, so repeated
+  calls do not allocate new workspaces."""
+  from neural_tangents_b200 import _lib
+  _, _, kernel_fn = cases.build(cases.myrtle(5), nt.stax)
+  x1 = np.random.default_rng(0).standard_normal((4, 32, 32, 3)).astype(np.float32)
+  x2 = np.random.default_rng(1).standard_normal((2, 32, 32, 3)).astype(np.float32)
+  D = min(2, _lib.device_count())
+  bk = nt.batch(kernel_fn, batch_size=2, device_count=D)
+  ref = kernel_fn(x1, x2, 'ntk')
+  n_ctx = None
+  for _ in range(4):
+    np.testing.assert_array_equal(bk(x1, x2, 'ntk'), ref)
+    if n_ctx is None:
+      n_ctx = len(_lib._contexts)
+    assert len(_lib._contexts) == n_ctx <= max(D, 1) + 1
