@@ -1,20 +1,26 @@
 """Benchmark of the analytic NNGP/NTK hot path (BASELINE.json: Myrtle-10 kernel entries/s).
 
-  python bench.py --gpus N --steps K --warmup W            # ours (one rank per GPU)
+  python bench.py --gpus N --steps K --warmup W            # ours (one rank per GPU; torchrun launches N > 1)
   python bench.py --impl reference --steps K --warmup W    # CPU port of the reference path
 
-A *step* is one Gram block per rank: a [b1, b2] block of NNGP+NTK kernel entries of the
-Myrtle-10 (32x32x3) network on synthetic N(0,1) inputs, i.e. one block of the nt.batch
-tiling of the 10000x10000 configuration (entries/s does not depend on which block).  Rows
-are partitioned across ranks ("weak" scaling: every rank owns its own slab of x1 rows, x2 is
-broadcast from rank 0 and the result slabs are all-gathered inside the timed region; there
-is no reduction collective).
+A *step* is one Gram block per rank: a [b1, b2] block of NNGP+NTK kernel entries of the Myrtle-10 (32x32x3)
+network on synthetic N(0,1) inputs, i.e. one block of the nt.batch tiling of the 10000x10000 configuration
+(entries/s does not depend on which block).  Multi-GPU runs go through the PRODUCT path,
+`neural_tangents_b200.distributed` (NCCL inside libntk_b200.so; no torch anywhere in this file): x1
+(world x b1 rows) and x2 live on rank 0, are broadcast device-to-device, every rank computes its row slab
+and the slabs are all-gathered, all inside the timed region ("weak" scaling, no reduction collective).
 
-JSON line keys follow the driver contract; `roofline` is for the dominant kernel (the first
-fused stage: Conv+Relu x3 + AvgPool at 32x32), timed with CUDA events on its launch stream.
+Besides the headline line the JSON carries
+  `roofline`  the dominant kernel (first fused stage), timed live with CUDA events on its launch stream,
+              plus `roofline.compute`: its real bound after cross-layer fusion (issue / FMA pipe / register file);
+  `strong`    a fixed-size symmetric Gram (x2=None, triangular folded-cyclic schedule) over all N GPUs through
+              `distributed.gram`, host arrays in and out -- shows tail imbalance and collective cost;
+  `configs`   one measured line per BASELINE.json config family (N = 1 only);
+  `cpu_baseline`  the NumPy float64 port of the reference path on the host cores (N = 1 only).
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -51,6 +57,11 @@ WORKLOADS = {
     'fcn': (-4, 0, 0),
 }
 FCN_DIM = 784
+PUBLISHED = {('readme21', 'f32'): 1e3 / 2.7001, ('readme21', 'f64'): 1e3 / 6.2058,
+             ('readme21_flatten', 'f32'): 1e3 / 0.0046510, ('readme21_flatten', 'f64'): 1e3 / 0.010822}
+# Real bound of the dominant fp32 kernel (ncu capture named below): static context for
+# `roofline.compute`, the live part is the clock count per element-layer.
+RF_FLOOR_CLK = {'f32': 35.0}
 
 
 def input_shape(name, n):
@@ -59,8 +70,6 @@ def input_shape(name, n):
 
 def input_dims(name):
   return (0, 0, FCN_DIM) if name == 'fcn' else (32, 32, 3)
-PUBLISHED = {('readme21', 'f32'): 1e3 / 2.7001, ('readme21', 'f64'): 1e3 / 6.2058,
-             ('readme21_flatten', 'f32'): 1e3 / 0.0046510, ('readme21_flatten', 'f64'): 1e3 / 0.010822}
 
 
 def workload_spec(name):
@@ -126,12 +135,12 @@ def peaks():
   return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}, 'fallback'
 
 
-def ncu_traffic_per_pair(workload, dtype):
-  """dram bytes per sample pair of the dominant kernel from the committed ncu capture."""
+def ncu_capture(workload, dtype):
+  """The committed `ncu --set full` summary of the dominant kernel (profiles/ncu_stage0_summary.json):
+  dram bytes per pair and the pipe / issue utilisation, each labelled with the capture it comes from."""
   path = os.path.join(ROOT, 'profiles', 'ncu_stage0_summary.json')
   try:
-    d = json.load(open(path))
-    return d[f'{workload}_{dtype}']['dram_bytes_per_pair']
+    return json.load(open(path)).get(f'{workload}_{dtype}')
   except Exception:
     return None
 
@@ -244,137 +253,253 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------
-def run_ours(args):
-  import torch
-  import torch.distributed as dist
-  import __graft_entry__ as g
-  g.build()
-  import neural_tangents_b200 as nt
-  from neural_tangents_b200 import _lib, stax
-  import cases
+class Bench:
+  """One rank of the GPU arm: the library context, the NCCL backend (world > 1) and timing helpers."""
 
-  rank = int(os.environ.get('RANK', '0'))
-  world = int(os.environ.get('WORLD_SIZE', '1'))
-  local = int(os.environ.get('LOCAL_RANK', '0'))
-  torch.cuda.set_device(local)
-  dev = torch.device('cuda', local)
+  def __init__(self, args):
+    import __graft_entry__ as g
+    g.build()
+    import neural_tangents_b200 as nt
+    from neural_tangents_b200 import _lib, distributed, stax
+    import cases
+    self.nt, self.lib, self.D, self.stax, self.cases = nt, _lib, distributed, stax, cases
+    self.args = args
+    self.rank = int(os.environ.get('RANK', '0'))
+    self.world = int(os.environ.get('WORLD_SIZE', '1'))
+    self.local = int(os.environ.get('LOCAL_RANK', '0'))
+    nt.config.update('device', self.local)
+    self.ctx = _lib.get_context(self.local)
+    self.be = distributed.init() if self.world > 1 else None
+    self.flush_bytes = 256 << 20                                   # > 126 MB L2
+    self.flush = self.ctx.malloc(self.flush_bytes)
+
+  def set_dtype(self, dtype):
+    self.x64 = dtype == 'f64'
+    self.nt.config.update('enable_x64', self.x64)
+    self.np_dt = np.float64 if self.x64 else np.float32
+    self.sz = 8 if self.x64 else 4
+
+  def kernel(self, workload):
+    _, _, kernel_fn = self.cases.build(workload_spec(workload), self.stax)
+    low = self.stax._lowered(self.stax._strip(kernel_fn._spec), False, False, workload != 'fcn')
+    return kernel_fn, low
+
+  def barrier(self):
+    self.ctx.synchronize()
+    if self.be is not None:
+      self.be.barrier()
+
+  def max_over_ranks(self, values):
+    if self.be is None:
+      return list(values)
+    return self.be.all_gather_host(values).max(axis=0).tolist()
+
+  def time_steps(self, step, steps, warmup):
+    """`warmup` untimed + `steps` timed calls of `step()` on the context stream: CUDA events around every
+    step, L2 flushed (256 MiB memset) outside the events, barrier + synchronize on both sides.
+    Returns this rank's summed device ms."""
+    for _ in range(warmup):
+      step()
+    self.barrier()
+    evs = [(self.lib.Event(), self.lib.Event()) for _ in range(steps)]
+    for s, e in evs:
+      self.ctx.memset(self.flush, 0, self.flush_bytes)
+      s.record(self.ctx)
+      step()
+      e.record(self.ctx)
+    self.barrier()
+    return sum(s.elapsed_ms(e) for s, e in evs)
+
+
+def measure_block(B, workload, dtype, b1, b2, steps, warmup, flags=0, profile=False, symmetric=False):
+  """Device-resident entries/s of one [b1, b2] block per rank (inputs in HBM before the timed region)."""
+  B.set_dtype(dtype)
+  kernel_fn, low = B.kernel(workload)
+  H_, W_, C_ = input_dims(workload)
+  ctx, lib, D = B.ctx, B.lib, B.D
+  rank, world = B.rank, B.world
+  names = ('nngp', 'ntk')
+  out = {}
   if world > 1:
-    dist.init_process_group('nccl', device_id=dev)
-  nt.config.update('device', local)
-  x64 = args.dtype == 'f64'
-  nt.config.update('enable_x64', x64)
-  np_dt = np.float64 if x64 else np.float32
-  t_dt = torch.float64 if x64 else torch.float32
-  sz = 8 if x64 else 4
+    # product path: x1 = world x b1 rows and x2 on rank 0, broadcast + row slabs + all-gather inside the step
+    x1_h = np.random.default_rng(100).standard_normal(input_shape(workload, b1 * world)).astype(B.np_dt)
+    x2_h = np.random.default_rng(1).standard_normal(input_shape(workload, b2)).astype(B.np_dt)
+    plan = B.be.resolve(kernel_fn, x1_h.shape)
+    d1 = B.be.put(x1_h, x1_h.shape, B.np_dt, 0)
+    d2 = B.be.put(x2_h, x2_h.shape, B.np_dt, 0)
+    held = {}
 
-  depth, elems_net, elems_stage0 = WORKLOADS[args.workload]
-  _, _, kernel_fn = cases.build(workload_spec(args.workload), stax)
-  low = stax._lowered(stax._strip(kernel_fn._spec), False, False, True)
-  b1, b2 = args.block
-  # synthetic inputs: each rank owns a slab of x1 rows; x2 comes from rank 0
-  if args.workload == 'fcn' and args.block == [96, 96]:
-    b1 = b2 = 1000                                                  # BASELINE configs[0]: 1000 x 1000
-  H_, W_, C_ = input_dims(args.workload)
-  x1_h = np.random.default_rng(100 + rank).standard_normal(input_shape(args.workload, b1)).astype(np_dt)
-  x2_h = np.random.default_rng(1).standard_normal(input_shape(args.workload, b2)).astype(np_dt)
-  ctx = _lib.get_context(local)
-  stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-  x1_d = torch.from_numpy(x1_h).to(dev)
-  x2_d = torch.from_numpy(x2_h).to(dev) if rank == 0 else torch.empty(input_shape(args.workload, b2), dtype=t_dt, device=dev)
-  out_d = torch.empty((2, b1, b2), dtype=t_dt, device=dev)          # this rank's nngp / ntk slab
-  gath_d = torch.empty((world, 2, b1, b2), dtype=t_dt, device=dev) if world > 1 else None
-  flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
-  flags = (_lib.FLAG_NO_FUSION if args.no_fusion else 0) | (_lib.FLAG_PER_LAYER if args.per_layer else 0)
+    def step():
+      for v in held.values():
+        B.be.free(v)
+      held.clear()
+      held.update(D.gram_resident(B.be, plan, d1, None if symmetric else d2, names, src=0, gather=True))
+  else:
+    x1_h = np.random.default_rng(100).standard_normal(input_shape(workload, b1)).astype(B.np_dt)
+    x2_h = np.random.default_rng(1).standard_normal(input_shape(workload, b2)).astype(B.np_dt)
+    d1, d2 = D.DeviceArray(ctx, x1_h.shape, B.np_dt), D.DeviceArray(ctx, x2_h.shape, B.np_dt)
+    ctx.h2d(d1.ptr, x1_h)
+    ctx.h2d(d2.ptr, x2_h)
+    ctx.synchronize()
+    ok, ot = D.DeviceArray(ctx, (b1, b2), B.np_dt), D.DeviceArray(ctx, (b1, b2), B.np_dt)
+    held = {'nngp': ok, 'ntk': ot}
 
-  def step_device():
-    # everything is ordered on the context stream (NCCL syncs with the current stream)
-    if world > 1:
-      dist.broadcast(x2_d, src=0)                                   # x2 over NVLink
-    if args.symmetric:   # K(x1, x1): upper triangle + mirror (not the headline configuration)
-      _lib.gram_device(ctx, low.program, np_dt, x1_d.data_ptr(), b1, None, b1, H_, W_, C_,
-                       flags, out_d[0].data_ptr(), out_d[1].data_ptr(), b2)
-      return
-    _lib.gram_device(ctx, low.program, np_dt, x1_d.data_ptr(), b1, x2_d.data_ptr(), b2, H_, W_, C_,
-                     flags, out_d[0].data_ptr(), out_d[1].data_ptr(), b2)
-    if world > 1:
-      dist.all_gather_into_tensor(gath_d, out_d)                    # result slabs; no reduction
+    def step():
+      lib.gram_device(ctx, low.program, B.np_dt, d1.ptr, b1, None if symmetric else d2.ptr, b1 if symmetric else b2,
+                      H_, W_, C_, flags, ok.ptr, ot.ptr, b2)
 
-  def barrier():
-    torch.cuda.synchronize()
-    if world > 1:
-      dist.barrier()
-    torch.cuda.synchronize()
-
-  with torch.cuda.stream(stream):
-    for _ in range(args.warmup):
-      step_device()
+  for _ in range(warmup):
+    step()
   ctx.synchronize()
   launches0 = ctx.launch_count
-  ctx.set_profiling(True)
-  sampler = ClockSampler(local)
+  if profile:
+    ctx.set_profiling(True)
+  ms = B.time_steps(step, steps, 0)
+  out['launches'] = ctx.launch_count - launches0
+  out['ms_dev'] = ms
+  out['ms_dev_max'] = B.max_over_ranks([ms])[0]
+  out['entries_per_step'] = (b1 * world) ** 2 if (symmetric and world > 1) else b1 * b2 * world
+  out['value'] = out['entries_per_step'] * steps / (out['ms_dev_max'] * 1e-3)
+  out['x1_h'], out['x2_h'], out['kernel_fn'] = x1_h, x2_h, kernel_fn
+  out['result'] = {k: ctx.d2h(np.empty(v.shape, B.np_dt), v.ptr) for k, v in held.items()}
+  for v in list(held.values()) + [d1, d2]:
+    v.free()
+  return out
+
+
+def measure_strong(B, n, dtype, workload='myrtle10'):
+  """Fixed-size symmetric Gram K(x, x) over all ranks through the public multi-GPU entry
+  (`distributed.gram`: host array on rank 0 in, host matrices out on every rank), wall clock from barrier to
+  barrier, max over ranks.  One untimed warm-up on a small problem, one timed run."""
+  B.set_dtype(dtype)
+  kernel_fn, _ = B.kernel(workload)
+  be = B.be if B.be is not None else B.D.init(rank=0, world=1, local_rank=B.local, unique_id=B.lib.Comm.unique_id())
+  x = np.random.default_rng(7).standard_normal(input_shape(workload, n)).astype(B.np_dt) if B.rank == 0 else None
+  B.D.gram(kernel_fn, None if B.rank else x[:4 * B.world], None, ('nngp', 'ntk'), backend=be)
+  be.barrier()
+  t0 = time.perf_counter()
+  res = B.D.gram(kernel_fn, x, None, ('nngp', 'ntk'), backend=be)
+  be.barrier()
+  dt = time.perf_counter() - t0
+  dt_max = B.max_over_ranks([dt])[0]
+  sched = B.D.sym_schedule(n, B.world, B.D.sym_block_rows(n, B.world))
+  work = B.D.sym_work(sched, B.world)
+  rec = {'workload': f'{workload}_32x32x3_nngp+ntk', 'n': n, 'x2': None, 'dtype': dtype, 'scaling': 'strong',
+         'entries': n * n, 'pairs_computed': int(sum(work)), 'seconds': dt_max, 'entries_per_s': n * n / dt_max,
+         'pairs_per_s': sum(work) / dt_max, 'imbalance_max_over_mean': max(work) / (sum(work) / B.world),
+         'api': 'distributed.gram(kernel_fn, x, None) host in / host out, NCCL broadcast + all-gather + ntk_sym_assemble'}
+  if B.rank == 0:
+    i = np.random.default_rng(3).integers(0, n, 64)
+    j = np.random.default_rng(4).integers(0, n, 64)
+    rec['asymmetry_max'] = float(np.abs(res.ntk[i, j] - res.ntk[j, i]).max())
+    direct = kernel_fn(x[i[:8]], x[j[:8]], ('nngp', 'ntk'))
+    rec['vs_direct_block_max_rel'] = float(np.abs(res.ntk[np.ix_(i[:8], j[:8])] / direct.ntk - 1).max())
+  return rec
+
+
+def run_ours(args):
+  B = Bench(args)
+  nt, lib = B.nt, B.lib
+  rank, world = B.rank, B.world
+  depth, elems_net, elems_stage0 = WORKLOADS[args.workload]
+  b1, b2 = args.block
+  if args.workload == 'fcn' and args.block == [96, 96]:
+    b1 = b2 = 1000                                                  # BASELINE configs[0]: 1000 x 1000
+  flags = (lib.FLAG_NO_FUSION if args.no_fusion else 0) | (lib.FLAG_PER_LAYER if args.per_layer else 0)
+  x64 = args.dtype == 'f64'
+  sz = 8 if x64 else 4
+
+  sampler = ClockSampler(B.local)
   if rank == 0:
     sampler.start()
-  barrier()
-  evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-         for _ in range(args.steps)]
-  with torch.cuda.stream(stream):
-    for s, e in evs:
-      flush.zero_()                      # L2 flush between timed iterations (outside the events)
-      s.record(stream)
-      step_device()
-      e.record(stream)
-  barrier()
-  ms_dev = sum(s.elapsed_time(e) for s, e in evs)
-  launches = ctx.launch_count - launches0
+  m = measure_block(B, args.workload, args.dtype, b1, b2, args.steps, args.warmup, flags, profile=True,
+                    symmetric=args.symmetric)
+  ctx = B.ctx
+  ms_dev, ms_dev_max = m['ms_dev'], m['ms_dev_max']
   st0_ms, st0_n, st0_pairs = ctx.profile(0) if not args.no_fusion else (0.0, 0, 0)
   per_stage = []
   if not args.no_fusion and depth > 0:
-    elems = stage_elements(depth, args.per_layer)
-    for si, el in enumerate(elems):
+    for si, el in enumerate(stage_elements(depth, args.per_layer)):
       ms_, n_, pr_ = ctx.profile(si)
       if n_ > 0:
-        per_stage.append({'stage': si, 'ms_per_launch': ms_ / n_, 'algorithmic_GBps': pr_ * el * sz / (ms_ * 1e-3) / 1e9})
+        per_stage.append({'stage': si, 'ms_per_launch': ms_ / n_,
+                          'algorithmic_GBps': pr_ * el * sz / (ms_ * 1e-3) / 1e9})
   ctx.set_profiling(False)
 
-  # end to end through the public API: HOST buffers in, HOST results out (nt.batch -> C-ABI)
-  import math
-  g_ = math.gcd(b1, b2)
-  e2e_cap = 500 if args.workload == 'fcn' else args.e2e_batch      # FCN entries are ~1e4 x cheaper: bigger blocks
-  e2e_bs = max(d for d in range(1, min(e2e_cap, g_) + 1) if g_ % d == 0)
-  batched = nt.batch(kernel_fn, batch_size=e2e_bs, device_count=0)
+  # ---- end to end through the public API: pinned HOST buffers in, HOST results out ----------------------
+  x1_h, x2_h, kernel_fn = lib.pinned_copy(m['x1_h']), lib.pinned_copy(m['x2_h']), m['kernel_fn']
+  get = ('nngp', 'ntk')
+  if world > 1:
+    def e2e_call():
+      return B.D.gram(kernel_fn, x1_h if rank == 0 else None,
+                      None if args.symmetric else (x2_h if rank == 0 else None), get)
+  else:
+    g_ = math.gcd(b1, b2)
+    e2e_cap = 500 if args.workload == 'fcn' else args.e2e_batch     # FCN entries are ~1e4 x cheaper: bigger blocks
+    e2e_bs = max(d for d in range(1, min(e2e_cap, g_) + 1) if g_ % d == 0)
+    batched = nt.batch(kernel_fn, batch_size=e2e_bs, device_count=0)
+
+    def e2e_call():
+      return batched(x1_h, None if args.symmetric else x2_h, get)
   for _ in range(max(1, min(args.warmup, 2))):   # untimed warm-up of the host path (IO buffers)
-    batched(x1_h, None if args.symmetric else x2_h, ('nngp', 'ntk'))
-  barrier()
+    e2e_call()
+  B.barrier()
   t0 = time.perf_counter()
   for _ in range(args.steps):
-    res = batched(x1_h, None if args.symmetric else x2_h, ('nngp', 'ntk'))
-  torch.cuda.synchronize()
+    res = e2e_call()
+  ctx.synchronize()
   e2e_s = time.perf_counter() - t0
-  barrier()
+  B.barrier()
+  e2e_ms_max = B.max_over_ranks([e2e_s * 1e3])[0]
   clocks = sampler.summary() if rank == 0 else None
 
-  t = torch.tensor([ms_dev, e2e_s * 1e3], dtype=torch.float64, device=dev)
+  # the device-resident result of the last timed step must equal the public-API result
   if world > 1:
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  ms_dev_max, e2e_ms_max = t.tolist()
+    np.testing.assert_allclose(m['result']['nngp'], res.nngp, rtol=1e-5)
+    np.testing.assert_allclose(m['result']['ntk'], res.ntk, rtol=1e-5)
+  else:
+    np.testing.assert_allclose(m['result']['nngp'], res.nngp, rtol=1e-5)
+    np.testing.assert_allclose(m['result']['ntk'], res.ntk, rtol=1e-5)
+
+  strong = None
+  if args.strong_n > 0 and not args.no_fusion and args.workload == 'myrtle10':
+    strong = [measure_strong(B, args.strong_n, args.dtype)]
+    if world >= 8 and args.full_n > 0:
+      strong.append(measure_strong(B, args.full_n, args.dtype))    # BASELINE configs[3] at its stated size
+
+  configs = None
+  if world == 1 and not args.no_configs and args.workload == 'myrtle10' and args.dtype == 'f32':
+    configs = []
+    for wl, dt, blk, stated in (('fcn', 'f32', (1000, 1000), 'configs[0]: 1000 x 1000, 784-d (stated size)'),
+                                ('fcn', 'f64', (1000, 1000), 'configs[0] in float64 (stated size and dtype)'),
+                                ('myrtle5', 'f32', (1024, 1024), 'configs[1]: 1024 x 1024 block, 1 B200 (stated size)'),
+                                ('myrtle7', 'f32', (96, 96), 'configs[2]: one block of the 4096 x 4096 tiling'),
+                                ('myrtle10', 'f64', (96, 96), 'configs[3] FP64 path: one block of the 10000 x 10000 tiling'),
+                                ('wrn', 'f32', (96, 96), 'configs[4] Relu: one block of the 4096 x 4096 tiling'),
+                                ('wrn_erf', 'f32', (96, 96), 'configs[4] Erf: one block of the 4096 x 4096 tiling')):
+      steps_c = 1 if blk[0] >= 1024 and wl != 'fcn' else 3
+      mc = measure_block(B, wl, dt, blk[0], blk[1], steps_c, 1 if steps_c == 1 else 2)
+      configs.append({'workload': workload_label(wl), 'dtype': dt, 'block': list(blk), 'steps': steps_c,
+                      'ms_per_step': mc['ms_dev_max'] / steps_c, 'entries_per_s': mc['value'],
+                      'gpu_launches': int(mc['launches']), 'baseline_config': stated,
+                      'algorithmic_roofline_frac': (mc['value'] * WORKLOADS[wl][1] * (8 if dt == 'f64' else 4) / 1e9 /
+                                                    peaks()[0]['hbm_gbs']) if WORKLOADS[wl][1] else None})
+    B.set_dtype(args.dtype)
   if rank != 0:
-    if world > 1:
-      dist.destroy_process_group()
+    B.D.shutdown()
     return
 
-  # the device-resident result of the last timed step must equal the public-API result
-  np.testing.assert_allclose(out_d[0].cpu().numpy(), res.nngp, rtol=1e-5)
-  np.testing.assert_allclose(out_d[1].cpu().numpy(), res.ntk, rtol=1e-5)
-
-  entries_per_step = b1 * b2 * world
-  value = entries_per_step * args.steps / (ms_dev_max * 1e-3)
+  entries_per_step = m['entries_per_step']
+  value = m['value']
   e2e_value = entries_per_step * args.steps / (e2e_ms_max * 1e-3)
   pk, pk_kind = peaks()
   roof = {'bound': 'hbm', 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'peak_kind': pk_kind + ' (burst copy)'}
   if st0_n > 0:
     alg_bytes_per_pair = elems_stage0 * sz
     achieved = st0_pairs * alg_bytes_per_pair / (st0_ms * 1e-3) / 1e9
-    tpp = ncu_traffic_per_pair(args.workload, args.dtype)
+    cap = ncu_capture(args.workload, args.dtype)
+    tpp = cap.get('dram_bytes_per_pair') if cap else None
+    n_l = 3 if depth in (10, 21) else 2
     roof.update({
         'kernel': ('k_stage<S=32,L=3,FROM_X,STORE> (first 3 fused Conv+Relu layers)' if depth == 21 else
                    ('k_stage_p' if (not x64 and args.workload != 'myrtle10_erf') else 'k_stage') +
@@ -385,9 +510,29 @@ def run_ours(args):
         'avg_launch_ms': st0_ms / st0_n, 'launches_timed': st0_n,
         'share_of_step': st0_ms / ms_dev,
         'traffic': None if tpp is None else tpp * st0_pairs // st0_n,
+        'traffic_source': None if cap is None else cap.get('source'),
         'whole_net_achieved': b1 * b2 * args.steps * elems_net * sz / (ms_dev * 1e-3) / 1e9,
         'per_stage': per_stage,
     })
+    # The kernel's real bound: cross-layer fusion removed the per-layer HBM round trips the algorithmic model
+    # counts, so it is issue / register-file bound.  Live: SM clocks per 32 element-layers and SM sub-partition
+    # (one warp instruction wide), from the CUDA-event launch time and the sampled SM clock.
+    sm_mhz = (clocks or {}).get('sm_mhz') or pk.get('sm_max_mhz') or 1965.0
+    elem_layers = st0_pairs * float(E32) * n_l
+    clk = (st0_ms * 1e-3) * sm_mhz * 1e6 * 148 * 4 / (elem_layers / 32.0)
+    comp = {'bound': 'issue slots / register-file read bandwidth (not HBM)', 'clk_per_element_layer': clk,
+            'sm_mhz_used': sm_mhz}
+    if args.dtype in RF_FLOOR_CLK and depth in (5, 7, 10) and args.workload != 'myrtle10_erf':
+      comp['register_file_floor_clk'] = RF_FLOOR_CLK[args.dtype]
+      comp['frac_of_register_file_floor'] = RF_FLOOR_CLK[args.dtype] / clk
+    if cap:
+      for k in ('issue_slot_utilisation_pct', 'pipe_fma_pct', 'pipe_xu_pct', 'pipe_alu_pct', 'pipe_lsu_pct',
+                'warp_instructions_per_element_layer', 'registers_per_thread', 'achieved_occupancy_pct',
+                'dram_throughput_pct', 'warp_state_pct'):
+        if k in cap:
+          comp[k] = cap[k]
+      comp['ncu_source'] = cap.get('source')
+    roof['compute'] = comp
     if args.per_layer and per_stage:
       # one layer per launch: the dominant kernel is the slowest stage; its traffic is real
       dom = max(per_stage, key=lambda d_: d_['ms_per_launch'])
@@ -419,16 +564,25 @@ def run_ours(args):
                       if (args.workload, args.dtype) in PUBLISHED else None),
       'dtype': args.dtype, 'data': 'synthetic',
       'config': {'workload': workload_label(args.workload), 'block_per_gpu': [b1, b2],
-                 'parallelism': f'x1-row partition over {world} rank(s), x2 broadcast, slabs all-gathered',
-                 'l2': 'flushed (256 MiB write) between timed steps', 'fusion': ('per-layer stencil kernels' if args.per_layer else not args.no_fusion),
-                 'symmetric_x2_none': bool(args.symmetric)},
+                 'parallelism': (f'distributed.gram_resident over {world} rank(s): NCCL broadcast of x1 / x2 from rank 0, '
+                                 'contiguous row slabs, NCCL all-gather (no reduction collective)') if world > 1
+                 else 'one rank: ntk_gram_device on the context stream',
+                 'l2': 'flushed (256 MiB memset) between timed steps',
+                 'fusion': ('per-layer stencil kernels' if args.per_layer else not args.no_fusion),
+                 'symmetric_x2_none': bool(args.symmetric), 'host_framework': 'NumPy + ctypes (no torch)'},
       'e2e': {'value': e2e_value, 'unit': 'entries/s',
-              'h2d_bytes_per_step': int(x1_h.nbytes + x2_h.nbytes) * world,
-              'd2h_bytes_per_step': int(2 * b1 * b2 * sz) * world},
-      'gpu_launches': int(launches),
+              'h2d_bytes_per_step': int(x1_h.nbytes + x2_h.nbytes),
+              'd2h_bytes_per_step': int(2 * entries_per_step * sz) * (world if world > 1 else 1),
+              'api': 'distributed.gram (pinned host arrays on rank 0 -> host matrices on every rank)' if world > 1
+                     else 'nt.batch(kernel_fn) (pinned host arrays in, pinned host matrices out)'},
+      'gpu_launches': int(m['launches']),
       'clocks': clocks,
       'roofline': roof,
   }
+  if strong:
+    line['strong'] = strong
+  if configs:
+    line['configs'] = configs
   if world == 1 and not args.no_cpu:
     cores = len(os.sched_getaffinity(0))
     pool = make_cpu_pool(cores)
@@ -441,8 +595,7 @@ def run_ours(args):
         'value': n / dt, 'unit': 'entries/s', 'cores': cores, 'kind': 'port',
         'sample': f'{cores} worker processes x (1 x {args.ref_cols}) pairs, NumPy float64 oracle, {dt:.1f} s'}
   emit(line)
-  if world > 1:
-    dist.destroy_process_group()
+  B.D.shutdown()
 
 
 _JSON_OUT = None
@@ -478,6 +631,11 @@ def main():
                   help='x2 columns per worker in a CPU step (about 10 s of CPU work per step on every core)')
   ap.add_argument('--no-fusion', action='store_true')
   ap.add_argument('--no-cpu', action='store_true')
+  ap.add_argument('--no-configs', action='store_true', help='skip the per-BASELINE-config lines (N = 1)')
+  ap.add_argument('--strong-n', type=int, default=2048,
+                  help='size of the fixed symmetric Gram of the `strong` record (0 = skip)')
+  ap.add_argument('--full-n', type=int, default=10000,
+                  help='with >= 8 ranks also run BASELINE configs[3] (N x N symmetric Myrtle-10) at this size (0 = skip)')
   ap.add_argument('--symmetric', action='store_true',
                   help='time K(x1, x1) (x2=None): triangle + mirror; needs a square --block')
   ap.add_argument('--per-layer', action='store_true',

@@ -177,6 +177,47 @@ def _serial_kernel_blocks(kernel_fn, k: Kernel, n1_bs, n2_bs, args, kwargs):
   return _stitch(blocks, cov2_is_none, n1, n2)
 
 
+def _symmetric_multi_device(kernel_fn, x, get, D):
+  """`kernel_fn(x, None, get)` over D GPUs of this process: the triangular folded-cyclic schedule of
+  `distributed.sym_schedule`, one host thread per device, mirrored on the host."""
+  from . import distributed, stax
+  names = (get,) if isinstance(get, str) else tuple(n.lower() for n in get)
+  n = x.shape[0]
+  sched = distributed.sym_schedule(n, D, distributed.sym_block_rows(n, D))
+  out = {nm: None for nm in names}
+  errs = []
+
+  def work(dev):
+    try:
+      with _lib.device_scope(dev):
+        for start, stop, r in sched:
+          if r != dev:
+            continue
+          res = stax._sym_rows(kernel_fn, x, start, stop, names)
+          for nm in names:
+            out[nm][start:stop, start:] = res[nm]
+    except BaseException as e:   # re-raised on the calling thread
+      errs.append(e)
+
+  from ._config import config
+  for nm in names:
+    out[nm] = np.empty((n, n), config.dtype)
+  threads = [threading.Thread(target=work, args=(d,)) for d in range(D)]
+  for t in threads:
+    t.start()
+  for t in threads:
+    t.join()
+  if errs:
+    raise errs[0]
+  for nm in names:
+    m = out[nm]
+    il = np.tril_indices(n, -1)
+    m[il] = m.T[il]
+  if isinstance(get, str):
+    return out[names[0]]
+  return stax._namedtuple(names)(*(out[nm] for nm in names))
+
+
 def batch(kernel_fn: Callable, batch_size: int = 0, device_count: int = -1,
           store_on_device: bool = True) -> Callable:
   """Returns a function that computes a kernel in batches over all devices.
@@ -239,6 +280,11 @@ def batch(kernel_fn: Callable, batch_size: int = 0, device_count: int = -1,
     n_per_dev, d_eff = _get_n_per_device(n1, D)
     # x2 (or x1 itself when x2 is None) is shared by every device; rows are split in slabs.
     x2_is_none = x2 is None and not is_kernel
+    if x2_is_none and d_eff > 1 and _native_matrix_output(kernel_fn, x1_or_kernel, get) and not args[1:] and \
+        not (set(kwargs) - {'get'}):
+      # K(x, x) on several GPUs: only the upper triangle is computed (the reference's TODO,
+      # `_src/batching.py:370`), row blocks dealt to the devices in folded cyclic order for balance
+      return _symmetric_multi_device(kernel_fn, x1_or_kernel, get, d_eff)
     x2_full = x1_or_kernel if x2_is_none else x2
     outs = [None] * d_eff
     threads = []
@@ -287,32 +333,51 @@ def gram_to_disk(kernel_fn: Callable, x1: np.ndarray, x2, get, out_dir: str, blo
   if block_rows <= 0:
     raise ValueError('block_rows must be positive.')
   os.makedirs(out_dir, exist_ok=True)
+  import hashlib
+  from ._config import config
   n1 = x1.shape[0]
   n2 = n1 if x2 is None else x2.shape[0]
-  manifest = {'n1': int(n1), 'n2': int(n2), 'get': list(names), 'block_rows': int(block_rows)}
+  symmetric = x2 is None
+
+  def digest(a):
+    return None if a is None else hashlib.sha1(np.ascontiguousarray(a).view(np.uint8)).hexdigest()
+  spec = getattr(kernel_fn, '_spec', None)
+  manifest = {'n1': int(n1), 'n2': int(n2), 'get': list(names), 'block_rows': int(block_rows),
+              'symmetric': bool(symmetric), 'dtype': np.dtype(config.dtype).name if spec is not None else None,
+              'x1_sha1': digest(x1), 'x2_sha1': digest(x2),
+              'network_sha1': None if spec is None else hashlib.sha1(repr(spec).encode()).hexdigest()}
   mpath = os.path.join(out_dir, 'manifest.json')
   if os.path.exists(mpath):
     old = json.load(open(mpath))
-    if any(old.get(k) != manifest[k] for k in ('n1', 'n2', 'get', 'block_rows')):
-      raise ValueError(f'{out_dir} holds a different computation ({old}); refusing to mix slabs.')
+    if any(old.get(k) != v for k, v in manifest.items()):
+      diff = sorted(k for k, v in manifest.items() if old.get(k) != v)
+      raise ValueError(f'{out_dir} holds a different computation (differs in {diff}); refusing to mix slabs.')
   else:
     with open(mpath, 'w') as f:
       json.dump(manifest, f)
-  x2e = x1 if x2 is None else x2
+  native_sym = symmetric and _native_matrix_output(kernel_fn, x1, get)
 
   def slab_path(name, r0):
     return os.path.join(out_dir, f'{name}.slab{r0:09d}.npy')
 
+  # x2 = None: a slab holds only the columns [r0, n2) of its rows (upper trapezoid; the rest is mirrored at
+  # assembly time), i.e. half the work of the reference's full square (`_src/batching.py:370`).
   for r0 in range(0, n1, block_rows):
     r1 = min(n1, r0 + block_rows)
     if all(os.path.exists(slab_path(n, r0)) for n in names):
       continue                                                  # finished in an earlier run
-    res = kernel_fn(x1[r0:r1], x2e, names if len(names) > 1 else names[0])
-    vals = [res] if len(names) == 1 else [getattr(res, n) for n in names]
+    c0 = r0 if symmetric else 0
+    if native_sym:
+      from . import stax
+      d = stax._sym_rows(kernel_fn, x1, r0, r1, names)
+      vals = [d[n] for n in names]
+    else:
+      res = kernel_fn(x1[r0:r1], x1[c0:] if symmetric else x2, names if len(names) > 1 else names[0])
+      vals = [res] if len(names) == 1 else [getattr(res, n) for n in names]
     for n, v in zip(names, vals):
       v = np.asarray(v)
-      if v.shape != (r1 - r0, n2):
-        raise ValueError(f'`{n}` of rows [{r0}, {r1}) has shape {v.shape}, expected {(r1 - r0, n2)}.')
+      if v.shape != (r1 - r0, n2 - c0):
+        raise ValueError(f'`{n}` of rows [{r0}, {r1}) has shape {v.shape}, expected {(r1 - r0, n2 - c0)}.')
       tmp = slab_path(n, r0) + '.tmp.npy'
       np.save(tmp, v)
       os.replace(tmp, slab_path(n, r0))                         # atomic: a slab file is always complete
@@ -323,8 +388,17 @@ def gram_to_disk(kernel_fn: Callable, x1: np.ndarray, x2, get, out_dir: str, blo
     full_path = os.path.join(out_dir, f'{n}.npy')
     full = np.lib.format.open_memmap(full_path, mode='w+', dtype=first.dtype, shape=(n1, n2))
     for r0 in range(0, n1, block_rows):
-      s = np.load(slab_path(n, r0), mmap_mode='r')
-      full[r0:r0 + s.shape[0]] = s
+      sl = np.load(slab_path(n, r0), mmap_mode='r')
+      rows = sl.shape[0]
+      if symmetric:
+        iu = np.triu_indices(rows)                              # entries (i, j >= i) of the leading square are valid
+        sq = np.array(sl[:, :rows])
+        sq.T[iu] = sq[iu]                                       # mirror inside the diagonal block
+        full[r0:r0 + rows, r0:r0 + rows] = sq
+        full[r0:r0 + rows, r0 + rows:] = sl[:, rows:]
+        full[r0 + rows:, r0:r0 + rows] = sl[:, rows:].T         # mirror below the diagonal block
+      else:
+        full[r0:r0 + rows] = sl
     full.flush()
     del full
     outs.append(np.load(full_path, mmap_mode='r'))

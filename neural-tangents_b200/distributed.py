@@ -134,12 +134,13 @@ def init(rank=None, world=None, local_rank=None, unique_id: bytes = None):
   local_rank = int(os.environ.get('LOCAL_RANK', str(rank))) if local_rank is None else local_rank
   ctx = _lib.get_context(local_rank)
   config.update('device', local_rank)
+  tag = None
   if unique_id is None:
     tag = '{}_{}_{}'.format(os.environ.get('MASTER_PORT', '0'), os.environ.get('TORCHELASTIC_RUN_ID', 'run'),
                             os.getppid())
     unique_id = _file_rendezvous(rank, world, tag)
   _default = DeviceBackend(_lib.Comm(ctx, unique_id, rank, world))
-  if rank == 0 and world > 1:
+  if rank == 0 and tag is not None:
     # every rank has read the id once the communicator exists (ncclCommInitRank is collective)
     try:
       os.remove(os.path.join(os.environ.get('NTK_B200_RENDEZVOUS_DIR', '/tmp'), f'ntk_b200_nccl_{tag}.id'))
@@ -205,16 +206,33 @@ class DeviceBackend:
     d.free()
     return [int(v) for v in buf]
 
-  def upload(self, x, shape, dtype, src):
-    """`x` (given on `src`) in every rank's HBM."""
+  def put(self, x, shape, dtype, src):
+    """Device array of `shape` on every rank; rank `src` fills it from the host array `x` (H2D)."""
     d = DeviceArray(self.ctx, shape, dtype)
-    keep = None
     if self.rank == src:
       keep = self.ctx.h2d(d.ptr, np.ascontiguousarray(x, dtype))
-    self.comm.broadcast(d.ptr, d.nbytes, src)
-    if keep is not None:
       self.ctx.synchronize()       # the pageable source must outlive the copy
+      del keep
     return d
+
+  def broadcast(self, d, src):
+    """`d` of rank `src` into every rank's `d`, device to device over NVLink."""
+    self.comm.broadcast(d.ptr, d.nbytes, src)
+
+  def all_gather_host(self, values):
+    """Small host vector of float64 from every rank -> [world, len] (timings: max over ranks)."""
+    v = np.ascontiguousarray(values, np.float64)
+    s = DeviceArray(self.ctx, v.shape, v.dtype)
+    r = DeviceArray(self.ctx, (self.world,) + v.shape, v.dtype)
+    self.ctx.h2d(s.ptr, v)
+    self.comm.all_gather(s.ptr, r.ptr, s.nbytes)
+    out = self.ctx.d2h(np.empty(r.shape, np.float64), r.ptr)
+    s.free()
+    r.free()
+    return out
+
+  def barrier(self):
+    self.all_gather_host([0.0])
 
   def alloc(self, shape, dtype):
     return DeviceArray(self.ctx, shape, dtype)
@@ -266,7 +284,7 @@ class DeviceBackend:
     keep = self.ctx.h2d(ro.ptr, row_of)
     out = DeviceArray(self.ctx, (n, n), slabs.dtype)
     _lib.sym_assemble(self.ctx, slabs.dtype, slabs.ptr, slabs.shape[1], ro.ptr, n, out.ptr, n)
-    self.ctx.synchronize()
+    self.ctx.synchronize()         # `row_of` and the gathered slabs are released by the caller right after
     del keep
     ro.free()
     return out
@@ -296,6 +314,48 @@ def _result(get, names, vals):
   return collections.namedtuple('AnalyticKernel', names)(*vals)
 
 
+def gram_resident(be, plan, d1, d2, names, src=0, gather=True, block_rows=None, broadcast=True):
+  """The device-resident core: `d1` / `d2` (None: symmetric) are device arrays on every rank, filled on rank
+  `src`.  Broadcast (NCCL), per-rank blocks (`ntk_gram_device`), all-gather, symmetric assembly.  Returns
+  {name: device array}; everything is enqueued on the rank's context stream and the call returns without a
+  host synchronisation of the results."""
+  dt = d1.dtype
+  n1 = d1.shape[0]
+  if broadcast and be.world > 1:
+    be.broadcast(d1, src)
+    if d2 is not None:
+      be.broadcast(d2, src)
+  if d2 is None:
+    n = n1
+    block = block_rows or sym_block_rows(n, be.world)
+    sched = sym_schedule(n, be.world, block)
+    rows_pad, row_of, local = sym_layout(sched, be.world)
+    slabs = {nm: be.alloc((rows_pad, n), dt) for nm in names}
+    for start, stop, l0 in local[be.rank]:
+      be.gram_block(plan, d1, start, stop, d1, start, slabs, l0, start, upper=True)
+    if not gather:
+      return slabs
+    outs = {}
+    for nm in names:
+      g = be.all_gather(slabs[nm]) if be.world > 1 else slabs[nm]
+      outs[nm] = be.sym_assemble(g, row_of, n)
+      if g is not slabs[nm]:
+        be.free(g)
+      be.free(slabs[nm])
+    return outs
+  n2 = d2.shape[0]
+  lo, hi = row_partition(n1, be.world, be.rank)
+  slabs = {nm: be.alloc((hi - lo, n2), dt) for nm in names}
+  be.gram_block(plan, d1, lo, hi, d2, 0, slabs, 0, 0, upper=False)
+  if not gather or be.world == 1:
+    return slabs
+  outs = {}
+  for nm in names:
+    outs[nm] = be.all_gather(slabs[nm])
+    be.free(slabs[nm])
+  return outs
+
+
 def gram(kernel_fn, x1, x2=None, get=('nngp', 'ntk'), backend=None, src=0, gather=True, to_host=True,
          block_rows=None):
   """`kernel_fn(x1, x2, get)` with the Gram rows partitioned over the ranks of `backend` (default: the
@@ -319,41 +379,11 @@ def gram(kernel_fn, x1, x2=None, get=('nngp', 'ntk'), backend=None, src=0, gathe
   nd = meta[0]
   shape1 = tuple(meta[1:1 + nd])
   has_x2, n2 = bool(meta[1 + nd]), meta[2 + nd]
-  n1 = shape1[0]
   plan = be.resolve(kernel_fn, shape1)
-  symmetric = not has_x2
-
-  d1 = be.upload(x1, shape1, dt, src)
-  d2 = be.upload(x2, (n2,) + shape1[1:], dt, src) if has_x2 else None
+  d1 = be.put(x1, shape1, dt, src)
+  d2 = be.put(x2, (n2,) + shape1[1:], dt, src) if has_x2 else None
   try:
-    if symmetric:
-      n = n1
-      block = block_rows or sym_block_rows(n, be.world)
-      sched = sym_schedule(n, be.world, block)
-      rows_pad, row_of, local = sym_layout(sched, be.world)
-      slabs = {nm: be.alloc((rows_pad, n), dt) for nm in names}
-      for start, stop, l0 in local[be.rank]:
-        be.gram_block(plan, d1, start, stop, d1, start, slabs, l0, start, upper=True)
-      if not gather:
-        outs = slabs
-      else:
-        outs = {}
-        for nm in names:
-          g = be.all_gather(slabs[nm])
-          outs[nm] = be.sym_assemble(g, row_of, n)
-          be.free(g)
-          be.free(slabs[nm])
-    else:
-      lo, hi = row_partition(n1, be.world, be.rank)
-      slabs = {nm: be.alloc((hi - lo, n2), dt) for nm in names}
-      be.gram_block(plan, d1, lo, hi, d2, 0, slabs, 0, 0, upper=False)
-      if not gather:
-        outs = slabs
-      else:
-        outs = {}
-        for nm in names:
-          outs[nm] = be.all_gather(slabs[nm])
-          be.free(slabs[nm])
+    outs = gram_resident(be, plan, d1, d2, names, src=src, gather=gather, block_rows=block_rows)
     be.synchronize()
   finally:
     be.free(d1)

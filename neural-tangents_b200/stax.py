@@ -330,6 +330,7 @@ def _make_kernel_fn(spec, req):
     if kwargs:
       raise NotImplementedError(f'unsupported kernel_fn arguments: {sorted(kwargs)}')
 
+    _warn_fan_in(spec)
     if isinstance(x1_or_kernel, Kernel) and x2 is None:
       out = _apply_to_kernel(spec, x1_or_kernel)
     else:
@@ -417,6 +418,26 @@ def _apply_to_inputs(spec, x1, x2, get_c):
       is_reversed=m.is_reversed if out_spatial else False, is_input=False, diagonal_batch=True,
       diagonal_spatial=False, shape1=tuple(shape1), shape2=tuple(shape2), batch_axis=0,
       channel_axis=len(shape1) - 1, mask1=None, mask2=None)
+
+
+def _sym_rows(kernel_fn, x, r0, r1, names):
+  """Rows [r0, r1) of the symmetric Gram K(x, x), columns [r0, n) only: `{name: [r1 - r0, n - r0]}` with the
+  entries (i, j < i) of the leading square unspecified (NTK_FLAG_UPPER_ONLY; the reference computes the full
+  square, `_src/batching.py:370`).  `kernel_fn` must come from this module and produce [n1, n2] matrices."""
+  spec = kernel_fn._spec
+  dt = config.dtype
+  xs = np.ascontiguousarray(x[r0:], dt)
+  spatial = x.ndim == 4
+  H, W = (x.shape[1], x.shape[2]) if spatial else (0, 0)
+  low = _lowered(_strip(spec), False, False, spatial)
+  oh, ow, _ = low.program.output_shape(H, W)
+  if oh > 0:
+    raise NotImplementedError('row slabs of a symmetric Gram need [n1, n2] matrix outputs')
+  flags = (_lib.FLAG_UPPER_ONLY | (_lib.FLAG_NO_FUSION if config.disable_fusion else 0) |
+           (_lib.FLAG_PER_LAYER if config.per_layer else 0))
+  res = _lib.gram_host(_lib.get_context(), low.program, xs[:r1 - r0], xs, H, W, x.shape[-1], flags, 0, 0,
+                       'ntk' in names, False)
+  return {n: res[n] for n in names}
 
 
 def _apply_to_kernel(spec, k: Kernel):
@@ -637,6 +658,18 @@ def FanInSum():
   layer = _layer(('faninsum',), init_fn, apply_fn)
   layer[2]._warning = warn
   return layer
+
+
+def _warn_fan_in(spec):
+  """`_src/stax/branching.py:405-410`: every FanIn layer warns that its inputs are assumed independent."""
+  import warnings
+
+  def has(sp):
+    return sp[0] == 'faninsum' or (sp[0] in ('serial', 'parallel') and any(has(c) for c in sp[1]))
+  if has(spec):
+    warnings.warn('`FanIn` layers assume independent inputs which is not verified in the code. '
+                  'Please make sure to have at least one `Dense` / `Conv` / `GlobalSelfAttention` '
+                  'etc. layer in each branch.')
 
 
 # ----------------------------------------------------------------------------

@@ -39,13 +39,13 @@ class GlooBackend:
     dist.broadcast(t, src=src)
     return [int(v) for v in t]
 
-  def upload(self, x, shape, dtype, src):
+  def put(self, x, shape, dtype, src):
+    return np.array(x, dtype) if self.rank == src else np.zeros(shape, dtype)
+
+  def broadcast(self, d, src):
     import torch
     import torch.distributed as dist
-    a = np.ascontiguousarray(x, dtype) if self.rank == src else np.zeros(shape, dtype)
-    t = torch.from_numpy(a)
-    dist.broadcast(t, src=src)
-    return t.numpy()
+    dist.broadcast(torch.from_numpy(d), src=src)     # in place (shares memory with the NumPy array)
 
   def alloc(self, shape, dtype):
     return np.full(shape, np.nan, dtype)

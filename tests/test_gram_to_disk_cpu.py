@@ -69,3 +69,38 @@ def test_gram_to_disk_symmetric_single_get(tmp_path):
   np.testing.assert_array_equal(out, ref)
   with pytest.raises(ValueError):
     b.gram_to_disk(make_kernel([]), x, None, (), str(tmp_path / 'e'))
+
+
+def test_gram_to_disk_symmetric_computes_only_the_upper_trapezoids(tmp_path):
+  """x2 = None: slab r0 holds columns [r0, n) only (half the work of the reference's full square,
+  `_src/batching.py:370`); the assembled matrix is mirrored; ragged last slab."""
+  b = _batching()
+  x = np.random.default_rng(2).standard_normal((23, 6))
+  shapes = []
+
+  def kernel_fn(x1, x2=None, get=None):
+    shapes.append((len(x1), len(x2)))
+    k = x1 @ x2.T
+    # poison what the schedule declares unneeded: the strictly lower part of the leading square
+    k[np.tril_indices(len(x1), -1)] = np.nan
+    return AK(k, 2 * k)
+  out = b.gram_to_disk(kernel_fn, x, None, ('nngp', 'ntk'), str(tmp_path), block_rows=10)
+  assert shapes == [(10, 23), (10, 13), (3, 3)]
+  np.testing.assert_allclose(out.nngp, x @ x.T, rtol=1e-13)
+  np.testing.assert_allclose(out.ntk, 2 * (x @ x.T), rtol=1e-13)
+  assert sum(a * c for a, c in shapes) < 0.7 * 23 * 23
+
+
+def test_gram_to_disk_refuses_other_data_of_the_same_shape(tmp_path):
+  """The manifest fingerprints the inputs: re-running in the same directory with different data of identical
+  sizes must not silently reuse stale slabs."""
+  b = _batching()
+  rng = np.random.default_rng(3)
+  x1, x2 = rng.standard_normal((8, 3)), rng.standard_normal((4, 3))
+  b.gram_to_disk(make_kernel([]), x1, x2, 'nngp', str(tmp_path), block_rows=4)
+  m = json.load(open(tmp_path / 'manifest.json'))
+  assert len(m['x1_sha1']) == 40 and m['symmetric'] is False
+  with pytest.raises(ValueError, match='x1_sha1'):
+    b.gram_to_disk(make_kernel([]), x1 + 1.0, x2, 'nngp', str(tmp_path), block_rows=4)
+  with pytest.raises(ValueError, match='x2_sha1'):
+    b.gram_to_disk(make_kernel([]), x1, x2 * 2.0, 'nngp', str(tmp_path), block_rows=4)

@@ -313,3 +313,37 @@ def test_batch_device_count_one_context_per_device(nt):
     if n_ctx is None:
       n_ctx = len(_lib._contexts)
     assert len(_lib._contexts) == n_ctx <= max(D, 1) + 1
+
+
+def test_gram_to_disk_on_gpu_symmetric_trapezoids(nt, tmp_path):
+  """SURVEY §8f row 2 on the GPU: restartable slab-by-slab symmetric Gram; slabs are NTK_FLAG_UPPER_ONLY
+  trapezoids; the assembled matrices equal the one-call result and the oracle."""
+  from neural_tangents_b200.batching import gram_to_disk
+  from oracle import ntk_oracle as O
+  spec = cases.myrtle(5)
+  _, _, kernel_fn = cases.build(spec, nt.stax)
+  x = np.random.default_rng(12).standard_normal((7, 32, 32, 3)).astype(np.float32)
+  out = gram_to_disk(kernel_fn, x, None, ('nngp', 'ntk'), str(tmp_path), block_rows=3)
+  one = kernel_fn(x, None, ('nngp', 'ntk'))
+  np.testing.assert_array_equal(np.asarray(out.nngp), one.nngp)
+  np.testing.assert_array_equal(np.asarray(out.ntk), one.ntk)
+  _check_sym(np.asarray(out.ntk), O.kernel_fn(spec, x, None, ('nngp', 'ntk'))[1], False)
+  again = gram_to_disk(kernel_fn, x, None, ('nngp', 'ntk'), str(tmp_path), block_rows=3)   # nothing recomputed
+  np.testing.assert_array_equal(np.asarray(again.ntk), one.ntk)
+  with pytest.raises(ValueError, match='x1_sha1'):
+    gram_to_disk(kernel_fn, x + 1, None, ('nngp', 'ntk'), str(tmp_path), block_rows=3)
+
+
+def test_batch_symmetric_over_two_devices_is_triangular(nt):
+  """`batch(device_count=2)(x, None)`: the triangular folded-cyclic schedule inside one process."""
+  from neural_tangents_b200 import _lib
+  if _lib.device_count() < 2:
+    pytest.skip('needs two GPUs')
+  spec = cases.myrtle(5)
+  _, _, kernel_fn = cases.build(spec, nt.stax)
+  x = np.random.default_rng(13).standard_normal((8, 32, 32, 3)).astype(np.float32)
+  one = kernel_fn(x, None, ('nngp', 'ntk'))
+  two = nt.batch(kernel_fn, batch_size=2, device_count=2)(x, None, ('nngp', 'ntk'))
+  np.testing.assert_array_equal(two.nngp, one.nngp)
+  np.testing.assert_array_equal(two.ntk, one.ntk)
+  np.testing.assert_array_equal(nt.batch(kernel_fn, batch_size=2, device_count=2)(x, None, 'ntk'), one.ntk)
