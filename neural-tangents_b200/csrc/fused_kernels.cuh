@@ -85,8 +85,6 @@ struct StageArgs {
   T in_scale;     // FROM_X: alpha_1 / C folded into x1
   T epi_scale;    // POOL: alpha_next/16; GAP: 1/S^4; STORE: unused (folded in coef)
   FLayer<T> lp[kMaxFusedLayers];
-  unsigned long long gtex;  // packed kernels with the texture-interpolated angle function (stage_packed.cuh): the
-                            // cudaTextureObject_t of this device's -G / sigma table; filled in by the launcher
 };
 
 // Upper-triangular pair enumeration of a W x W block: row l holds the W - l pairs (l, l..W-1)

@@ -1,9 +1,6 @@
 // Instantiations + launcher of the packed-FP32 stage kernel (stage_packed.cuh): fp32, 32x32 and 16x16.
 // Compiled twice: as is (pure-ABRelu stages) and from stage_packed_erf.cu with NTK_PACKED_ERF = 1 (Erf-capable
 // instantiations, their own copy of the constant tables).
-#include <cmath>
-#include <mutex>
-
 #include "stage_packed.cuh"
 
 #ifndef NTK_PACKED_ERF
@@ -30,56 +27,13 @@ inline int variant() {
   return v;
 }
 
-// Per-device texture of the angle function for the VAR & 4 kernels (stage_packed.cuh: act_pair_tex):
-// T[i] = -G(i / sigma) / sigma with G(c) = acos(c) / sqrt(1 - c^2), G(1) = 1; linear filtering, clamped.
-constexpr int kMaxDevices = 64;
-cudaTextureObject_t g_gtex[kMaxDevices] = {0};
-std::mutex g_gtex_mu;
-
-int gtex_for_current_device(unsigned long long* out) {
-  int dev = 0;
-  NTK_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= kMaxDevices) return fail(NTK_EINVAL, "device %d out of range", dev);
-  std::lock_guard<std::mutex> lock(g_gtex_mu);
-  if (!g_gtex[dev]) {
-    std::vector<float> t(kGTexN);
-    for (int i = 0; i < kGTexN; ++i) {
-      const double c = (double)i / (double)(kGTexN - 1);
-      const double g = c < 1.0 ? acos(c) / sqrt((1.0 - c) * (1.0 + c)) : 1.0;
-      t[i] = (float)(-g / (double)kGTexSigma);
-    }
-    cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
-    cudaArray_t arr = nullptr;
-    NTK_CUDA(cudaMallocArray(&arr, &desc, kGTexN, 0));
-    NTK_CUDA(cudaMemcpy2DToArray(arr, 0, 0, t.data(), kGTexN * sizeof(float), kGTexN * sizeof(float), 1,
-                                 cudaMemcpyHostToDevice));
-    cudaResourceDesc res;
-    memset(&res, 0, sizeof(res));
-    res.resType = cudaResourceTypeArray;
-    res.res.array.array = arr;
-    cudaTextureDesc td;
-    memset(&td, 0, sizeof(td));
-    td.addressMode[0] = cudaAddressModeClamp;
-    td.filterMode = cudaFilterModeLinear;
-    td.readMode = cudaReadModeElementType;
-    td.normalizedCoords = 0;
-    cudaTextureObject_t tex = 0;
-    NTK_CUDA(cudaCreateTextureObject(&tex, &res, &td, nullptr));
-    g_gtex[dev] = tex;
-  }
-  *out = (unsigned long long)g_gtex[dev];
-  return NTK_OK;
-}
-
 template <int S, int L, int IN, int EPI, bool NTK, int CIN, bool RC, int LAG = 1, int MINB = 2, bool Q2P = true,
           int VAR = 0>
-int launch_p_impl(cudaStream_t stream, int64_t* launches, const StageArgs<float>& a0) {
+int launch_p_impl(cudaStream_t stream, int64_t* launches, const StageArgs<float>& a) {
   using G = PGeom<S>;
   auto kern = k_stage_p<S, L, IN, EPI, NTK, CIN, RC, LAG, MINB, Q2P, NTK_PACKED_ERF != 0, VAR>;
   const size_t smem = stage_p_smem_bytes<S, L, IN, EPI, NTK, CIN, Q2P>();
   NTK_TRY(ensure_dynamic_smem((const void*)kern, smem));
-  StageArgs<float> a = a0;
-  if (VAR & 4) NTK_TRY(gtex_for_current_device(&a.gtex));
   const long long blocks = (a.P + G::GROUPS - 1) / G::GROUPS;
   (*launches)++;
   kern<<<(unsigned)blocks, G::NT, smem, stream>>>(a);
@@ -116,23 +70,15 @@ int launch_p_epi(cudaStream_t stream, int64_t* launches, int epi, const StageArg
       // Measured on B200 for the dominant kernel: 38.43 -> 37.07 ms per 9216 pairs, results bit-identical
       // (profiles/check_variant.py), so it is the default whenever the stage has no bias; NTK_B200_PVAR=7 forces
       // the general instantiation for A/B runs.
-      // VAR bit 0 = degree-7 fit of G (NTK_B200_PVAR=4, or 6 together with bit 1): a round-2 candidate, NOT measured
-      // (SASS: 68.0 / 65.4 register words per element-layer against 70.3 / 67.3); the self-pair runs keep the degree-8
-      // kernel, so it gives up the exact duplicate-pair diagonal.
+      // VAR bit 0 = degree-7 fit of G (NTK_B200_PVAR=4, or 6 together with bit 1).  Measured in round 2 on B200
+      // (bench lines of the same box, 5 steps): default 37.10 ms | PVAR=6 36.60 ms (-1.3 %) | PVAR=2 (3 CTAs / SM,
+      // planar q2) 37.81 | PVAR=7 (with bias adds) 38.46 | PVAR=4 38.37.  1.3 % does not pay for 5x the error of G and the
+      // loss of the exact duplicate-pair diagonal (the self-pair runs keep the degree-8 kernel): not the default.
       if constexpr (!NTK_PACKED_ERF && L == 3 && IN == IN_FROM_X && NTK && S == 32) {
         const bool no_bias = a.lp[0].bias == 0.f && a.lp[1].bias == 0.f && a.lp[2].bias == 0.f;
         if (variant() == 4) return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false, 1, 2, true, 1>(stream, launches, a);
         if (variant() == 6 && no_bias)
           return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false, 1, 2, true, 3>(stream, launches, a);
-        // VAR bit 2 = texture-interpolated G (act_pair_tex), round-2 candidates: LAG 1 / 2, 2 / 3 CTAs per SM
-        if (variant() == 10 && no_bias)
-          return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false, 1, 2, true, 6>(stream, launches, a);
-        if (variant() == 11 && no_bias)
-          return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false, 2, 2, true, 6>(stream, launches, a);
-        if (variant() == 12 && no_bias)
-          return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false, 1, 3, true, 6>(stream, launches, a);
-        if (variant() == 13 && no_bias)
-          return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false, 2, 3, true, 6>(stream, launches, a);
         if (variant() != 7 && no_bias)
           return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false, 1, 2, true, 2>(stream, launches, a);
       }

@@ -127,49 +127,9 @@ __device__ __forceinline__ void act_pair(float2 K, float2 U, float2 q1, float2 n
   if (NTK) Uo = __ffma2_rn(kd, U, Ko);
 }
 
-// ---- texture-interpolated angle function (VAR bit 2) ------------------------------------------------------
-// The degree-8 Horner chain of G is 8 of the ~20 packed instructions an element pair costs, and it is bound by
-// register-file reads (4 words per step).  The texture unit evaluates a piecewise-linear G in hardware instead:
-// one TEX per element on the otherwise idle texture pipe, with 1 register word of input.
-//   table    T[i] = -G(i / sigma) / sigma,  i = 0..sigma,  sigma = 2^13 intervals on [0, 1]  (32 KB, L1-resident)
-//   filter   linear, 8 fractional weight bits: |error| <= |T[i+1] - T[i]| / 512 + curvature = 2.4e-7 + 2e-9 in G
-//            (the degree-8 fit: 1.0e-7 + rounding; degree 7: 5.6e-7)
-//   scaling  the staged -q2 values are pre-multiplied by sigma^-2, an exact power of two, so that
-//            MUFU.RSQ(|q1 q2 sigma^-2|) = sigma / sqrt(q1 q2) IS the texel scale: the coordinate is one scalar FFMA,
-//            |K| * rb' + 0.5 (it replaces the FMUL of the polynomial path), and sin * G = (s rb') * T needs no rescale.
-//            K^2 - q1 q2 is fma(np', sigma^2, K^2): a power-of-two scale is exact, so the sum is rounded once exactly
-//            like the FADD it replaces and an exact-duplicate pair still gives exactly 0.
-constexpr int kGTexLog2 = 13;
-constexpr int kGTexN = (1 << kGTexLog2) + 1;                  // texels
-constexpr float kGTexSigma = (float)(1 << kGTexLog2);
-constexpr float kGTexSigma2 = kGTexSigma * kGTexSigma;         // 2^26
-constexpr float kGTexInvSigma2 = 1.f / kGTexSigma2;
-
-template <bool NTK>
-__device__ __forceinline__ void act_pair_tex(float2 K, float2 U, float2 q1, float2 nq2s, float2 coef2, float2 hab2,
-                                             cudaTextureObject_t tex, float2& Ko, float2& Uo) {
-  const float2 nps = __fmul2_rn(q1, nq2s);                 // -(q1 q2) / sigma^2 (exact scaling of the rounded product)
-  const float2 kk = __fmul2_rn(K, K);
-  float2 d;
-  d.x = __fmaf_rn(nps.x, kGTexSigma2, kk.x);               // == K^2 - rn(q1 q2), rounded once
-  d.y = __fmaf_rn(nps.y, kGTexSigma2, kk.y);
-  float2 rbs, s;
-  rbs.x = rsq_fast(fabsf(nps.x));                          // sigma / sqrt(q1 q2)
-  rbs.y = rsq_fast(fabsf(nps.y));
-  s.x = sqrt_fast(fabsf(d.x));
-  s.y = sqrt_fast(fabsf(d.y));
-  const float2 sns = __fmul2_rn(s, rbs);                   // sigma * sin(theta)
-  float2 g;                                                // -G(|cos theta|) / sigma
-  g.x = tex1D<float>(tex, __fmaf_rn(fabsf(K.x), rbs.x, 0.5f));
-  g.y = tex1D<float>(tex, __fmaf_rn(fabsf(K.y), rbs.y, 0.5f));
-  const float2 u = __ffma2_rn(sns, g, f2s(kHalfPiF));
-  float2 us;
-  us.x = copysign_bits(u.x, K.x);
-  us.y = copysign_bits(u.y, K.y);
-  const float2 kd = __ffma2_rn(coef2, us, hab2);
-  Ko = __ffma2_rn(kd, K, __fmul2_rn(coef2, s));
-  if (NTK) Uo = __ffma2_rn(kd, U, Ko);
-}
+// Measured and rejected in round 2 (profiles/ab_variants_r02.log): G from the texture unit (piecewise-linear table,
+// one TEX per element instead of the 8-step Horner chain; 25.1 instead of 26.9 instructions per element-layer, same
+// accuracy) ran 2.8x SLOWER (103.8 vs 37.1 ms): fp32 filtered fetches run at ~1 texel / clk / SM on B200.
 
 // Erf on two elements (elementwise.py:67-112; erf_act_point in fused_kernels.cuh).  The q-map of an Erf layer
 // holds D = 1 + 2 b^2 q, so q1 = D1 and nq2 = -D2 here; with Kh = 2 b^2 K:
@@ -238,8 +198,7 @@ size_t stage_p_smem_bytes() {
 //   Q2P   q2 rows hold explicit (e, e+4) pairs (one LDS.64 per pair, 2x shared memory) or are planar
 //         (two LDS.32 per pair)
 //   ERF   the stage may contain Erf layers (runtime branch per layer); ERF = false carries no Erf code
-//   VAR   bit 2: the angle function G comes from the texture unit (act_pair_tex) instead of the degree-8 polynomial;
-//         bit 1: the convs have no bias (the predicated bias adds are compiled out; bit-identical results, used by
+//   VAR   bit 1: the convs have no bias (the predicated bias adds are compiled out; bit-identical results, used by
 //         default for the dominant kernel when b_std = 0); bit 0: degree-7 fit of G, an unmeasured round-2
 //         candidate reachable only through NTK_B200_PVAR (stage_packed.cu)
 template <int S, int L, int IN, int EPI, bool NTK, int CIN, bool RC, int LAG = 1, int MINB = 2, bool Q2P = true,
@@ -310,15 +269,14 @@ k_stage_p(const StageArgs<float> a) {
       }
     }
     // global q-maps: [n][L][S][S] x (q, 1/sqrt(q)); only q is used here.  A tiny floor keeps
-    // rsqrt(q1 q2) finite for all-zero receptive fields (K is 0 there, so the result is unchanged);
-    // 1e-12 leaves q1 q2 sigma^-2 a normal number in the texture variant.
-    constexpr float kQFloor = 1e-12f;
+    // rsqrt(q1 q2) finite for all-zero receptive fields (K is 0 there, so the result is unchanged).
+    constexpr float kQFloor = 1e-18f;
     const float2* g1 = reinterpret_cast<const float2*>(a.qm1) + (long long)si * L * S * S;
     const float2* g2 = reinterpret_cast<const float2*>(a.qm2) + (long long)sj * L * S * S;
     for (int e = tg; e < L * S * S; e += TPP) {
       const int w = e % S, row = e / S;
       q1A[row * S + perm8(w)] = fmaxf(__ldg(&g1[e].x), kQFloor);
-      const float nq = -fmaxf(__ldg(&g2[e].x), kQFloor) * ((VAR & 4) ? kGTexInvSigma2 : 1.f);
+      const float nq = -fmaxf(__ldg(&g2[e].x), kQFloor);
       if (Q2P) {
         q2B[(row * S + w) * 2] = nq;
         q2B[(row * S + ((w + S - 4) % S)) * 2 + 1] = nq;
@@ -507,8 +465,6 @@ k_stage_p(const StageArgs<float> a) {
           }
           if (ERF && a.lp[l].kind == ACT_ERF)
             act_pair_erf<NTK>(ck, cu, q1p[j], nq2, a.lp[l].e_in, a.lp[l].eA, a.lp[l].eT, a.lp[l].eC, BK[l][j], BU[l][j]);
-          else if (VAR & 4)
-            act_pair_tex<NTK>(ck, cu, q1p[j], nq2, coef2, hab2, (cudaTextureObject_t)a.gtex, BK[l][j], BU[l][j]);
           else
             act_pair<NTK, (VAR & 1) != 0>(ck, cu, q1p[j], nq2, coef2, hab2, BK[l][j], BU[l][j]);
         }
