@@ -54,11 +54,15 @@ enum {
   NTK_OP_ABRELU = 3,   /* `_src/stax/elementwise.py:423-477` f[0]=a f[1]=b, i[0]=do_stabilize           */
   NTK_OP_ERF = 4,      /* `_src/stax/elementwise.py:67-112`  f[0]=a f[1]=b f[2]=c                        */
   NTK_OP_AVGPOOL = 5,  /* `_src/stax/linear.py:1631-1664,3499-3572`
-                                                          i = {wh,ww,sh,sw,padding,normalize_edges}      */
-  NTK_OP_GAP = 6,      /* `_src/stax/linear.py:1771-1801`                                               */
+                                                          i = {wh,ww,sh,sw,padding,flags}: flags bit 0 =
+                                                          normalize_edges, bit 1 = SumPool (`:1503`, no division) */
+  NTK_OP_GAP = 6,      /* `_src/stax/linear.py:1771-1801`  i[0] = 1: GlobalSumPool (`:1674`)              */
   NTK_OP_FLATTEN = 7,  /* `_src/stax/linear.py:1865-1899`                                               */
   NTK_OP_FANINSUM = 8, /* `_src/stax/branching.py:55-117`  dst = src + src2                              */
-  NTK_OP_IDENTITY = 9  /* `_src/stax/linear.py:107-119`    dst = src (FanOut is expressed by slot reuse) */
+  NTK_OP_IDENTITY = 9, /* `_src/stax/linear.py:107-119`    dst = src (FanOut is expressed by slot reuse) */
+  NTK_OP_GELU = 10,    /* `_src/stax/elementwise.py:195-263`                                             */
+  NTK_OP_SIN = 11,     /* `_src/stax/elementwise.py:266-341` a sin(b x + c): f = {a, b, c} (Cos: c + pi/2) */
+  NTK_OP_RBF = 12      /* `_src/stax/elementwise.py:344-400` f[0] = gamma                                */
 };
 
 /* padding modes (`_src/stax/linear.py:54-69`) */

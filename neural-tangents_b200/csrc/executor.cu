@@ -18,6 +18,8 @@ NTK_FUSED_INSTANCES(extern, float)
 NTK_FUSED_INSTANCES(extern, double)
 NTK_FUSED_ERF_INSTANCES(extern, float)
 NTK_FUSED_ERF_INSTANCES(extern, double)
+NTK_FUSED_EMB_INSTANCES(extern, float)
+NTK_FUSED_EMB_INSTANCES(extern, double)
 NTK_RES_ERF_INSTANCES(extern, float)
 NTK_RES_ERF_INSTANCES(extern, double)
 NTK_RES_INSTANCES(extern, float)
@@ -194,7 +196,7 @@ int op_pool(Env& env, const ntk_op_t& op, const TState& in, TState& out, int t1,
   AxisGeom gh = axis_geom(in.H, wh, sh, pad), gw = axis_geom(in.W, ww, sw, pad);
   if (gh.out <= 0 || gw.out <= 0) return fail(NTK_EINVAL, "AvgPool output would be empty");
   PoolGeom g{in.H, in.W, gh.out, gw.out, wh, ww, sh, sw, gh.lo, gw.lo, pad == NTK_PAD_CIRCULAR,
-             (op.i[5] && pad == NTK_PAD_SAME) ? 1 : 0};
+             ((op.i[5] & 1) && pad == NTK_PAD_SAME) ? 1 : 0, (op.i[5] & 2) ? 1 : 0};
   const long long per_o = per_of(g.Ho, g.Wo);
   int st = NTK_OK;
   auto run = [&](Buf* src, long long P, Buf** dst) -> int {
@@ -238,7 +240,7 @@ int op_reduce(Env& env, const ntk_op_t& op, const TState& in, TState& out, int t
              in.H, in.W);
     else
       LAUNCH(env, (k_reduce_spatial<T, false>), grid, kThreads, 0, (const T*)src->p, (T*)o->p, P,
-             in.H, in.W);
+             in.H, in.W, op.i[0] == 1 ? 1 : 0);
     *dst = o;
     return NTK_OK;
   };
@@ -409,6 +411,9 @@ int run_ops(Env& env, const ntk_program& prog, std::vector<TState>& slots, int f
         break;
       case NTK_OP_ABRELU:
       case NTK_OP_ERF:
+      case NTK_OP_GELU:
+      case NTK_OP_SIN:
+      case NTK_OP_RBF:
         NTK_TRY(op_act<T>(env, op, in, out, steal, t1, t2));
         break;
       case NTK_OP_DENSE:
@@ -615,6 +620,9 @@ int validate_program(ntk_program& p) {
       case NTK_OP_DENSE:
       case NTK_OP_ABRELU:
       case NTK_OP_ERF:
+      case NTK_OP_GELU:
+      case NTK_OP_SIN:
+      case NTK_OP_RBF:
       case NTK_OP_GAP:
       case NTK_OP_FLATTEN:
       case NTK_OP_FANINSUM:
@@ -1048,6 +1056,9 @@ int ntk_program_output_shape(const ntk_program_t* prog, int32_t H, int32_t W,
         break;
       case NTK_OP_ABRELU:
       case NTK_OP_ERF:
+      case NTK_OP_GELU:
+      case NTK_OP_SIN:
+      case NTK_OP_RBF:
         if (!in.g) return fail(NTK_ENOTGAUSSIAN, "The input to the activation function must be Gaussian");
         o.g = false;
         break;

@@ -2,5 +2,6 @@
 #include "instantiate.cuh"
 namespace ntk {
 NTK_FUSED_ERF_INSTANCES(extern, float)
+NTK_FUSED_EMB_INSTANCES(extern, float)
 NTK_FUSED_INSTANCES(, float)
 }  // namespace ntk

@@ -2,5 +2,6 @@
 #include "instantiate.cuh"
 namespace ntk {
 NTK_FUSED_ERF_INSTANCES(extern, double)
+NTK_FUSED_EMB_INSTANCES(extern, double)
 NTK_FUSED_INSTANCES(, double)
 }  // namespace ntk

@@ -85,6 +85,9 @@ struct StageArgs {
   T in_scale;     // FROM_X: alpha_1 / C folded into x1
   T epi_scale;    // POOL: alpha_next/16; GAP: 1/S^4; STORE: unused (folded in coef)
   FLayer<T> lp[kMaxFusedLayers];
+  // EMB kernels: the RH x RW image sits in the top-left corner of the S x S shear (MNIST 28x28 in 32x32, any
+  // H, W <= 32); positions outside are cut off by the link masks and never reach a result.  RH == RW == S otherwise.
+  int RH, RW;
 };
 
 // Upper-triangular pair enumeration of a W x W block: row l holds the W - l pairs (l, l..W-1)
@@ -342,22 +345,25 @@ struct Vec2<double> {
 //   src_mode 0: diag0[h,w] = in_scale * sum_c x[h,w,c]^2      (FROM_X stages)
 //   src_mode 1: diag0[h,w] = selfK[n][ch=0][h][w][cw=0]        (sheared self-pair tensor)
 // ---------------------------------------------------------------------------------------
+// RH x RW: the real image size (<= S; the image sits in the top-left corner of the S x S map, see StageArgs).
 template <typename T, int S>
 __global__ void k_qmaps(const T* __restrict__ src, int src_mode, int C, T in_scale, int L,
-                        FLayer<T> l0, FLayer<T> l1, FLayer<T> l2, T* __restrict__ qm) {
+                        FLayer<T> l0, FLayer<T> l1, FLayer<T> l2, T* __restrict__ qm, int RH, int RW) {
   __shared__ T P[S * S];
   __shared__ T R[S * S];
   const int n = blockIdx.x;
   const FLayer<T> lp[3] = {l0, l1, l2};
   for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
     const int h = e / S, w = e % S;
-    T v;
-    if (src_mode == 0) {
-      const T* x = src + ((long long)n * S * S + e) * C;
-      v = mul_rn(mul_rn(x[0], in_scale), x[0]);
-      for (int c = 1; c < C; ++c) v = fma_t(mul_rn(x[c], in_scale), x[c], v);
-    } else {
-      v = src[(((long long)n * S + 0) * S + h) * S * S + (long long)w * S + 0];
+    T v = (T)0;
+    if (h < RH && w < RW) {
+      if (src_mode == 0) {
+        const T* x = src + ((long long)n * RH * RW + h * RW + w) * C;
+        v = mul_rn(mul_rn(x[0], in_scale), x[0]);
+        for (int c = 1; c < C; ++c) v = fma_t(mul_rn(x[c], in_scale), x[c], v);
+      } else {
+        v = src[(((long long)n * S + 0) * S + h) * S * S + (long long)w * S + 0];
+      }
     }
     P[e] = v;
   }
@@ -366,13 +372,13 @@ __global__ void k_qmaps(const T* __restrict__ src, int src_mode, int C, T in_sca
   for (int l = 0; l < L; ++l) {
     for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
       const int h = e / S, w = e % S;
-      const T mL = w > 0 ? (T)1 : (T)0, mR = w < S - 1 ? (T)1 : (T)0;
+      const T mL = (w > 0 && w < RW) ? (T)1 : (T)0, mR = w < RW - 1 ? (T)1 : (T)0;
       R[e] = hsum3<T>(P[h * S + (w > 0 ? w - 1 : w)], P[e], P[h * S + (w < S - 1 ? w + 1 : w)], mL, mR);
     }
     __syncthreads();
     for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
       const int h = e / S, w = e % S;
-      const T vU = h > 0 ? (T)1 : (T)0, vD = h < S - 1 ? (T)1 : (T)0;
+      const T vU = (h > 0 && h < RH) ? (T)1 : (T)0, vD = h < RH - 1 ? (T)1 : (T)0;
       const T q = vsum3<T>(R[(h > 0 ? h - 1 : h) * S + w], R[e], R[(h < S - 1 ? h + 1 : h) * S + w], vU,
                            vD, lp[l].bias);
       typename Vec2<T>::type o;
@@ -417,7 +423,10 @@ struct StageGeom {
 // the self-pair pipeline; the cross-pair kernels keep compile-time trip counts.
 // ERF: the stage may contain Erf layers (runtime branch per layer); ERF = false instantiations carry
 // no Erf code, so the ABRelu hot path is unchanged by it.
-template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN, int SH, bool RC, bool ERF>
+// EMB: the image is RH x RW <= S x S (StageArgs): staging, link masks and the GAP epilogue use the real size and
+// the vertical masks are computed instead of read from the constant tables (which hold RH == S).
+template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN, int SH, bool RC, bool ERF,
+          bool EMB = false>
 __global__ void __launch_bounds__(StageGeom<S, WPT, SH>::NT)
 k_stage(const StageArgs<T> a) {
   using G = StageGeom<S, WPT, SH>;
@@ -483,13 +492,29 @@ k_stage(const StageArgs<T> a) {
   {
     // the row part is loaded by the whole CTA when shared, else by its group
     const int rt = SHARED_ROW ? tid : tg, rn = SHARED_ROW ? G::NT : TPP;
-    if (IN == IN_FROM_X) {
+    if (IN == IN_FROM_X && !EMB) {
       const T* g1 = a.x1 + (long long)si * S * S * CIN;
       const T* g2 = a.x2 + (long long)sj * S * S * CIN;
       for (int e = rt; e < S * S * CIN; e += rn) x1s[e] = mul_rn(g1[e], a.in_scale);
       for (int e = tg; e < S * S; e += TPP) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) x2s[e * 4 + c] = c < CIN ? g2[e * CIN + c] : (T)0;
+      }
+    }
+    if (IN == IN_FROM_X && EMB) {  // [RH, RW, CIN] samples, zero outside
+      const T* g1 = a.x1 + (long long)si * a.RH * a.RW * CIN;
+      const T* g2 = a.x2 + (long long)sj * a.RH * a.RW * CIN;
+      for (int e = rt; e < S * S; e += rn) {
+        const int h = e / S, w = e % S;
+        const bool in = h < a.RH && w < a.RW;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) x1s[e * CIN + c] = in ? mul_rn(g1[(h * a.RW + w) * CIN + c], a.in_scale) : (T)0;
+      }
+      for (int e = tg; e < S * S; e += TPP) {
+        const int h = e / S, w = e % S;
+        const bool in = h < a.RH && w < a.RW;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) x2s[e * 4 + c] = (c < CIN && in) ? g2[(h * a.RW + w) * CIN + c] : (T)0;
       }
     }
     const V2* g1 = reinterpret_cast<const V2*>(a.qm1) + (long long)si * L * S * S;
@@ -545,11 +570,15 @@ k_stage(const StageArgs<T> a) {
   // lk[i]: link between w0+i-1 and w0+i is intact (both inside the image, w' does not wrap)
   T lk[WPT + 1];
   int off2[WPT];  // (w0 + i + cw) mod S (column of the second member), as a byte offset into a V2 row
+  const int RWc = EMB ? a.RW : S, RHc = EMB ? a.RH : S;
 #pragma unroll
   for (int i = 0; i <= WPT; ++i) {
     const int wl = w0 + i - 1, wr = w0 + i;
-    lk[i] = (wl >= 0 && wr <= S - 1 && ((wl + cw) % S) != S - 1) ? (T)1 : (T)0;
+    lk[i] = (wl >= 0 && wr <= RWc - 1 && ((wl + cw) % S) + 1 <= RWc - 1) ? (T)1 : (T)0;
   }
+  bool inw[WPT];  // EMB + GAP: element (w0 + i, w' = w0 + i + cw) lies inside the RW-wide image
+#pragma unroll
+  for (int i = 0; i < WPT; ++i) inw[i] = !EMB || (w0 + i < RWc && ((w0 + i + cw) % S) < RWc);
 #pragma unroll
   for (int i = 0; i < WPT; ++i) off2[i] = ((w0 + i + cw) % S) * (int)sizeof(V2);
   const unsigned q2base = (unsigned)__cvta_generic_to_shared(q2m);
@@ -657,8 +686,15 @@ k_stage(const StageArgs<T> a) {
       r_out = full_row(r_out < 0 ? 0 : (r_out > nrows - 1 ? nrows - 1 : r_out));
       const int ch = r_out / S, h = r_out % S;
       const int h2 = (h + ch) % S;
-      const float2 vm = vmask_at<S>(r_out);
-      const T vU = (T)vm.x, vD = (T)vm.y;
+      T vU, vD;
+      if (EMB) {
+        vU = (h > 0 && h2 > 0 && h < RHc && h2 < RHc) ? (T)1 : (T)0;
+        vD = (h + 1 < RHc && h2 + 1 < RHc) ? (T)1 : (T)0;
+      } else {
+        const float2 vm = vmask_at<S>(r_out);
+        vU = (T)vm.x;
+        vD = (T)vm.y;
+      }
       // ---- vertical taps of the two OLD rows first (last use of the oldest row) ----------
       T tk[WPT], tt[WPT];
 #pragma unroll
@@ -729,8 +765,10 @@ k_stage(const StageArgs<T> a) {
           }
         }
       } else if (EPI == EPI_GAP) {
+        const bool row_in = !EMB || (h < RHc && ((h + ch) % S) < RHc);
 #pragma unroll
         for (int i = 0; i < WPT; ++i) {
+          if (EMB && !(row_in && inw[i])) continue;
           gap_k = add_rn(gap_k, BK[L - 1][i]);
           if (NTK) gap_t = add_rn(gap_t, BT[L - 1][i]);
         }
@@ -872,13 +910,26 @@ struct FusedStage {
   double c[kMaxFusedLayers];          // Erf only
   int kind[kMaxFusedLayers] = {0};    // ACT_ABRELU | ACT_ERF
   int epi = EPI_STORE;  // what follows this chunk
+  // the pool behind this chunk (epi == EPI_POOL): SAME padding (== VALID on even sizes only) and
+  // SumPool (no division by the window, `_src/stax/linear.py:1503`: x16 for a 2x2 window on both members)
+  bool pool_same = false;
+  double pool_mul = 1.0;
 };
 
 struct FusedPlan {
   bool ok = false;
   std::vector<FusedStage> stages;    // chunks of <= 3 layers; resolution halves after EPI_POOL
   std::vector<ntk_op_t> dense_tail;  // Dense ops applied to the [n1,n2] result
+  // tail = `tail_pools` 2x2/2 pools, then GlobalAvgPool / GlobalSumPool / Flatten: a global mean times `tail_mul`
+  // (x16 per SumPool; GlobalSumPool multiplies by the final map size at run time)
+  int tail_pools = 0;
+  bool tail_flatten = false, tail_gsum = false, tail_same = false;
+  double tail_mul = 1.0;
 };
+
+// AvgPool / SumPool op flags: i[5] bit 0 = normalize_edges, bit 1 = SumPool; GAP: i[0] = 1 for GlobalSumPool
+inline bool pool_is_sum(const ntk_op_t& o) { return (o.i[5] & 2) != 0; }
+inline bool pool_normalize_edges(const ntk_op_t& o) { return (o.i[5] & 1) != 0; }
 
 // Recognises:  ([Conv3x3/1/SAME, ABRelu]+  AvgPool2x2/2?)+  (AvgPool2x2/2)* (GAP | Flatten@1x1)  Dense*
 inline FusedPlan plan_fused(const std::vector<ntk_op_t>& ops, int n_slots, int out_slot,
@@ -898,15 +949,19 @@ inline FusedPlan plan_fused(const std::vector<ntk_op_t>& ops, int n_slots, int o
   auto is_act = [](const ntk_op_t& o) { return (o.kind == NTK_OP_ABRELU && o.i[0] == 0) || o.kind == NTK_OP_ERF; };
   auto is_pool = [](const ntk_op_t& o) {
     return o.kind == NTK_OP_AVGPOOL && o.i[0] == 2 && o.i[1] == 2 && o.i[2] == 2 && o.i[3] == 2 &&
-           o.i[4] != NTK_PAD_CIRCULAR && !(o.i[4] == NTK_PAD_SAME && o.i[5]);
+           o.i[4] != NTK_PAD_CIRCULAR && !(o.i[4] == NTK_PAD_SAME && pool_normalize_edges(o) && !pool_is_sum(o));
   };
   int k = 0;
   int pending_pools = 0;  // pools seen after the last layer run
+  bool pend_same = false;
+  double pend_mul = 1.0;
   while (k < n) {
     if (!(is_conv(ops[k]) && k + 1 < n && is_act(ops[k + 1]))) break;
     if (!plan.stages.empty()) {
       if (pending_pools > 1) return FusedPlan();
       plan.stages.back().epi = pending_pools == 1 ? EPI_POOL : EPI_STORE;
+      plan.stages.back().pool_same = pend_same;
+      plan.stages.back().pool_mul = pend_mul;
     }
     // gather the run of conv+act layers and cut it into chunks of <= kMaxFusedLayers
     std::vector<std::pair<int, int>> run;
@@ -931,8 +986,12 @@ inline FusedPlan plan_fused(const std::vector<ntk_op_t>& ops, int n_slots, int o
       plan.stages.push_back(st);
     }
     pending_pools = 0;
+    pend_same = false;
+    pend_mul = 1.0;
     while (k < n && is_pool(ops[k])) {
       ++pending_pools;
+      pend_same = pend_same || ops[k].i[4] == NTK_PAD_SAME;
+      if (pool_is_sum(ops[k])) pend_mul *= 16.0;
       ++k;
     }
   }
@@ -948,37 +1007,54 @@ inline FusedPlan plan_fused(const std::vector<ntk_op_t>& ops, int n_slots, int o
     plan.dense_tail.push_back(ops[k]);
   }
   plan.ok = true;
-  // encode the tail requirement in an extra pseudo-stage field: L == 0 marker
+  plan.tail_pools = pending_pools;
+  plan.tail_flatten = flatten;
+  plan.tail_gsum = !flatten && ops[k - 1 - (int)plan.dense_tail.size()].i[0] == 1;
+  plan.tail_same = pend_same;
+  plan.tail_mul = pend_mul;
+  // L == 0 marker stage closes the list (keeps `stages.size() - 1` == number of real stages)
   FusedStage tail;
   tail.L = 0;
-  tail.epi = flatten ? 1 : 0;
-  tail.w2[0] = (double)pending_pools;
   plan.stages.push_back(tail);
   return plan;
 }
 
-inline int fused_final_size(const FusedPlan& plan, int S) {
-  for (size_t s = 0; s + 1 < plan.stages.size(); ++s)
-    if (plan.stages[s].epi == EPI_POOL) S /= 2;
-  return S;
+// Shear size of an H x W image: the smallest instantiated S in {8, 16, 32} that holds it (0: none).
+inline int fused_shear_size(int H, int W) {
+  const int m = H > W ? H : W;
+  return m <= 8 ? 8 : (m <= 16 ? 16 : (m <= 32 ? 32 : 0));
 }
+
+// Images that are not S x S RGB run the EMB family of the scalar stage kernels (pure ABRelu stages only).
+inline bool fused_needs_emb(int H, int W, int C) { return !(H == W && (H == 32 || H == 16 || H == 8) && C == 3); }
 
 template <typename T>
 bool fused_supported(const FusedPlan& plan, int H, int W, int C) {
-  if (!plan.ok || H != W) return false;
-  if (H != 32 && H != 16 && H != 8) return false;
-  if (C != 3) return false;  // FROM_X stages are instantiated for RGB inputs
-  int S = H;
+  if (!plan.ok || H < 1 || W < 1) return false;
+  int S = fused_shear_size(H, W);
+  if (S == 0) return false;
+  if (C != 3 && C != 1) return false;  // FROM_X stages are instantiated for grey and RGB inputs
+  const bool emb = fused_needs_emb(H, W, C);
+  int RH = H, RW = W;
   for (size_t s = 0; s + 1 < plan.stages.size(); ++s) {
-    if (plan.stages[s].epi == EPI_POOL) {
+    const FusedStage& st = plan.stages[s];
+    if (emb)
+      for (int l = 0; l < st.L; ++l)
+        if (st.kind[l] != ACT_ABRELU) return false;  // the EMB family carries no Erf code
+    if (st.epi == EPI_POOL) {
       if (S <= 8) return false;  // S = 4 stages are not instantiated
+      // VALID drops an odd last row (floor); SAME pads it with zeros the garbage outside the image cannot provide
+      if (st.pool_same && ((RH | RW) & 1)) return false;
+      if (RH < 2 || RW < 2) return false;
       S /= 2;
+      RH /= 2;
+      RW /= 2;
     }
   }
-  const FusedStage& tail = plan.stages.back();
-  const int pools = (int)tail.w2[0];
-  if (S % (1 << pools) != 0) return false;
-  if (tail.epi == 1 && (S >> pools) != 1) return false;  // Flatten needs a 1x1 map
+  // the tail pools + global reduction are computed as one global mean: every tail pool must tile the map exactly
+  const int pools = plan.tail_pools;
+  if (RH % (1 << pools) != 0 || RW % (1 << pools) != 0) return false;
+  if (plan.tail_flatten && ((RH >> pools) != 1 || (RW >> pools) != 1)) return false;  // Flatten needs a 1x1 map
   return true;
 }
 
@@ -999,10 +1075,11 @@ size_t stage_smem_bytes() {
   return (size_t)G::GROUPS * (xs1 + xs2 + 2 * qm + stg) * sizeof(T);
 }
 
-template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN, bool ERF, int SH = 1, bool RC = false>
+template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN, bool ERF, int SH = 1, bool RC = false,
+          bool EMB = false>
 int launch_stage_impl(cudaStream_t stream, int64_t* launches, const StageArgs<T>& a) {
   using G = StageGeom<S, WPT, SH>;
-  auto kern = k_stage<T, S, WPT, L, IN, EPI, NTK, CIN, SH, RC, ERF>;
+  auto kern = k_stage<T, S, WPT, L, IN, EPI, NTK, CIN, SH, RC, ERF, EMB>;
   const size_t smem = stage_smem_bytes<T, S, WPT, L, IN, EPI, NTK, CIN, SH>();
   NTK_TRY(ensure_dynamic_smem((const void*)kern, smem));
   long long blocks = (a.P + G::GROUPS - 1) / G::GROUPS;
@@ -1013,7 +1090,7 @@ int launch_stage_impl(cudaStream_t stream, int64_t* launches, const StageArgs<T>
   return NTK_OK;
 }
 
-template <typename T, int S, int L, int IN, bool NTK, int CIN, bool ERF>
+template <typename T, int S, int L, int IN, bool NTK, int CIN, bool ERF, bool EMB = false>
 int launch_stage_epi(cudaStream_t stream, int64_t* launches, int epi, const StageArgs<T>& a) {
   constexpr int WPT = StageCfg<T, S>::WPT;
   // (An SH = 3 variant -- three column samples sharing one row sample per CTA, 12 instead of 8 resident
@@ -1022,33 +1099,53 @@ int launch_stage_epi(cudaStream_t stream, int64_t* launches, int epi, const Stag
   if (!NTK && a.col_count != S) {  // self-pair pipeline (nngp only): partial column range
     switch (epi) {
       case EPI_STORE:
-        return launch_stage_impl<T, S, WPT, L, IN, EPI_STORE, false, CIN, ERF, 1, true>(stream, launches, a);
+        return launch_stage_impl<T, S, WPT, L, IN, EPI_STORE, false, CIN, ERF, 1, true, EMB>(stream, launches, a);
       case EPI_POOL:
-        return launch_stage_impl<T, S, WPT, L, IN, EPI_POOL, false, CIN, ERF, 1, true>(stream, launches, a);
+        return launch_stage_impl<T, S, WPT, L, IN, EPI_POOL, false, CIN, ERF, 1, true, EMB>(stream, launches, a);
       default:
         return fail(NTK_EINVAL, "partial column range with a GAP epilogue");
     }
   }
   switch (epi) {
     case EPI_STORE:
-      return launch_stage_impl<T, S, WPT, L, IN, EPI_STORE, NTK, CIN, ERF>(stream, launches, a);
+      return launch_stage_impl<T, S, WPT, L, IN, EPI_STORE, NTK, CIN, ERF, 1, false, EMB>(stream, launches, a);
     case EPI_POOL:
-      return launch_stage_impl<T, S, WPT, L, IN, EPI_POOL, NTK, CIN, ERF>(stream, launches, a);
+      return launch_stage_impl<T, S, WPT, L, IN, EPI_POOL, NTK, CIN, ERF, 1, false, EMB>(stream, launches, a);
     default:
-      return launch_stage_impl<T, S, WPT, L, IN, EPI_GAP, NTK, CIN, ERF>(stream, launches, a);
+      return launch_stage_impl<T, S, WPT, L, IN, EPI_GAP, NTK, CIN, ERF, 1, false, EMB>(stream, launches, a);
   }
 }
 
-template <typename T, int S, int IN, bool NTK, int CIN, bool ERF>
+template <typename T, int S, int IN, bool NTK, int CIN, bool ERF, bool EMB = false>
 int launch_stage_L(cudaStream_t stream, int64_t* launches, int L, int epi, const StageArgs<T>& a) {
   switch (L) {
     case 1:
-      return launch_stage_epi<T, S, 1, IN, NTK, CIN, ERF>(stream, launches, epi, a);
+      return launch_stage_epi<T, S, 1, IN, NTK, CIN, ERF, EMB>(stream, launches, epi, a);
     case 2:
-      return launch_stage_epi<T, S, 2, IN, NTK, CIN, ERF>(stream, launches, epi, a);
+      return launch_stage_epi<T, S, 2, IN, NTK, CIN, ERF, EMB>(stream, launches, epi, a);
     default:
-      return launch_stage_epi<T, S, 3, IN, NTK, CIN, ERF>(stream, launches, epi, a);
+      return launch_stage_epi<T, S, 3, IN, NTK, CIN, ERF, EMB>(stream, launches, epi, a);
   }
+}
+
+// EMB family (pure ABRelu): images of any size RH x RW <= S x S with C in {1, 3}; instantiated in fused_*_emb.cu.
+template <typename T, bool NTK>
+int launch_stage_emb(cudaStream_t stream, int64_t* launches, int S, int L, int from_x, int C, int epi,
+                     const StageArgs<T>& a) {
+  if (from_x) {
+    if (C == 1) {
+      if (S == 32) return launch_stage_L<T, 32, IN_FROM_X, NTK, 1, false, true>(stream, launches, L, epi, a);
+      if (S == 16) return launch_stage_L<T, 16, IN_FROM_X, NTK, 1, false, true>(stream, launches, L, epi, a);
+      return launch_stage_L<T, 8, IN_FROM_X, NTK, 1, false, true>(stream, launches, L, epi, a);
+    }
+    if (C != 3) return fail(NTK_EUNSUPPORTED, "fused FROM_X stages are instantiated for C == 1 and C == 3");
+    if (S == 32) return launch_stage_L<T, 32, IN_FROM_X, NTK, 3, false, true>(stream, launches, L, epi, a);
+    if (S == 16) return launch_stage_L<T, 16, IN_FROM_X, NTK, 3, false, true>(stream, launches, L, epi, a);
+    return launch_stage_L<T, 8, IN_FROM_X, NTK, 3, false, true>(stream, launches, L, epi, a);
+  }
+  if (S == 32) return launch_stage_L<T, 32, IN_LOAD, NTK, 1, false, true>(stream, launches, L, epi, a);
+  if (S == 16) return launch_stage_L<T, 16, IN_LOAD, NTK, 1, false, true>(stream, launches, L, epi, a);
+  return launch_stage_L<T, 8, IN_LOAD, NTK, 1, false, true>(stream, launches, L, epi, a);
 }
 
 // Packed-FP32 (FFMA2) instance for fp32 at 32x32: stage_packed.cuh / stage_packed.cu.
@@ -1099,10 +1196,14 @@ bool stage_is_packed(int S, int C, int n_erf, int L) {
 
 template <typename T, bool NTK>
 int launch_stage(cudaStream_t stream, int64_t* launches, int S, int L, int from_x, int C, int epi,
-                 const StageArgs<T>& a) {
+                 const StageArgs<T>& a, bool emb = false) {
   int n_erf = 0;
   for (int l = 0; l < L; ++l) n_erf += a.lp[l].kind == ACT_ERF;
   const bool any_erf = n_erf > 0;
+  if (emb) {
+    if (any_erf) return fail(NTK_EUNSUPPORTED, "the embedded-size stage kernels are ABRelu only");
+    return launch_stage_emb<T, NTK>(stream, launches, S, L, from_x, C, epi, a);
+  }
   if (stage_is_packed<T>(S, from_x ? C : 3, n_erf, L))
     return launch_stage_packed_any(stream, launches, S, L, from_x, epi, NTK, any_erf, a);
   if (any_erf) return launch_stage_k<T, NTK, true>(stream, launches, S, L, from_x, C, epi, a);
@@ -1111,16 +1212,16 @@ int launch_stage(cudaStream_t stream, int64_t* launches, int S, int L, int from_
 
 template <typename T>
 int launch_qmaps(cudaStream_t stream, int64_t* launches, int S, const T* src, int src_mode, int n,
-                 int C, T in_scale, int L, const FLayer<T>* lp, T* qm) {
+                 int C, T in_scale, int L, const FLayer<T>* lp, T* qm, int RH, int RW) {
   (*launches)++;
   FLayer<T> z{(T)0, (T)0, (T)0, (T)0};
   FLayer<T> l0 = lp[0], l1 = L > 1 ? lp[1] : z, l2 = L > 2 ? lp[2] : z;
   if (S == 32)
-    k_qmaps<T, 32><<<n, 256, 0, stream>>>(src, src_mode, C, in_scale, L, l0, l1, l2, qm);
+    k_qmaps<T, 32><<<n, 256, 0, stream>>>(src, src_mode, C, in_scale, L, l0, l1, l2, qm, RH, RW);
   else if (S == 16)
-    k_qmaps<T, 16><<<n, 256, 0, stream>>>(src, src_mode, C, in_scale, L, l0, l1, l2, qm);
+    k_qmaps<T, 16><<<n, 256, 0, stream>>>(src, src_mode, C, in_scale, L, l0, l1, l2, qm, RH, RW);
   else
-    k_qmaps<T, 8><<<n, 64, 0, stream>>>(src, src_mode, C, in_scale, L, l0, l1, l2, qm);
+    k_qmaps<T, 8><<<n, 64, 0, stream>>>(src, src_mode, C, in_scale, L, l0, l1, l2, qm, RH, RW);
   NTK_CUDA(cudaGetLastError());
   return NTK_OK;
 }
@@ -1186,9 +1287,12 @@ void stage_constants(const FusedPlan& plan, size_t s, FLayer<T>* lp, double* nex
 // the pair grid is tiled so that the stage boundaries fit in the arena.
 template <typename T>
 int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t* launches,
-               StageProfile* prof, const T* x1, int n1, const T* x2, int n2, bool symmetric, int S0,
-               int /*W*/, int C, bool want_ntk, T* out_nngp, T* out_ntk, long long ld,
+               StageProfile* prof, const T* x1, int n1, const T* x2, int n2, bool symmetric, int H0,
+               int W0, int C, bool want_ntk, T* out_nngp, T* out_ntk, long long ld,
                bool full_square = false, bool upper = false) {
+  const int S0 = fused_shear_size(H0, W0);
+  const bool emb = fused_needs_emb(H0, W0, C);
+  const size_t xrow = (size_t)H0 * W0 * C;  // elements per input sample
   // `upper` (NTK_FLAG_UPPER_ONLY): x1 holds the same samples as x2[0:n1]; only entries (i, j >= i) are wanted.
   upper = upper && !symmetric && n2 >= n1;
   const bool triangular = (symmetric && !full_square && n1 == n2 && n1 > 1) || upper;
@@ -1197,13 +1301,22 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
   // ---- 1. q-maps for every stage and both sample sets (self-pair pipeline) --------------
   // qm[s][set]: [n][L][S][S][2]
   std::vector<T*> qm1(n_st), qm2(n_st);
-  std::vector<int> Ss(n_st);
+  std::vector<int> Ss(n_st), RHs(n_st), RWs(n_st);
+  int RH_last = H0, RW_last = W0;
   {
-    int S = S0;
+    int S = S0, RH = H0, RW = W0;
     for (size_t s = 0; s < n_st; ++s) {
       Ss[s] = S;
-      if (plan.stages[s].epi == EPI_POOL) S /= 2;
+      RHs[s] = RH;
+      RWs[s] = RW;
+      if (plan.stages[s].epi == EPI_POOL) {
+        S /= 2;
+        RH /= 2;
+        RW /= 2;
+      }
     }
+    RH_last = RHs[n_st - 1];
+    RW_last = RWs[n_st - 1];
   }
   for (size_t s = 0; s < n_st; ++s) {
     const size_t per = (size_t)plan.stages[s].L * Ss[s] * Ss[s] * 2 * sizeof(T);
@@ -1253,14 +1366,17 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
         T* qm = (set == 0 ? qm1[s] : qm2[s]) + (size_t)c0 * plan.stages[s].L * Ss[s] * Ss[s] * 2;
         const int S = Ss[s];
         if (s == 0)
-          NTK_TRY(launch_qmaps<T>(stream, launches, S, x + (size_t)c0 * S * S * C, 0, m, C, in_scale,
-                                  plan.stages[s].L, lp, qm));
+          NTK_TRY(launch_qmaps<T>(stream, launches, S, x + (size_t)c0 * xrow, 0, m, C, in_scale,
+                                  plan.stages[s].L, lp, qm, RHs[s], RWs[s]));
         else
-          NTK_TRY(launch_qmaps<T>(stream, launches, S, cur, 1, m, C, (T)1, plan.stages[s].L, lp, qm));
+          NTK_TRY(launch_qmaps<T>(stream, launches, S, cur, 1, m, C, (T)1, plan.stages[s].L, lp, qm, RHs[s],
+                                  RWs[s]));
         if (s + 1 == n_st) break;  // the last stage's self tensors are never needed
         // run the stage on the self pairs (nngp only) to get the next boundary
         StageArgs<T> a{};
-        a.x1 = a.x2 = x + (size_t)c0 * S * S * C;
+        a.RH = RHs[s];
+        a.RW = RWs[s];
+        a.x1 = a.x2 = x + (size_t)c0 * xrow;
         a.inK = cur;
         a.inT = nullptr;
         T* nxt = (cur == bufA) ? bufB : bufA;
@@ -1275,11 +1391,11 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
         a.col_count = std::min(S, 2 * k_in[s] + 1);
         a.col_start = a.col_count == S ? 0 : k_in[s];
         a.in_scale = in_scale;
-        a.epi_scale = (T)(next_alpha / 16.0);
+        a.epi_scale = (T)(next_alpha * plan.stages[s].pool_mul / 16.0);
         for (int l = 0; l < plan.stages[s].L; ++l) a.lp[l] = lp[l];
         if (epi == EPI_POOL)
           NTK_CUDA(cudaMemsetAsync(nxt, 0, (size_t)m * So * So * So * So * sizeof(T), stream));
-        NTK_TRY((launch_stage<T, false>(stream, launches, S, plan.stages[s].L, s == 0, C, epi, a)));
+        NTK_TRY((launch_stage<T, false>(stream, launches, S, plan.stages[s].L, s == 0, C, epi, a, emb)));
         cur = nxt;
       }
     }
@@ -1330,9 +1446,12 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
   T* resT = want_ntk ? (T*)arena.alloc((size_t)t1 * t2 * sizeof(T)) : nullptr;
   if (!resK || (want_ntk && !resT)) return fail(NTK_ENOMEM, "workspace too small");
 
-  const FusedStage& tail = plan.stages.back();
-  const int S_last = Ss[n_st - 1];
-  (void)tail;
+  // tail: pools + GlobalAvgPool / Flatten == global mean over the last stage's map; SumPool / GlobalSumPool scale it
+  double tail_scale = plan.tail_mul / ((double)RH_last * RH_last * RW_last * RW_last);
+  if (plan.tail_gsum) {
+    const double fh = (double)(RH_last >> plan.tail_pools), fw = (double)(RW_last >> plan.tail_pools);
+    tail_scale *= fh * fh * fw * fw;
+  }
   for (int r0 = 0; r0 < n1; r0 += t1) {
     const int a1 = std::min(t1, n1 - r0);
     // K(x, x) is symmetric: only pairs (i, j >= i) are computed and the strictly lower triangle
@@ -1349,8 +1468,10 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
         double next_alpha = 1.0;
         stage_constants<T>(plan, s, lp, &next_alpha);
         StageArgs<T> a{};
-        a.x1 = x1 + (size_t)r0 * S * S * C;
-        a.x2 = x2 + (size_t)c0 * S * S * C;
+        a.RH = RHs[s];
+        a.RW = RWs[s];
+        a.x1 = x1 + (size_t)r0 * xrow;
+        a.x2 = x2 + (size_t)c0 * xrow;
         const int epi = plan.stages[s].epi;
         const int So = epi == EPI_POOL ? S / 2 : S;
         const size_t in_per = (size_t)S * S * S * S, out_per = (size_t)So * So * So * So;
@@ -1360,17 +1481,17 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
         if (epi == EPI_GAP) {
           a.outK = resK;
           a.outT = resT;
-          a.epi_scale = (T)(1.0 / ((double)S_last * S_last * S_last * S_last));
+          a.epi_scale = (T)tail_scale;
         } else {
           a.outK = nxt;
           a.outT = want_ntk ? nxt + (size_t)P * out_per : nullptr;
-          a.epi_scale = (T)(next_alpha / 16.0);
+          a.epi_scale = (T)(next_alpha * plan.stages[s].pool_mul / 16.0);
           if (epi == EPI_POOL) {
             // the packed kernels zero their own (pre-accumulation) output while other CTAs compute
             // -- DRAM is idle in this kernel -- instead of a 4.8 GB memset in front of every launch
             int n_erf = 0;
             for (int l = 0; l < plan.stages[s].L; ++l) n_erf += plan.stages[s].kind[l] == ACT_ERF;
-            a.zero_out = stage_is_packed<T>(S, s == 0 ? C : 3, n_erf, plan.stages[s].L) ? 1 : 0;
+            a.zero_out = (!emb && stage_is_packed<T>(S, s == 0 ? C : 3, n_erf, plan.stages[s].L)) ? 1 : 0;
             if (!a.zero_out)
               NTK_CUDA(cudaMemsetAsync(nxt, 0, (size_t)P * out_per * sizeof(T) * (want_ntk ? 2 : 1), stream));
           }
@@ -1393,9 +1514,9 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
           NTK_CUDA(cudaEventRecord(ev0, stream));
         }
         if (want_ntk)
-          NTK_TRY((launch_stage<T, true>(stream, launches, S, plan.stages[s].L, s == 0, C, epi, a)));
+          NTK_TRY((launch_stage<T, true>(stream, launches, S, plan.stages[s].L, s == 0, C, epi, a, emb)));
         else
-          NTK_TRY((launch_stage<T, false>(stream, launches, S, plan.stages[s].L, s == 0, C, epi, a)));
+          NTK_TRY((launch_stage<T, false>(stream, launches, S, plan.stages[s].L, s == 0, C, epi, a, emb)));
         if (timed) {
           NTK_CUDA(cudaEventRecord(ev1, stream));
           prof->pending[s].push_back({ev0, ev1});

@@ -158,6 +158,7 @@ __global__ void k_conv(const T* __restrict__ in, const T* __restrict__ addend, T
 // ---- AvgPool rule: linear.py:3499-3572 (independent offsets on both members) --
 struct PoolGeom {
   int Hi, Wi, Ho, Wo, wh, ww, sh, sw, loh, low, circular, normalize_edges;
+  int sum;  // SumPool (linear.py:1503): no division
 };
 
 template <typename T>
@@ -222,7 +223,7 @@ __global__ void k_pool(const T* __restrict__ in, T* __restrict__ out, long long 
     }
     T norm = g.normalize_edges ? (T)((long long)cnt_h * cnt_h2 * cnt_w * cnt_w2)
                                : (T)((long long)g.wh * g.wh * g.ww * g.ww);
-    out[idx] = acc / norm;
+    out[idx] = g.sum ? acc : acc / norm;
   }
 }
 
@@ -243,9 +244,44 @@ __global__ void k_diag(const T* __restrict__ cov, T* __restrict__ q, long long n
 // ---- activations ---------------------------------------------------------------
 // ABRelu: elementwise.py:444-455;  Erf: elementwise.py:84-93 + kernel.py:426-439.
 struct ActParams {
-  int kind;       // NTK_OP_ABRELU or NTK_OP_ERF
+  int kind;       // NTK_OP_ABRELU, NTK_OP_ERF, NTK_OP_GELU, NTK_OP_SIN (a, b, c) or NTK_OP_RBF (a = gamma)
   double a, b, c;
 };
+
+__device__ __forceinline__ float exp_t(float a) { return expf(a); }
+__device__ __forceinline__ double exp_t(double a) { return exp(a); }
+
+// Gelu (elementwise.py:225-240): k = nngp, q1 / q2 the diagonal variances of the two members.
+template <typename T>
+__device__ __forceinline__ void gelu_point(T k, T q1, T q2, T& k_out, T& dot) {
+  const T prod = q1 * q2, prod_plus_1 = (q1 + (T)1) * (q2 + (T)1);
+  const T delta_squared = prod_plus_1 - k * k;
+  const T delta = sqrt_t(max_t(delta_squared, (T)0));
+  const T angles = atan2_t(k, delta);
+  const T two_pi = (T)2 * Consts<T>::pi();
+  T nk = (k * k + prod * delta_squared) / (prod_plus_1 * delta);
+  nk = (nk + k * angles) / two_pi + (T)0.25 * k;
+  T first = (T)1 / delta_squared + ((T)1 - prod) / prod_plus_1 + (T)1;
+  first *= k / delta / two_pi;
+  dot = first + (T)0.25 + angles / two_pi;
+  k_out = nk;
+}
+
+// Sin(a, b, c) (elementwise.py:294-300): sum_ = q1 + q2
+template <typename T>
+__device__ __forceinline__ void sin_point(T k, T sum_, T half_a2, T b2, T cos2c, T& k_out, T& dot) {
+  const T s1 = exp_t(b2 * ((T)-0.5 * sum_ + k));
+  const T s2 = exp_t(b2 * ((T)-0.5 * sum_ - k)) * cos2c;
+  k_out = half_a2 * (s1 - s2);
+  dot = half_a2 * b2 * (s1 + s2);
+}
+
+// Rbf(gamma) (elementwise.py:375-379)
+template <typename T>
+__device__ __forceinline__ void rbf_point(T k, T sum_, T gamma, T& k_out, T& dot) {
+  k_out = exp_t(gamma * (-sum_ + (T)2 * k));
+  dot = (T)2 * gamma * k_out;
+}
 
 template <typename T>
 __device__ __forceinline__ void abrelu_point(T k, T prod, T coef_s, T half_ab, T& k_out, T& dot) {
@@ -279,6 +315,7 @@ __global__ void k_act(T* __restrict__ K, T* __restrict__ Tt, const T* __restrict
   const T coef_s = (a - b) * (a - b) / ((T)2 * Consts<T>::pi());
   const T half_ab = (a * a + b * b) / (T)2;
   const T bb = b * b, aa = a * a, cc = (T)(ap.c * ap.c);
+  const T cos2c = ap.kind == NTK_OP_SIN ? (T)cos(2.0 * ap.c) : (T)0;
   T factor = (T)1;
   if (stab) factor = max_t(*stab, (T)1e-12);
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -307,12 +344,21 @@ __global__ void k_act(T* __restrict__ K, T* __restrict__ Tt, const T* __restrict
       if (stab) ko *= factor;
       K[idx] = ko;
       if (Tt) Tt[idx] *= dot;
-    } else {
+    } else if (ap.kind == NTK_OP_ERF) {
       k *= bb;
       T prod = ((T)1 + (T)2 * bb * v1) * ((T)1 + (T)2 * bb * v2);
       erf_point<T>(k, prod, ko, dot);
       K[idx] = fma_t(aa, ko, cc);
       if (Tt) Tt[idx] = aa * (bb * Tt[idx] * dot);
+    } else {
+      if (ap.kind == NTK_OP_GELU)
+        gelu_point<T>(k, v1, v2, ko, dot);
+      else if (ap.kind == NTK_OP_SIN)
+        sin_point<T>(k, v1 + v2, aa / (T)2, bb, cos2c, ko, dot);
+      else
+        rbf_point<T>(k, v1 + v2, a, ko, dot);
+      K[idx] = ko;
+      if (Tt) Tt[idx] *= dot;
     }
   }
 }
@@ -339,7 +385,7 @@ __global__ void k_absmax(const T* __restrict__ x, long long n, T* __restrict__ o
 // One block per pair; fixed-order tree reduction (deterministic).
 template <typename T, bool kFlatten>
 __global__ void k_reduce_spatial(const T* __restrict__ in, T* __restrict__ out, long long P, int H,
-                                 int W) {
+                                 int W, int sum = 0) {
   __shared__ T sm[kThreads / 32];
   const long long per = (long long)H * H * W * W;
   for (long long p = blockIdx.x; p < P; p += gridDim.x) {
@@ -359,7 +405,7 @@ __global__ void k_reduce_spatial(const T* __restrict__ in, T* __restrict__ out, 
     if (threadIdx.x < 32) {
       T v = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : (T)0;
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (threadIdx.x == 0) out[p] = v / (T)(kFlatten ? (long long)H * W : per);
+      if (threadIdx.x == 0) out[p] = sum ? v : v / (T)(kFlatten ? (long long)H * W : per);
     }
     __syncthreads();
   }

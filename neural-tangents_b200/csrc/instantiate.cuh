@@ -14,6 +14,13 @@
                                                  const StageArgs<T>&);                                     \
   KW template int fused_configure_device<T, true>();
 
+// launch_stage_emb<T, NTK> (embedded-size scalar stage kernels, C in {1, 3}) lives in fused_*_emb.cu
+#define NTK_FUSED_EMB_INSTANCES(KW, T)                                                                     \
+  KW template int launch_stage_emb<T, true>(cudaStream_t, int64_t*, int, int, int, int, int,               \
+                                            const StageArgs<T>&);                                          \
+  KW template int launch_stage_emb<T, false>(cudaStream_t, int64_t*, int, int, int, int, int,              \
+                                             const StageArgs<T>&);
+
 #define NTK_FUSED_INSTANCES(KW, T)                                                                        \
   KW template int fused_gram<T>(const FusedPlan&, Arena&, cudaStream_t, int64_t*, StageProfile*, const T*, \
                                 int, const T*, int, bool, int, int, int, bool, T*, T*, long long, bool, bool); \

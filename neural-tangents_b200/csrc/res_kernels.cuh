@@ -641,11 +641,12 @@ inline ResPlan plan_resnet(const std::vector<ntk_op_t>& ops, int out_slot) {
   }
   if (plan.blocks.empty() || k >= n) return ResPlan();
   // tail: GAP, or AvgPool covering the whole (square) map followed by Flatten -- checked at run time
-  if (ops[k].kind == NTK_OP_GAP && ops[k].src == z) {
+  if (ops[k].kind == NTK_OP_GAP && ops[k].i[0] == 0 && ops[k].src == z) {
     z = ops[k].dst;
     ++k;
   } else if (ops[k].kind == NTK_OP_AVGPOOL && ops[k].src == z && k + 1 < n && ops[k + 1].kind == NTK_OP_FLATTEN &&
-             ops[k + 1].src == ops[k].dst && ops[k].i[4] == NTK_PAD_VALID && ops[k].i[0] == ops[k].i[1]) {
+             ops[k + 1].src == ops[k].dst && ops[k].i[4] == NTK_PAD_VALID && ops[k].i[0] == ops[k].i[1] &&
+             (ops[k].i[5] & 2) == 0) {
     plan.n_strided |= ops[k].i[0] << 8;  // remember the pool window to validate against S
     z = ops[k + 1].dst;
     k += 2;

@@ -25,7 +25,8 @@ from .kernel import Kernel
 import enum
 
 __all__ = ['serial', 'parallel', 'FanOut', 'FanInSum', 'Identity', 'Dense', 'Conv', 'Relu',
-           'ABRelu', 'LeakyRelu', 'Abs', 'Erf', 'AvgPool', 'GlobalAvgPool', 'Flatten', 'Padding']
+           'ABRelu', 'LeakyRelu', 'Abs', 'Erf', 'Sigmoid_like', 'Gelu', 'Sin', 'Cos', 'Rbf', 'AvgPool', 'SumPool',
+           'GlobalAvgPool', 'GlobalSumPool', 'Flatten', 'Padding']
 
 
 class Padding(enum.Enum):
@@ -37,11 +38,11 @@ class Padding(enum.Enum):
 
 # Names the reference's `stax` exports that are outside the B200 hot path: asking
 # for them fails loudly instead of with an AttributeError that looks like a typo.
-_OUT_OF_SCOPE = ('repeat', 'Cos', 'Elementwise', 'ElementwiseNumerical', 'Exp', 'ExpNormalized',
-                 'Gabor', 'Gaussian', 'Gelu', 'Hermite', 'Monomial', 'Polynomial', 'Rbf',
-                 'RectifiedMonomial', 'Sigmoid_like', 'Sign', 'Sin', 'Aggregate', 'ConvLocal',
+_OUT_OF_SCOPE = ('repeat', 'Elementwise', 'ElementwiseNumerical', 'Exp', 'ExpNormalized',
+                 'Gabor', 'Gaussian', 'Hermite', 'Monomial', 'Polynomial',
+                 'RectifiedMonomial', 'Sign', 'Aggregate', 'ConvLocal',
                  'ConvTranspose', 'Index', 'DotGeneral', 'Dropout', 'GlobalSelfAttention',
-                 'GlobalSumPool', 'ImageResize', 'LayerNorm', 'SumPool', 'Slice', 'FanInConcat',
+                 'ImageResize', 'LayerNorm', 'Slice', 'FanInConcat',
                  'FanInProd', 'AggregateImplementation', 'AttentionMechanism', 'PositionalEmbedding',
                  'Bool', 'Diagonal', 'MaskedArray', 'layer', 'requires', 'supports_masking', 'unmask_fn')
 
@@ -49,8 +50,8 @@ _OUT_OF_SCOPE = ('repeat', 'Cos', 'Elementwise', 'ElementwiseNumerical', 'Exp', 
 def __getattr__(name):
   if name in _OUT_OF_SCOPE:
     raise NotImplementedError(f'stax.{name} exists in neural_tangents but is outside the B200 '
-                              'hot path (Dense/Conv/Relu/Erf/AvgPool/GlobalAvgPool/Flatten/'
-                              'FanOut/FanInSum/serial/parallel); see DESIGN.md §9')
+                              'hot path (Dense/Conv/Relu/Erf/Gelu/Sin/Cos/Rbf/AvgPool/SumPool/GlobalAvgPool/'
+                              'GlobalSumPool/Flatten/FanOut/FanInSum/serial/parallel); see DESIGN.md §9')
   raise AttributeError(name)
 
 
@@ -234,13 +235,19 @@ class _Lowered:
       return self._emit(_lib.OP_ABRELU, cur, (bool(spec[3]),), (spec[1], spec[2]), meta=m)
     if kind == 'erf':
       return self._emit(_lib.OP_ERF, cur, (), (spec[1], spec[2], spec[3]), meta=m)
-    if kind == 'avgpool':
+    if kind == 'gelu':
+      return self._emit(_lib.OP_GELU, cur, (), (), meta=m)
+    if kind == 'sin':
+      return self._emit(_lib.OP_SIN, cur, (), (spec[1], spec[2], spec[3]), meta=m)
+    if kind == 'rbf':
+      return self._emit(_lib.OP_RBF, cur, (), (spec[1],), meta=m)
+    if kind in ('avgpool', 'sumpool'):
       (wh, ww), (sh, sw) = spec[1], spec[2]
-      return self._emit(_lib.OP_AVGPOOL, cur, (wh, ww, sh, sw, _lib.PAD[spec[3]], bool(spec[4])),
-                        meta=m)
-    if kind == 'gap':
+      flags = (1 if spec[4] else 0) | (2 if kind == 'sumpool' else 0)   # bit 0 normalize_edges, bit 1 SumPool
+      return self._emit(_lib.OP_AVGPOOL, cur, (wh, ww, sh, sw, _lib.PAD[spec[3]], flags), meta=m)
+    if kind in ('gap', 'gsp'):
       m.is_reversed, m.spatial = False, False                # linear.py:1801
-      return self._emit(_lib.OP_GAP, cur, meta=m)
+      return self._emit(_lib.OP_GAP, cur, (1 if kind == 'gsp' else 0,), meta=m)
     if kind == 'flatten':
       m.is_reversed, m.spatial = False, False                # linear.py:1896
       return self._emit(_lib.OP_FLATTEN, cur, meta=m)
@@ -282,7 +289,7 @@ def _out_shape(spec, shape):
     return [_out_shape(s, sh) for s, sh in zip(spec[1], shape)]
   if kind == 'faninsum':
     return shape[0] if isinstance(shape, list) else shape
-  if kind in ('identity', 'abrelu', 'erf'):
+  if kind in ('identity', 'abrelu', 'erf', 'gelu', 'sin', 'rbf'):
     return shape
   shape = tuple(shape)
   if kind == 'dense':
@@ -290,10 +297,10 @@ def _out_shape(spec, shape):
   if kind == 'conv':
     return (shape[0], _axis_out(shape[1], spec[1][0], spec[2][0], spec[3]),
             _axis_out(shape[2], spec[1][1], spec[2][1], spec[3]), spec[-1])
-  if kind == 'avgpool':
+  if kind in ('avgpool', 'sumpool'):
     return (shape[0], _axis_out(shape[1], spec[1][0], spec[2][0], spec[3]),
             _axis_out(shape[2], spec[1][1], spec[2][1], spec[3]), shape[3])
-  if kind == 'gap':
+  if kind in ('gap', 'gsp'):
     return (shape[0], shape[-1])
   if kind == 'flatten':
     return (shape[0], int(np.prod(shape[1:])))
@@ -586,6 +593,76 @@ def Erf(a: float = 1., b: float = 1., c: float = 0.):
     from scipy.special import erf as _erf
     return a * _erf(b * inputs) + c
 
+  return _layer(spec, init_fn, apply_fn)
+
+
+def Sigmoid_like():
+  """`_src/stax/elementwise.py:115-126`."""
+  return Erf(a=0.5, b=1 / 2.4020563531719796, c=0.5)
+
+
+def Gelu(approximate: bool = False):
+  """`_src/stax/elementwise.py:195-263`; `approximate` only affects the finite-width `apply_fn`."""
+  spec = ('gelu',)
+  init_fn = lambda rng, input_shape: (input_shape, ())
+
+  def apply_fn(params, inputs, **kw):
+    if approximate:
+      return 0.5 * inputs * (1 + np.tanh(math.sqrt(2 / math.pi) * (inputs + 0.044715 * inputs**3)))
+    from scipy.special import erf as _erf
+    return 0.5 * inputs * (1 + _erf(inputs / math.sqrt(2)))
+
+  return _layer(spec, init_fn, apply_fn)
+
+
+def Sin(a: float = 1., b: float = 1., c: float = 0.):
+  """`_src/stax/elementwise.py:266-320`: `a sin(b x + c)`."""
+  spec = ('sin', float(a), float(b), float(c))
+  init_fn = lambda rng, input_shape: (input_shape, ())
+  apply_fn = lambda params, inputs, **kw: a * np.sin(b * inputs + c)
+  return _layer(spec, init_fn, apply_fn)
+
+
+def Cos(a: float = 1., b: float = 1., c: float = 0.):
+  """`_src/stax/elementwise.py:323-341`: `Sin(a, b, c + pi / 2)`."""
+  return Sin(a=a, b=b, c=c + math.pi / 2)
+
+
+def Rbf(gamma: float = 1.0):
+  """`_src/stax/elementwise.py:344-400`: dual activation `sqrt(2) sin(sqrt(2 gamma) x + pi/4)`."""
+  spec = ('rbf', float(gamma))
+  init_fn = lambda rng, input_shape: (input_shape, ())
+  apply_fn = lambda params, inputs, **kw: math.sqrt(2) * np.sin(math.sqrt(2 * gamma) * inputs + math.pi / 4)
+  return _layer(spec, init_fn, apply_fn)
+
+
+def SumPool(window_shape, strides=None, padding: str = 'VALID', batch_axis: int = 0, channel_axis: int = -1):
+  """`_src/stax/linear.py:1503-1547`: AvgPool without the division by the window."""
+  _only_supported(batch_axis=(batch_axis, (0,)), channel_axis=(channel_axis, (-1,)))
+  if len(window_shape) != 2:
+    raise NotImplementedError('only 2-D pooling is on the B200 hot path')
+  w = tuple(int(v) for v in window_shape)
+  strides = tuple(strides) if strides is not None else (1, 1)
+  padding = getattr(padding, 'name', padding).upper()
+  if padding not in _lib.PAD:
+    raise ValueError(f'unknown padding {padding}')
+  spec = ('sumpool', w, strides, padding, False)
+
+  def init_fn(rng, input_shape):
+    return _out_shape(spec, input_shape), ()
+
+  def apply_fn(params, inputs, **kwargs):
+    return _windows(inputs, w, strides, padding).sum(axis=(3, 4))
+
+  return _layer(spec, init_fn, apply_fn)
+
+
+def GlobalSumPool(batch_axis: int = 0, channel_axis: int = -1):
+  """`_src/stax/linear.py:1674-1720`."""
+  _only_supported(batch_axis=(batch_axis, (0,)), channel_axis=(channel_axis, (-1,)))
+  spec = ('gsp',)
+  init_fn = lambda rng, input_shape: ((input_shape[0], input_shape[-1]), ())
+  apply_fn = lambda params, inputs, **kw: inputs.sum(axis=tuple(range(1, inputs.ndim - 1)))
   return _layer(spec, init_fn, apply_fn)
 
 

@@ -32,6 +32,8 @@ shares no code with the product front end:
   ('abrelu', a, b, do_stabilize)          # Relu == ('abrelu', 0., 1., False)
   ('erf', a, b, c)
   ('avgpool', (wh, ww), (sh, sw), 'SAME'|'VALID'|'CIRCULAR', normalize_edges)
+  ('sumpool', (wh, ww), (sh, sw), padding)   ('gsp',)      # SumPool / GlobalSumPool
+  ('gelu',)  ('sin', a, b, c)  ('cos', a, b, c)  ('rbf', gamma)
   ('gap',) ('flatten',) ('identity',)
   ('fanout', n) ('parallel', [spec, ...]) ('faninsum',)
 """
@@ -305,6 +307,80 @@ def erf(st: OState, a: float, b: float, c: float) -> OState:
   return st.replace(cov1=cov1, nngp=nngp, cov2=cov2, ntk=ntk, is_gaussian=False)
 
 
+def _elementwise_pairs(st: OState, prep1, f):
+  """Shared driver of the closed-form activations below: `prep1(q)` maps the per-sample diagonals to the
+  quantity whose outer combination `f` needs (get_diagonal_outer_prods, requirements.py:1077-1117), and
+  `f(k, outer12_args..., t)` is the reference's `nngp_ntk_fn` (the full, non-diagonal_spatial branch)."""
+  if not st.is_gaussian:                                       # elementwise.py:1267-1270
+    raise ValueError('The input to the activation function must be Gaussian')
+  q1 = _diag(st.cov1)
+  q2 = q1 if st.cov2 is None else _diag(st.cov2)
+  nngp, ntk = f(st.nngp, prep1(q1, q2, True), st.ntk)
+  cov1, _ = f(st.cov1, prep1(q1, q1, False), None)
+  cov2 = None
+  if st.cov2 is not None:
+    cov2, _ = f(st.cov2, prep1(q2, q2, False), None)
+  return st.replace(cov1=cov1, nngp=nngp, cov2=cov2, ntk=ntk, is_gaussian=False)
+
+
+def _outer_sum(qa: np.ndarray, qb: np.ndarray, batch_outer: bool) -> np.ndarray:
+  """sum[n1,n2,h,h',w,w'] = qa[n1,h,w] + qb[n2,h',w'] (get_diagonal_outer_prods with op.add)."""
+  if qa.ndim == 1:
+    return qa[:, None] + qb[None, :] if batch_outer else qa + qb
+  if batch_outer:
+    return qa[:, None, :, None, :, None] + qb[None, :, None, :, None, :]
+  return qa[:, :, None, :, None] + qb[:, None, :, None, :]
+
+
+def gelu(st: OState) -> OState:
+  """elementwise.py:195-263 (Gelu, full-spatial branch `nngp_ntk_fn`)."""
+  def prep(qa, qb, batch_outer):
+    return _outer(qa, qb, batch_outer), _outer(qa + 1, qb + 1, batch_outer)
+
+  def f(k, prods, t):                                          # elementwise.py:225-240
+    prod, prod_plus_1 = prods
+    delta_squared = prod_plus_1 - k**2
+    delta = _sqrt(delta_squared)
+    angles = np.arctan2(k, delta)
+    new_k = (k**2 + prod * delta_squared) / (prod_plus_1 * delta)
+    new_k = new_k + k * angles
+    new_k = new_k / (2 * math.pi)
+    new_k = new_k + 0.25 * k
+    if t is not None:
+      second_term = 0.25 + angles / (2 * math.pi)
+      first_term = 1 / delta_squared + (1 - prod) / prod_plus_1 + 1
+      first_term = first_term * (k / delta / (2. * math.pi))
+      t = t * (first_term + second_term)
+    return new_k, t
+
+  return _elementwise_pairs(st, prep, f)
+
+
+def sin(st: OState, a: float, b: float, c: float) -> OState:
+  """elementwise.py:266-320 (Sin(a, b, c) = a sin(b x + c)); Cos(a, b, c) == Sin(a, b, c + pi/2), :323-341."""
+  half_a_square = a**2 / 2.
+
+  def f(k, sum_, t):                                           # elementwise.py:294-300
+    s1 = np.exp(b**2 * (-0.5 * sum_ + k))
+    s2 = np.exp(b**2 * (-0.5 * sum_ - k)) * math.cos(2 * c)
+    if t is not None:
+      t = t * (half_a_square * b**2 * (s1 + s2))
+    return half_a_square * (s1 - s2), t
+
+  return _elementwise_pairs(st, _outer_sum, f)
+
+
+def rbf(st: OState, gamma: float) -> OState:
+  """elementwise.py:344-400 (Rbf): nngp = exp(gamma (-(q1 + q2) + 2 k)), ntk *= 2 gamma nngp."""
+  def f(k, sum_, t):                                           # elementwise.py:375-379
+    k = np.exp(gamma * (-sum_ + 2 * k))
+    if t is not None:
+      t = t * (2 * gamma * k)
+    return k, t
+
+  return _elementwise_pairs(st, _outer_sum, f)
+
+
 # --------------------------------------------------------------------------
 # AvgPool: linear.py:1631-1664 -> _pool_kernel 3499-3559, _normalize 3562-3572.
 # reduce_window with window (wh,wh,ww,ww): independent offsets on both members.
@@ -333,9 +409,15 @@ def _window_sum_axis(m: np.ndarray, ax: int, k: int, s: int, padding: str) -> np
   return acc
 
 
-def _pool_mat(m, window, strides, padding, normalize_edges, batch_ndim):
+def _pool_mat(m, window, strides, padding, normalize_edges, batch_ndim, pool_sum=False):
   if m is None or m.ndim == 0:                                 # linear.py:1647
     return m
+  if pool_sum:                                                 # _Pooling.SUM: linear.py:3556-3557 skips _normalize
+    out = m
+    for i, (k, s) in enumerate(((window[0], strides[0]), (window[0], strides[0]),
+                                (window[1], strides[1]), (window[1], strides[1]))):
+      out = _window_sum_axis(out, batch_ndim + i, k, s, padding)
+    return out
   out = m
   for i, (k, s) in enumerate(((window[0], strides[0]), (window[0], strides[0]),
                               (window[1], strides[1]), (window[1], strides[1]))):
@@ -350,13 +432,15 @@ def _pool_mat(m, window, strides, padding, normalize_edges, batch_ndim):
   return out / float(window[0]**2 * window[1]**2)              # linear.py:3570-3571
 
 
-def avgpool(st: OState, window, strides, padding, normalize_edges=False) -> OState:
+def avgpool(st: OState, window, strides, padding, normalize_edges=False, pool_sum=False) -> OState:
+  """AvgPool (linear.py:1459-1501) and, with `pool_sum`, SumPool (linear.py:1503-1547): same rule without the
+  division by the window."""
   if not st.spatial:
     raise ValueError('AvgPool needs spatial inputs')
-  nngp = _pool_mat(st.nngp, window, strides, padding, normalize_edges, 2)
-  ntk = _pool_mat(st.ntk, window, strides, padding, normalize_edges, 2)
-  cov1 = _pool_mat(st.cov1, window, strides, padding, normalize_edges, 1)
-  cov2 = _pool_mat(st.cov2, window, strides, padding, normalize_edges, 1)
+  nngp = _pool_mat(st.nngp, window, strides, padding, normalize_edges, 2, pool_sum)
+  ntk = _pool_mat(st.ntk, window, strides, padding, normalize_edges, 2, pool_sum)
+  cov1 = _pool_mat(st.cov1, window, strides, padding, normalize_edges, 1, pool_sum)
+  cov2 = _pool_mat(st.cov2, window, strides, padding, normalize_edges, 1, pool_sum)
   h, w = nngp.shape[2], nngp.shape[4]
   return st.replace(nngp=nngp, ntk=ntk, cov1=cov1, cov2=cov2,
                     shape1=(st.shape1[0], h, w, st.shape1[-1]),
@@ -367,7 +451,8 @@ def avgpool(st: OState, window, strides, padding, normalize_edges=False) -> OSta
 # GlobalAvgPool: linear.py:1771-1801 (+ mean_and_var requirements.py:1120-1159)
 # Flatten: linear.py:1865-1899 (trace/size loop 1880-1882)
 # --------------------------------------------------------------------------
-def global_avg_pool(st: OState) -> OState:
+def global_avg_pool(st: OState, pool_sum: bool = False) -> OState:
+  """GlobalAvgPool (linear.py:1723-1808); `pool_sum`: GlobalSumPool (linear.py:1674-1720, `jnp.sum`, :1748)."""
   if not st.spatial:
     raise ValueError('GlobalAvgPool needs spatial inputs')
 
@@ -375,8 +460,9 @@ def global_avg_pool(st: OState) -> OState:
     if m is None:
       return m
     if m.ndim == 0:
-      return m                       # mean of a 0-d array is itself
-    return m.mean(axis=tuple(range(batch_ndim, m.ndim)))
+      return m                       # mean / sum over no axes of a 0-d array is itself
+    ax = tuple(range(batch_ndim, m.ndim))
+    return m.sum(axis=ax) if pool_sum else m.mean(axis=ax)
 
   return st.replace(nngp=mp(st.nngp, 2), ntk=mp(st.ntk, 2), cov1=mp(st.cov1, 1),
                     cov2=mp(st.cov2, 1), spatial=False, is_reversed=False,
@@ -453,6 +539,18 @@ def apply_spec(spec, st):
     return avgpool(st, spec[1], spec[2], spec[3], spec[4] if len(spec) > 4 else False)
   if kind == 'gap':
     return global_avg_pool(st)
+  if kind == 'sumpool':
+    return avgpool(st, spec[1], spec[2], spec[3], False, True)
+  if kind == 'gsp':
+    return global_avg_pool(st, True)
+  if kind == 'gelu':
+    return gelu(st)
+  if kind == 'sin':
+    return sin(st, spec[1], spec[2], spec[3])
+  if kind == 'cos':
+    return sin(st, spec[1], spec[2], spec[3] + math.pi / 2)
+  if kind == 'rbf':
+    return rbf(st, spec[1])
   if kind == 'flatten':
     return flatten(st)
   raise ValueError(f'unknown spec {kind}')

@@ -95,6 +95,38 @@ CASES = {
     'kernel_conv_relu': (('serial', [conv(W=1.2, b=0.1), RELU]), (2, 4, 3, 2), (3, 4, 3, 2), None),
     'kernel_conv2_pool': (('serial', [conv(W=1.2, b=0.1), RELU, conv(k=(3, 2)), RELU, pool((2, 1), (2, 1))]),
                           (2, 4, 4, 2), None, None),
+    # ---- round 2 (append-only: the input seeds derive from the case order) ----
+    # MNIST geometry: 28x28x1 through the Myrtle-5 body (28 -> 14 -> 7) with a GlobalAvgPool tail
+    'myrtle5_gap_mnist': (myrtle(5, 'gap'), (2, 28, 28, 1), (3, 28, 28, 1), ('nngp', 'ntk')),
+    'myrtle5_gap_mnist_sym': (myrtle(5, 'gap'), (3, 28, 28, 1), None, ('nngp', 'ntk')),
+    # grey 32x32, non-square RGB, odd size with a VALID pool (15 -> 7)
+    'myrtle5_grey32': (myrtle(5), (2, 32, 32, 1), (2, 32, 32, 1), ('nngp', 'ntk')),
+    'conv_pool_20x12': (('serial', [conv(W=1.3, b=0.1), RELU, conv(), RELU, pool(), conv(W=1.1, b=0.2), RELU,
+                                    ('gap',), ('dense', 1.2, 0.1)]),
+                        (2, 20, 12, 3), (3, 20, 12, 3), ('nngp', 'ntk')),
+    'conv_pool_15_odd': (('serial', [conv(W=1.3, b=0.1), RELU, pool(), conv(), ('abrelu', 0.1, 1., False),
+                                     ('gap',), ('dense', 1., 0.)]),
+                         (2, 15, 15, 1), (2, 15, 15, 1), ('nngp', 'ntk')),
+    # SumPool / GlobalSumPool (linear.py:1503, 1674)
+    'sumpool_gsp': (('serial', [conv(W=1.2, b=0.1), RELU, ('sumpool', (2, 2), (2, 2), 'VALID'), conv(), RELU,
+                                ('gsp',), ('dense', 1., 0.1)]),
+                    (2, 8, 8, 3), (3, 8, 8, 3), ('nngp', 'ntk')),
+    'sumpool_same_stride1': (('serial', [conv(W=1.2, b=0.1), ('erf', 1., 1., 0.), ('sumpool', (3, 2), (1, 1), 'SAME'),
+                                         ('gap',), ('dense', 1., 0.)]),
+                             (2, 5, 6, 2), (2, 5, 6, 2), ('nngp', 'ntk')),
+    # closed-form activations of elementwise.py:195-400
+    'gelu_conv': (('serial', [conv(W=1.2, b=0.1), ('gelu',), conv(W=1.1, b=0.), ('gelu',), ('gap',),
+                              ('dense', 1., 0.1)]),
+                  (3, 6, 6, 2), (2, 6, 6, 2), ('nngp', 'ntk')),
+    'gelu_fcn_sym': (('serial', [('dense', 1.5, 0.1), ('gelu',), ('dense', 1.2, 0.05), ('gelu',), ('dense', 1., 0.)]),
+                     (5, 16), None, ('nngp', 'ntk')),
+    'sin_cos_conv': (('serial', [conv(W=1.1, b=0.2), ('sin', 1.2, 0.7, 0.3), conv(W=1., b=0.1), ('cos', 0.9, 1.1, 0.2),
+                                 ('flatten',), ('dense', 1., 0.1)]),
+                     (2, 5, 4, 3), (3, 5, 4, 3), ('nngp', 'ntk')),
+    'rbf_fcn': (('serial', [('dense', 1., 0.), ('rbf', 0.7), ('dense', 1.3, 0.1), ('rbf', 1.5), ('dense', 1., 0.)]),
+                (4, 10), (3, 10), ('nngp', 'ntk')),
+    'rbf_conv_pool': (('serial', [conv(W=1., b=0.1), ('rbf', 0.5), pool(), conv(), RELU, ('gap',), ('dense', 1., 0.)]),
+                      (2, 6, 6, 2), (2, 6, 6, 2), ('nngp', 'ntk')),
 }
 
 
@@ -124,6 +156,18 @@ def build(spec, stax):
     return stax.AvgPool(spec[1], strides=spec[2], padding=spec[3], normalize_edges=spec[4])
   if kind == 'gap':
     return stax.GlobalAvgPool()
+  if kind == 'sumpool':
+    return stax.SumPool(spec[1], strides=spec[2], padding=spec[3])
+  if kind == 'gsp':
+    return stax.GlobalSumPool()
+  if kind == 'gelu':
+    return stax.Gelu()
+  if kind == 'sin':
+    return stax.Sin(spec[1], spec[2], spec[3])
+  if kind == 'cos':
+    return stax.Cos(spec[1], spec[2], spec[3])
+  if kind == 'rbf':
+    return stax.Rbf(spec[1])
   if kind == 'flatten':
     return stax.Flatten()
   raise ValueError(kind)

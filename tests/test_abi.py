@@ -210,3 +210,35 @@ def test_diag_path_selection_covers_odd_sizes(lib):
   assert low.program.path(64, 64, 1, x64=True) == 'generic'     # 8 x 64 x 64 doubles do not fit
   assert low.program.path(96, 96, 1) == 'generic'
   assert low.program.path(28, 14, 1) == 'generic'
+
+
+def test_fused_path_covers_grey_nonsquare_and_mnist_sizes(lib):
+  """Round 2: the fused stage kernels take any H x W <= 32 x 32 with 1 or 3 channels (embedded in the next
+  shear size); what the embedding cannot express (SAME pools on odd sizes, > 32 px, other channel counts, Erf on
+  embedded sizes) stays on the per-op path."""
+  import cases
+  from neural_tangents_b200 import stax
+
+  def path(spec, H, W, C, **kw):
+    _, _, kf = cases.build(spec, stax)
+    low = stax._lowered(stax._strip(kf._spec), False, False, True)
+    return low.program.path(H, W, C, **kw)
+  gap5 = cases.myrtle(5, 'gap')
+  assert path(gap5, 28, 28, 1) == 'fused'                     # MNIST
+  assert path(gap5, 28, 28, 1, x64=True) == 'fused'
+  assert path(cases.myrtle(5), 32, 32, 1) == 'fused'          # grey CIFAR-sized
+  assert path(cases.CASES['conv_pool_20x12'][0], 20, 12, 3) == 'fused'
+  assert path(cases.CASES['conv_pool_15_odd'][0], 15, 15, 1) == 'fused'      # VALID pool on an odd size: floor
+  assert path(gap5, 24, 24, 3) == 'fused'
+  assert path(gap5, 28, 28, 2) == 'generic'                   # channel counts other than 1 / 3
+  assert path(gap5, 40, 40, 3) == 'generic'                   # larger than the largest shear
+  same_pool = ('serial', [cases.conv(), cases.RELU, cases.pool(pad='SAME'), cases.conv(), cases.RELU, ('gap',)])
+  assert path(same_pool, 16, 16, 3) == 'fused'                # SAME == VALID on even sizes
+  assert path(same_pool, 15, 15, 3) == 'generic'              # SAME pads an odd size with zeros
+  erf5 = ('serial', [('erf', 1., 1., 0.) if l == cases.RELU else l for l in gap5[1]])
+  assert path(erf5, 32, 32, 3) == 'fused' and path(erf5, 28, 28, 1) == 'generic'
+  # SumPool / GlobalSumPool ride the same kernels (epilogue scales)
+  sp = ('serial', [cases.conv(), cases.RELU, ('sumpool', (2, 2), (2, 2), 'VALID'), cases.conv(), cases.RELU, ('gsp',)])
+  assert path(sp, 32, 32, 3) == 'fused' and path(sp, 28, 28, 1) == 'fused'
+  # Gelu / Sin / Rbf run on the per-op path
+  assert path(cases.CASES['gelu_conv'][0], 32, 32, 3) == 'generic'

@@ -347,3 +347,50 @@ def test_batch_symmetric_over_two_devices_is_triangular(nt):
   np.testing.assert_array_equal(two.nngp, one.nngp)
   np.testing.assert_array_equal(two.ntk, one.ntk)
   np.testing.assert_array_equal(nt.batch(kernel_fn, batch_size=2, device_count=2)(x, None, 'ntk'), one.ntk)
+
+
+@pytest.mark.parametrize('shape', [(28, 28, 1), (32, 32, 1), (24, 20, 3), (30, 30, 3), (12, 16, 1)])
+def test_embedded_sizes_fused_path_vs_oracle(nt, shape):
+  """Round 2 widening: any H x W <= 32 x 32, C in {1, 3}, embedded in the next shear size (EMB kernels).  Myrtle-10
+  body (3 + 3 + 3 fused layers, two pools) with a GlobalAvgPool tail, against the oracle and the per-op path."""
+  from oracle import ntk_oracle as O
+  H, W, C = shape
+  spec = cases.myrtle(10, 'gap')
+  _, _, kernel_fn = cases.build(spec, nt.stax)
+  low = nt.stax._lowered(nt.stax._strip(kernel_fn._spec), False, False, True)
+  assert low.program.path(H, W, C) == 'fused'
+  x1 = np.random.default_rng(31).standard_normal((3, H, W, C)).astype(np.float32)
+  x2 = np.random.default_rng(32).standard_normal((2, H, W, C)).astype(np.float32)
+  ref = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'))
+  sref = O.kernel_fn(spec, x1, None, ('nngp', 'ntk'))
+  for x64 in (False, True):
+    nt.config.update('enable_x64', x64)
+    out = kernel_fn(x1, x2, ('nngp', 'ntk'))
+    np.testing.assert_allclose(out.nngp, ref[0], rtol=RTOL[x64])
+    np.testing.assert_allclose(out.ntk, ref[1], rtol=RTOL[x64])
+    np.testing.assert_allclose(kernel_fn(x1, x2, 'nngp'), ref[0], rtol=RTOL[x64])
+    sym = kernel_fn(x1, None, ('nngp', 'ntk'))
+    _check_sym(sym.nngp, sref[0], x64)
+    _check_sym(sym.ntk, sref[1], x64)
+  nt.config.update('enable_x64', False)
+
+
+def test_sum_pools_on_the_fused_kernels(nt):
+  """SumPool / GlobalSumPool (linear.py:1503, 1674) are epilogue scales of the fused kernels."""
+  from oracle import ntk_oracle as O
+  spec = ('serial', [cases.conv(W=1.2, b=0.1), cases.RELU, cases.conv(), cases.RELU,
+                     ('sumpool', (2, 2), (2, 2), 'VALID'), cases.conv(), cases.RELU, ('sumpool', (2, 2), (2, 2), 'SAME'),
+                     ('gsp',), ('dense', 1.1, 0.2)])
+  _, _, kernel_fn = cases.build(spec, nt.stax)
+  for shape in ((32, 32, 3), (28, 28, 1)):
+    low = nt.stax._lowered(nt.stax._strip(kernel_fn._spec), False, False, True)
+    assert low.program.path(*shape) == 'fused'
+    x1 = np.random.default_rng(41).standard_normal((2,) + shape).astype(np.float32)
+    x2 = np.random.default_rng(42).standard_normal((3,) + shape).astype(np.float32)
+    ref = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'))
+    for x64 in (False, True):
+      nt.config.update('enable_x64', x64)
+      out = kernel_fn(x1, x2, ('nngp', 'ntk'))
+      np.testing.assert_allclose(out.nngp, ref[0], rtol=RTOL[x64])
+      np.testing.assert_allclose(out.ntk, ref[1], rtol=RTOL[x64])
+  nt.config.update('enable_x64', False)
