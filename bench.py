@@ -462,10 +462,20 @@ def run_ours(args):
     np.testing.assert_allclose(m['result']['ntk'], res.ntk, rtol=1e-5)
 
   strong = None
-  if args.strong_n > 0 and not args.no_fusion and args.workload == 'myrtle10':
-    strong = [measure_strong(B, args.strong_n, args.dtype)]
+  if args.strong_n > 0 and not args.no_fusion and args.workload == 'myrtle10' and args.dtype == 'f32':
+    strong = [measure_strong(B, args.strong_n, 'f32')]
+    if not args.no_configs:
+      # BASELINE configs[2]: Myrtle-7, 4096 x 4096 at 1 / 2 / 4 / 8 GPUs (stated size; x2 = None)
+      strong.append(measure_strong(B, 4096, 'f32', 'myrtle7'))
     if world >= 8 and args.full_n > 0:
-      strong.append(measure_strong(B, args.full_n, args.dtype))    # BASELINE configs[3] at its stated size
+      # BASELINE configs[3] (Myrtle-10, 10000 x 10000, FP32 and FP64) and configs[4] (WideResNet Relu / Erf,
+      # 4096 x 4096 at 8 GPUs) at their stated sizes
+      strong.append(measure_strong(B, args.full_n, 'f32'))
+      if not args.no_configs:
+        strong.append(measure_strong(B, 4096, 'f32', 'wrn'))
+        strong.append(measure_strong(B, 4096, 'f32', 'wrn_erf'))
+        strong.append(measure_strong(B, args.full_n, 'f64'))
+    B.set_dtype(args.dtype)
 
   configs = None
   if world == 1 and not args.no_configs and args.workload == 'myrtle10' and args.dtype == 'f32':

@@ -135,6 +135,11 @@ class Arena {
     }
     free_[off] = sz;
   }
+  size_t largest_free() const {
+    size_t m = 0;
+    for (const auto& f : free_) m = f.second > m ? f.second : m;
+    return m;
+  }
   size_t peak() const { return peak_; }
   bool dry() const { return dry_; }
 

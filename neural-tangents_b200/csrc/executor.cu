@@ -1126,7 +1126,8 @@ int ntk_context_create(int32_t device, size_t workspace_bytes, ntk_context_t** o
   if (workspace_bytes == 0) {
     size_t free_b = 0, total_b = 0;
     NTK_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    workspace_bytes = std::min<size_t>((size_t)(free_b * 0.5), (size_t)48 << 30);
+    // default: 70 % of the free HBM, at most 128 GB (a B200 has 180 GB; big tiles amortise the launch tails)
+    workspace_bytes = std::min<size_t>((size_t)(free_b * 0.7), (size_t)128 << 30);
   }
   NTK_CUDA(cudaMalloc((void**)&c->ws, workspace_bytes));
   c->ws_bytes = workspace_bytes;

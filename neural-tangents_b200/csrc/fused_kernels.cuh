@@ -1417,8 +1417,16 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
       sum2 = std::max(sum2, bsz[i] + (i + 1 < bsz.size() ? bsz[i + 1] : 0));
     }
   }
-  // free arena bytes: probe by allocating progressively smaller blocks
+  // Tile size from the free workspace: two boundary buffers of max_b bytes per pair plus the [pairs] results.
+  // (Large tiles matter: every stage launch ends in a partial wave of ~1 ms CTAs; 40k-pair tiles lose ~3 % to
+  // those tails, 150k-pair tiles < 1 %.)
   long long tile_pairs = (long long)n1 * n2;
+  if (sum2 > 0) {
+    const size_t per_pair = 2 * max_b + 2 * sizeof(T);
+    const size_t avail = arena.largest_free();
+    const long long fit = avail > ((size_t)8 << 20) ? (long long)((avail - ((size_t)8 << 20)) / per_pair) : 1;
+    tile_pairs = std::max<long long>(1, std::min<long long>(tile_pairs, fit));
+  }
   T* bnd[2] = {nullptr, nullptr};
   size_t bnd_bytes = 0;
   if (sum2 > 0) {
