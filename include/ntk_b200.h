@@ -249,6 +249,28 @@ int ntk_comm_all_gather(ntk_comm_t* comm, const void* send_dev, void* recv_dev, 
 int ntk_sym_assemble(ntk_context_t* ctx, int32_t dtype, const void* slabs, int64_t ld_slabs,
                      const int32_t* row_of, int32_t n, void* out, int64_t ld_out);
 
+/* ---- the caller of the Gram path: closed-form inference on device-resident matrices ----------------
+ * `predict.gp_inference` / `gradient_descent_mse_ensemble(t=None)` (`_src/predict.py:566-750,753-1100`) solve
+ * (K_dd + reg I) alpha = y and return K_td alpha.  These entry points do that where the Gram kernels left their
+ * results, in HBM, in float64: `ntk_chol_factor` copies / widens a symmetric [n, n] matrix of `dtype`, adds
+ * diag_reg * (absolute ? 1 : trace(K) / n) to the diagonal (`_add_diagonal_regularizer`, `_src/predict.py:1186-1214`)
+ * and factorises it (blocked Cholesky on the fp64 tensor cores; `_get_cho_solve`, `:1217-1240`).
+ * All work is enqueued on the context stream; only ntk_chol_info synchronises. */
+typedef struct ntk_chol ntk_chol_t;
+int ntk_chol_factor(ntk_context_t* ctx, int32_t dtype, const void* k_dev, int32_t n, int64_t ld, double diag_reg,
+                    int32_t absolute, ntk_chol_t** out);
+/* info = 0: success; info = k > 0: the leading minor of order k is not positive definite (LAPACK convention). */
+int ntk_chol_info(ntk_context_t* ctx, const ntk_chol_t* f, int32_t* info);
+/* B <- (K + reg I)^-1 B for B [n, nrhs] float64 row-major (ldb elements); work_dev holds n * nrhs doubles. */
+int ntk_chol_solve(ntk_context_t* ctx, const ntk_chol_t* f, double* b_dev, int32_t nrhs, int64_t ldb,
+                   double* work_dev);
+/* out[m, nrhs] (float64) = A[m, n] (dtype_a) X[n, nrhs] (float64): K_test_train alpha. */
+int ntk_matmul_f64(ntk_context_t* ctx, int32_t dtype_a, const void* a_dev, int32_t m, int32_t n, int64_t lda,
+                   const double* x_dev, int32_t nrhs, int64_t ldx, double* out_dev, int64_t ldo);
+/* Lower Cholesky factor, [n, n] float64 row-major on the device (strict upper triangle zero). */
+const double* ntk_chol_factor_ptr(const ntk_chol_t* f);
+void ntk_chol_destroy(ntk_chol_t* f);
+
 /* ---- device memory helpers (so a host language needs no CUDA binding) ---- */
 int ntk_device_malloc(int32_t device, size_t bytes, void** ptr);
 int ntk_device_free(int32_t device, void* ptr);

@@ -37,7 +37,9 @@ EXPORTED_SYMBOLS = (
     'ntk_comm_destroy', 'ntk_comm_rank', 'ntk_comm_world', 'ntk_comm_nccl_version', 'ntk_comm_broadcast',
     'ntk_comm_all_gather', 'ntk_sym_assemble', 'ntk_memset_async', 'ntk_context_device', 'ntk_host_alloc',
     'ntk_host_free', 'ntk_event_create', 'ntk_event_record', 'ntk_event_elapsed_ms', 'ntk_event_destroy',
-    'ntk_stream_create', 'ntk_stream_synchronize', 'ntk_stream_query', 'ntk_stream_destroy')
+    'ntk_stream_create', 'ntk_stream_synchronize', 'ntk_stream_query', 'ntk_stream_destroy',
+    'ntk_chol_factor', 'ntk_chol_info', 'ntk_chol_solve', 'ntk_matmul_f64', 'ntk_chol_factor_ptr',
+    'ntk_chol_destroy')
 
 
 class NtkOp(ctypes.Structure):
@@ -150,6 +152,14 @@ def load():
     lib.ntk_stream_query.argtypes = [vp, P(i32)]
     lib.ntk_stream_destroy.argtypes = [vp]
     lib.ntk_stream_destroy.restype = None
+    lib.ntk_chol_factor.argtypes = [vp, i32, vp, i32, i64, ctypes.c_double, i32, P(vp)]
+    lib.ntk_chol_info.argtypes = [vp, vp, P(i32)]
+    lib.ntk_chol_solve.argtypes = [vp, vp, vp, i32, i64, vp]
+    lib.ntk_matmul_f64.argtypes = [vp, i32, vp, i32, i32, i64, vp, i32, i64, vp, i64]
+    lib.ntk_chol_factor_ptr.argtypes = [vp]
+    lib.ntk_chol_factor_ptr.restype = vp
+    lib.ntk_chol_destroy.argtypes = [vp]
+    lib.ntk_chol_destroy.restype = None
     _lib = lib
     return lib
 
@@ -568,3 +578,74 @@ def sym_assemble(ctx, dtype, slabs_ptr, ld_slabs, row_of_ptr, n, out_ptr, ld_out
   with ctx.lock:
     check(load().ntk_sym_assemble(ctx.handle, dtype_code(dtype), ctypes.c_void_p(slabs_ptr), ld_slabs,
                                   ctypes.c_void_p(row_of_ptr), n, ctypes.c_void_p(out_ptr), ld_out))
+
+
+class DeviceCholesky:
+  """Regularised Cholesky factor of a device-resident symmetric matrix (`ntk_chol_*`): `(K + reg I) = L L^T` in
+  float64 on the GPU that holds K.  `solve(b)` takes / returns host arrays of shape [n, ...]; `matmul(a_ptr, ...)`
+  multiplies a device matrix with the last solution without leaving the device."""
+
+  def __init__(self, ctx, dtype, k_ptr, n, ld, diag_reg=0., absolute=False):
+    self._lib, self.ctx, self.n = load(), ctx, int(n)
+    self._h = ctypes.c_void_p()
+    with ctx.lock:
+      check(self._lib.ntk_chol_factor(ctx.handle, dtype_code(dtype), ctypes.c_void_p(k_ptr), n, ld, float(diag_reg),
+                                      int(bool(absolute)), ctypes.byref(self._h)))
+      info = ctypes.c_int32()
+      check(self._lib.ntk_chol_info(ctx.handle, self._h, ctypes.byref(info)))
+    if info.value != 0:
+      self.close()
+      raise np.linalg.LinAlgError(f'{info.value}-th leading minor of the array is not positive definite')
+
+  def solve_device(self, b_ptr, nrhs, ldb=None):
+    """In place on a device [n, nrhs] float64 matrix."""
+    work = self.ctx.malloc(self.n * nrhs * 8)
+    try:
+      with self.ctx.lock:
+        check(self._lib.ntk_chol_solve(self.ctx.handle, self._h, ctypes.c_void_p(b_ptr), nrhs, ldb or nrhs,
+                                       ctypes.c_void_p(work)))
+        self.ctx.synchronize()
+    finally:
+      self.ctx.free(work)
+
+  def solve(self, b):
+    b = np.asarray(b, np.float64)
+    b2 = np.ascontiguousarray(b.reshape(self.n, -1))
+    d = self.ctx.malloc(b2.nbytes)
+    try:
+      self.ctx.h2d(d, b2)
+      self.solve_device(d, b2.shape[1])
+      out = self.ctx.d2h(np.empty_like(b2), d)
+    finally:
+      self.ctx.free(d)
+    return out.reshape(b.shape)
+
+  def matmul(self, a_dtype, a_ptr, m, lda, x):
+    """[m, n] device matrix (a_dtype) times the host matrix x [n, nrhs] -> host [m, nrhs] float64."""
+    x2 = np.ascontiguousarray(np.asarray(x, np.float64).reshape(self.n, -1))
+    nrhs = x2.shape[1]
+    dx, do = self.ctx.malloc(x2.nbytes), self.ctx.malloc(m * nrhs * 8)
+    try:
+      self.ctx.h2d(dx, x2)
+      with self.ctx.lock:
+        check(self._lib.ntk_matmul_f64(self.ctx.handle, dtype_code(a_dtype), ctypes.c_void_p(a_ptr), m, self.n, lda,
+                                       ctypes.c_void_p(dx), nrhs, nrhs, ctypes.c_void_p(do), nrhs))
+      return self.ctx.d2h(np.empty((m, nrhs), np.float64), do)
+    finally:
+      self.ctx.free(dx)
+      self.ctx.free(do)
+
+  def factor(self):
+    """The lower factor L as a host array (tests)."""
+    return self.ctx.d2h(np.empty((self.n, self.n), np.float64), self._lib.ntk_chol_factor_ptr(self._h))
+
+  def close(self):
+    if self._h:
+      self._lib.ntk_chol_destroy(self._h)
+      self._h = ctypes.c_void_p()
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass

@@ -4,10 +4,11 @@
 (`:1103-1150`) for the case the B200 path produces:
 `[n1, n2]` kernel matrices (outputs block-diagonal along the logit axis, `trace_axes=(-1,)`).
 
-The Gram matrices come from `kernel_fn` (libntk_b200.so on the GPU); the n x n factorisations
-here are host float64 linear algebra (Cholesky for t = None, one symmetric eigendecomposition
-for finite t), which is what the reference does with `jax.scipy.linalg` on its default device.
-Moving these solves onto the GPU next to the Gram slabs is the round-2 item of DESIGN.md.
+The Gram matrices come from `kernel_fn` (libntk_b200.so on the GPU).  `gradient_descent_mse_ensemble(t=None)`
+means -- the common case, `K_td (K_dd + reg I)^-1 y` -- never leave the GPU: the train-train Gram stays in HBM,
+is factorised there in float64 (`ntk_chol_factor`: blocked Cholesky on the fp64 tensor cores), and only the
+[n_test, n_out] predictions are copied back (`_DeviceMeans`).  Posterior covariances and finite times use host
+float64 linear algebra (Cholesky / one symmetric eigendecomposition), as the reference does with `jax.scipy.linalg`.
 """
 import collections
 from typing import Callable, Optional
@@ -149,8 +150,40 @@ def gp_inference(k_train_train, y_train, diag_reg: float = 0., diag_reg_absolute
   return predict_fn
 
 
+class _DeviceMeans:
+  """Infinite-time means on the device (`_src/predict.py:858-869,936-939` + `gp_inference` mean, `:681-689`):
+  K_dd is computed into HBM, (K_dd + reg I) = L L^T and alpha = (K_dd + reg I)^-1 y are cached per kernel name,
+  `mean(name, x_test)` = K_td alpha with K_td produced and consumed on the GPU."""
+
+  def __init__(self, kernel_fn, x_train, y, diag_reg, absolute):
+    self.kernel_fn, self.x_train, self.y = kernel_fn, x_train, y
+    self.diag_reg, self.absolute = diag_reg, absolute
+    self.chol, self.alpha = {}, {}
+
+  def _factor(self, name):
+    from . import _lib, stax
+    if name not in self.chol:
+      k = stax._gram_on_device(self.kernel_fn, self.x_train, None, (name,))[name]
+      try:
+        self.chol[name] = _lib.DeviceCholesky(k.ctx, k.dtype, k.ptr, k.shape[0], k.shape[1], self.diag_reg,
+                                              self.absolute)
+      finally:
+        k.free()
+      self.alpha[name] = self.chol[name].solve(self.y)
+    return self.chol[name]
+
+  def mean(self, name, x_test):
+    from . import stax
+    ch = self._factor(name)
+    k_td = stax._gram_on_device(self.kernel_fn, x_test, self.x_train, (name,))[name]
+    try:
+      return ch.matmul(k_td.dtype, k_td.ptr, k_td.shape[0], k_td.shape[1], self.alpha[name])
+    finally:
+      k_td.free()
+
+
 def gradient_descent_mse_ensemble(kernel_fn, x_train, y_train, learning_rate: float = 1., diag_reg: float = 0.,
-                                  diag_reg_absolute_scale: bool = False, trace_axes=(-1,),
+                                  diag_reg_absolute_scale: bool = False, trace_axes=(-1,), device_solve=None,
                                   **kernel_fn_train_train_kwargs) -> Callable:
   """Mean and covariance of an infinite ensemble of infinitely wide networks trained on MSE with
   continuous gradient descent for time `t` (`_src/predict.py:753-1100`).
@@ -162,6 +195,13 @@ def gradient_descent_mse_ensemble(kernel_fn, x_train, y_train, learning_rate: fl
   y = _check_targets(y_train, trace_axes)
   norm = float(y.size)
   cache, eig, inf = {}, {}, {}
+  # `device_solve`: None = on the GPU whenever `kernel_fn` is a B200 kernel_fn called without extra kwargs,
+  # False = host SciPy (the round-1 path), True = require the device path.
+  native = hasattr(kernel_fn, '_spec') and not kernel_fn_train_train_kwargs and isinstance(x_train, np.ndarray)
+  if device_solve and not native:
+    raise ValueError('device_solve=True needs a kernel_fn built by neural_tangents_b200.stax and no extra kwargs')
+  dev = _DeviceMeans(kernel_fn, x_train, y, diag_reg, diag_reg_absolute_scale) if (native and device_solve is not False) \
+      else None
 
   def k_train_train(names):
     missing = tuple(n for n in names if n not in cache)
@@ -196,6 +236,10 @@ def gradient_descent_mse_ensemble(kernel_fn, x_train, y_train, learning_rate: fl
   def predict_fn(t=None, x_test=None, get=None, compute_cov: bool = False, **kernel_fn_test_test_kwargs):
     _, names = _canonicalize_get(get)
     dep = dependency(names, compute_cov)
+    if dev is not None and t is None and not compute_cov and not kernel_fn_test_test_kwargs:
+      # infinite time, means only: Gram -> Cholesky -> K_td alpha, all in HBM
+      vals = [y.copy() if x_test is None else dev.mean(g, x_test) for g in names]
+      return _pack(get, names, vals)
     k_dd = k_train_train(dep)
     kw = dict(kernel_fn_train_train_kwargs)
     kw.update(kernel_fn_test_test_kwargs)

@@ -447,6 +447,43 @@ def _sym_rows(kernel_fn, x, r0, r1, names):
   return {n: res[n] for n in names}
 
 
+def _gram_on_device(kernel_fn, x1, x2, names):
+  """`kernel_fn(x1, x2, names)` with the [n1, n2] results left in HBM: `{name: distributed.DeviceArray}` on this
+  thread's GPU (the consumer is `predict`'s device-side Cholesky: no host round trip of the Gram matrices)."""
+  from .distributed import DeviceArray
+  spec = kernel_fn._spec
+  dt = np.dtype(config.dtype)
+  _check_inputs(x1, x2)
+  spatial = x1.ndim == 4
+  H, W = (x1.shape[1], x1.shape[2]) if spatial else (0, 0)
+  low = _lowered(_strip(spec), False, False, spatial)
+  oh, _, _ = low.program.output_shape(H, W)
+  if oh > 0:
+    raise NotImplementedError('device-resident Grams are [n1, n2] matrices; this network keeps spatial axes')
+  ctx = _lib.get_context()
+  n1 = x1.shape[0]
+  n2 = n1 if x2 is None else x2.shape[0]
+  flags = (_lib.FLAG_NO_FUSION if config.disable_fusion else 0) | (_lib.FLAG_FULL_SQUARE if config.full_square else 0)
+  d1 = DeviceArray(ctx, x1.shape, dt)
+  d2 = None if x2 is None else DeviceArray(ctx, x2.shape, dt)
+  out = {n: DeviceArray(ctx, (n1, n2), dt) for n in ('nngp',) + (('ntk',) if 'ntk' in names else ())}
+  try:
+    k1 = ctx.h2d(d1.ptr, np.ascontiguousarray(x1, dt))
+    k2 = None if x2 is None else ctx.h2d(d2.ptr, np.ascontiguousarray(x2, dt))
+    _lib.gram_device(ctx, low.program, dt, d1.ptr, n1, None if d2 is None else d2.ptr, n2, H, W, x1.shape[-1], flags,
+                     out['nngp'].ptr, out['ntk'].ptr if 'ntk' in out else None, n2)
+    ctx.synchronize()
+    del k1, k2
+  finally:
+    d1.free()
+    if d2 is not None:
+      d2.free()
+  for n in list(out):
+    if n not in names:
+      out.pop(n).free()
+  return out
+
+
 def _apply_to_kernel(spec, k: Kernel):
   if not k.diagonal_batch:
     raise NotImplementedError('`diagonal_batch=False` kernels are outside the B200 hot path')
