@@ -104,6 +104,7 @@ k_dgemm(int M, int N, int K, double alpha, const TA* __restrict__ A, long long l
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         if (col + e >= N) continue;
+        if (LOWER && col + e > row) continue;   // the strict upper triangle is never written (stays zero)
         double* p = C + (long long)row * ldc + col + e;
         *p = beta == 0.0 ? alpha * c[i][j][e] : alpha * c[i][j][e] + beta * *p;
       }

@@ -87,9 +87,12 @@ def test_ensemble_means_on_device_equal_host_solve(nt, x64):
   np.testing.assert_allclose(a.ntk, b.ntk, rtol=tol, atol=tol)
   np.testing.assert_allclose(dev(t=None, x_test=x_test, get='ntk'), a.ntk, rtol=0, atol=0)
   np.testing.assert_array_equal(dev(t=None, x_test=None, get='ntk'), y)
-  if x64:
-    k_dd = O.kernel_fn(spec, x_train, None, ('ntk',))[0]
-    k_td = O.kernel_fn(spec, x_test, x_train, ('ntk',))[0]
-    A = k_dd + 1e-4 * np.trace(k_dd) / 70 * np.eye(70)
-    np.testing.assert_allclose(a.ntk, k_td @ np.linalg.solve(A, y), rtol=1e-7, atol=1e-9)
+  if x64:   # against the float64 oracle on a problem it can hold in host memory (12 x 12 pairs of 32^4 tensors)
+    xs, ys = x_train[:12], y[:12]
+    small = nt.predict.gradient_descent_mse_ensemble(kernel_fn, xs, ys, diag_reg=1e-4, device_solve=True)
+    k_dd = O.kernel_fn(spec, xs, None, ('ntk',))[0]
+    k_td = O.kernel_fn(spec, x_test[:3], xs, ('ntk',))[0]
+    A = k_dd + 1e-4 * np.trace(k_dd) / 12 * np.eye(12)
+    np.testing.assert_allclose(small(t=None, x_test=x_test[:3], get='ntk'), k_td @ np.linalg.solve(A, ys), rtol=1e-7,
+                               atol=1e-9)
   nt.config.update('enable_x64', False)
