@@ -64,9 +64,12 @@ struct ResArgs {
   FLayer<T> lp[2];  // ABRelu constants in front of unit u (pre-scaled by unit u's alpha); bias of unit u
 };
 
-template <int S>
+// fp32: 8 consecutive w per thread; fp64: 4 -- the three rings of 8 doubles for K and T alone are 192 registers, which
+// spilled ~1 KB per thread in round 1 (k_res<double>: 680-712 byte stack frames); with 4 the kernel fits and twice as
+// many warps cover the DFMA latency.
+template <int S, int W = 8>
 struct ResGeom {
-  static constexpr int WPT = 8;
+  static constexpr int WPT = W;
   static constexpr int TPP = S * S / WPT;
   static constexpr int NT = TPP < 128 ? 128 : TPP;
   static constexpr int GROUPS = NT / TPP;
@@ -77,10 +80,15 @@ struct ResGeom {
 
 // ERF: the network contains Erf activations (a runtime branch per activation row picks the closed
 // form); pure-ABRelu networks run the ERF = false instantiation, which carries no Erf code.
+template <typename T>
+struct ResWpt {
+  static constexpr int value = sizeof(T) == 8 ? 4 : 8;
+};
+
 template <typename T, int S, int IN, bool NTK, int CIN, bool ERF>
-__global__ void __launch_bounds__(ResGeom<S>::NT)
+__global__ void __launch_bounds__((ResGeom<S, ResWpt<T>::value>::NT))
 k_res(const ResArgs<T> a) {
-  using G = ResGeom<S>;
+  using G = ResGeom<S, ResWpt<T>::value>;
   using V2 = typename Vec2<T>::type;
   constexpr int WPT = G::WPT, TPP = G::TPP, LPG = G::LPG, NWB = G::NWB, LW = G::LW;
 
@@ -693,12 +701,12 @@ int launch_res(cudaStream_t stream, int64_t* launches, int S, bool from_x, const
   };
   auto smem_for = [&](int s, bool fx) {
     const size_t per = (fx ? (size_t)s * s * 3 + (size_t)s * s * 4 : 0) + 2 * (size_t)(2 * s * s * 2);
-    const int tpp = s * s / 8, nt = tpp < 128 ? 128 : tpp;
+    const int tpp = s * s / ResWpt<T>::value, nt = tpp < 128 ? 128 : tpp;
     return per * (nt / tpp) * sizeof(T);
   };
 #define NTK_RES_CASE(SS)                                                                              \
   if (S == SS) {                                                                                      \
-    using G = ResGeom<SS>;                                                                            \
+    using G = ResGeom<SS, ResWpt<T>::value>;                                                          \
     if (from_x) return go(k_res<T, SS, IN_FROM_X, NTK, 3, ERF>, G::NT, G::GROUPS, smem_for(SS, true)); \
     return go(k_res<T, SS, IN_LOAD, NTK, 1, ERF>, G::NT, G::GROUPS, smem_for(SS, false));             \
   }

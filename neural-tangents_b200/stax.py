@@ -26,7 +26,7 @@ import enum
 
 __all__ = ['serial', 'parallel', 'FanOut', 'FanInSum', 'Identity', 'Dense', 'Conv', 'Relu',
            'ABRelu', 'LeakyRelu', 'Abs', 'Erf', 'Sigmoid_like', 'Gelu', 'Sin', 'Cos', 'Rbf', 'AvgPool', 'SumPool',
-           'GlobalAvgPool', 'GlobalSumPool', 'Flatten', 'Padding']
+           'GlobalAvgPool', 'GlobalSumPool', 'Flatten', 'Padding', 'Bool', 'Diagonal']
 
 
 class Padding(enum.Enum):
@@ -44,7 +44,7 @@ _OUT_OF_SCOPE = ('repeat', 'Elementwise', 'ElementwiseNumerical', 'Exp', 'ExpNor
                  'ConvTranspose', 'Index', 'DotGeneral', 'Dropout', 'GlobalSelfAttention',
                  'ImageResize', 'LayerNorm', 'Slice', 'FanInConcat',
                  'FanInProd', 'AggregateImplementation', 'AttentionMechanism', 'PositionalEmbedding',
-                 'Bool', 'Diagonal', 'MaskedArray', 'layer', 'requires', 'supports_masking', 'unmask_fn')
+                 'MaskedArray', 'layer', 'requires', 'supports_masking', 'unmask_fn')
 
 
 def __getattr__(name):
@@ -70,6 +70,87 @@ class FrozenDict(dict):
 
 _DEFAULT_INPUT_REQ = FrozenDict(diagonal_batch=True, diagonal_spatial=False, batch_axis=0,
                                 use_dropout=False, channel_axis=-1, mask_constant=None)
+
+
+class Bool(enum.IntEnum):
+  """Trinary logic of the requirement negotiation (`_src/stax/requirements.py:397-422`)."""
+  NO = 0
+  MAYBE = 1
+  YES = 2
+
+  def __and__(self, other):
+    return Bool(min(int(self), int(other)))
+
+  __rand__ = __and__
+
+
+class Diagonal:
+  """Whether a layer can work on / emits kernels that hold only the spatial diagonal
+  (`_src/stax/requirements.py:425-515`).  `a >> b` is the requirement of `b(a(.))` (serial), `a & b` that of two
+  parallel branches; `bool(d)` is the `diagonal_spatial` the network runs with when the user does not ask."""
+  __slots__ = ('input', 'output')
+
+  def __init__(self, input: Bool = Bool.YES, output: Bool = Bool.NO):
+    object.__setattr__(self, 'input', Bool(input))
+    object.__setattr__(self, 'output', Bool(output))
+
+  def __setattr__(self, *a):
+    raise AttributeError('Diagonal is immutable')
+
+  def __rshift__(self, other: 'Diagonal') -> 'Diagonal':
+    if self.output == Bool.YES:          # everything behind is diagonal already: later layers cannot constrain
+      return self
+    if self.output > Bool.NO and other.input > Bool.NO:
+      inp = self.input
+    elif self.output == Bool.NO and other.input < Bool.YES:
+      inp = Bool.NO
+    else:
+      inp = Bool(min(self.input, other.input))
+    return Diagonal(inp, other.output)
+
+  def __lshift__(self, other: 'Diagonal') -> 'Diagonal':
+    return other >> self
+
+  def __and__(self, other: 'Diagonal') -> 'Diagonal':
+    return Diagonal(self.input & other.input, self.output & other.output)
+
+  __rand__ = __and__
+
+  def __bool__(self):
+    return self.input == Bool.YES and self.output > Bool.NO
+
+  def __eq__(self, other):
+    return isinstance(other, Diagonal) and (self.input, self.output) == (other.input, other.output)
+
+  def __hash__(self):
+    return hash((int(self.input), int(self.output)))
+
+  def __repr__(self):
+    return f'Diagonal(input={self.input!r}, output={self.output!r})'
+
+
+def _fold_input_req(kernel_fns, fold):
+  """`_get_input_req_attr` (`_src/stax/combinators.py:204-268`): requirements of a `serial` (fold = `>>`) or
+  `parallel` (fold = `&`) combination from those of its members."""
+  import operator
+  import warnings
+  req = {}
+  for f in kernel_fns:
+    for k, v in getattr(f, 'input_req', {}).items():
+      if k == 'use_dropout':
+        if k in req and req[k] != v:
+          raise ValueError('`use_dropout` is a single whole-network attribute and cannot be set to different values.')
+        req[k] = v
+      elif k in ('batch_axis', 'channel_axis'):
+        if k not in req:
+          req[k] = v
+        elif fold is operator.and_ and req[k] != v:
+          warnings.warn(f'For `kernel_fn`, `{k}` parameters must match in all parallel branches, got {req[k]} and {v}.')
+      elif k in ('diagonal_batch', 'diagonal_spatial'):
+        req[k] = fold(req[k], v) if k in req else v
+      else:
+        raise NotImplementedError(k)
+  return req
 
 _KERNEL_FIELDS = ('nngp', 'ntk', 'cov1', 'cov2', 'x1_is_x2', 'is_gaussian', 'is_reversed',
                   'is_input', 'diagonal_batch', 'diagonal_spatial', 'shape1', 'shape2',
@@ -336,6 +417,10 @@ def _make_kernel_fn(spec, req):
       raise NotImplementedError('`diagonal_batch=False` is outside the B200 hot path')
     if kwargs:
       raise NotImplementedError(f'unsupported kernel_fn arguments: {sorted(kwargs)}')
+    d_req = req.get('diagonal_spatial')
+    if diagonal_spatial is True and (d_req is False or (isinstance(d_req, Diagonal) and d_req.input == Bool.NO)):
+      raise ValueError(f'Asked to compute `kernel_fn` output with `diagonal_spatial == True`, while `kernel_fn` '
+                       f'requires `diagonal_spatial == {d_req}`.')
 
     _warn_fan_in(spec)
     if isinstance(x1_or_kernel, Kernel) and x2 is None:
@@ -529,9 +614,9 @@ def _apply_to_kernel(spec, k: Kernel):
 
 
 def _layer(spec, init_fn, apply_fn, req=None):
-  r = dict(_DEFAULT_INPUT_REQ)
-  r.update(req or {})
-  return init_fn, apply_fn, _make_kernel_fn(spec, FrozenDict(r))
+  """`req`: the static requirements of the layer as the reference's `@requires(...)` states them; `nt.batch` and
+  the combinators read them from `kernel_fn.input_req` (`_src/stax/requirements.py:371-386,1053`)."""
+  return init_fn, apply_fn, _make_kernel_fn(spec, FrozenDict(req or {}))
 
 
 def _only_supported(**conds):
@@ -562,7 +647,7 @@ def Dense(out_dim: int, W_std: float = 1., b_std: Optional[float] = None, batch_
     out = W_std / math.sqrt(inputs.shape[-1]) * (inputs @ W)
     return out if b is None else out + b_std * b
 
-  return _layer(spec, init_fn, apply_fn)
+  return _layer(spec, init_fn, apply_fn, dict(batch_axis=0, channel_axis=-1, diagonal_spatial=Diagonal()))
 
 
 def Conv(out_chan: int, filter_shape, strides=None, padding: str = 'VALID', W_std: float = 1.,
@@ -595,7 +680,8 @@ def Conv(out_chan: int, filter_shape, strides=None, padding: str = 'VALID', W_st
     out = W_std / math.sqrt(inputs.shape[-1] * k[0] * k[1]) * out
     return out if b is None else out + b_std * b
 
-  return _layer(spec, init_fn, apply_fn)
+  # shared weights mix positions: the output is never spatially diagonal (`linear.py:1321-1324`)
+  return _layer(spec, init_fn, apply_fn, dict(batch_axis=0, channel_axis=3, diagonal_spatial=Diagonal(output=Bool.NO)))
 
 
 def ABRelu(a: float, b: float, do_stabilize: bool = False):
@@ -603,7 +689,7 @@ def ABRelu(a: float, b: float, do_stabilize: bool = False):
   spec = ('abrelu', float(a), float(b), bool(do_stabilize))
   init_fn = lambda rng, input_shape: (input_shape, ())
   apply_fn = lambda params, inputs, **kw: a * np.minimum(inputs, 0) + b * np.maximum(inputs, 0)
-  return _layer(spec, init_fn, apply_fn)
+  return _layer(spec, init_fn, apply_fn, dict(diagonal_spatial=Diagonal()))
 
 
 def Relu(do_stabilize: bool = False):
@@ -630,7 +716,7 @@ def Erf(a: float = 1., b: float = 1., c: float = 0.):
     from scipy.special import erf as _erf
     return a * _erf(b * inputs) + c
 
-  return _layer(spec, init_fn, apply_fn)
+  return _layer(spec, init_fn, apply_fn, dict(diagonal_spatial=Diagonal()))
 
 
 def Sigmoid_like():
@@ -649,7 +735,7 @@ def Gelu(approximate: bool = False):
     from scipy.special import erf as _erf
     return 0.5 * inputs * (1 + _erf(inputs / math.sqrt(2)))
 
-  return _layer(spec, init_fn, apply_fn)
+  return _layer(spec, init_fn, apply_fn, dict(diagonal_spatial=Diagonal()))
 
 
 def Sin(a: float = 1., b: float = 1., c: float = 0.):
@@ -657,7 +743,7 @@ def Sin(a: float = 1., b: float = 1., c: float = 0.):
   spec = ('sin', float(a), float(b), float(c))
   init_fn = lambda rng, input_shape: (input_shape, ())
   apply_fn = lambda params, inputs, **kw: a * np.sin(b * inputs + c)
-  return _layer(spec, init_fn, apply_fn)
+  return _layer(spec, init_fn, apply_fn, dict(diagonal_spatial=Diagonal()))
 
 
 def Cos(a: float = 1., b: float = 1., c: float = 0.):
@@ -670,7 +756,7 @@ def Rbf(gamma: float = 1.0):
   spec = ('rbf', float(gamma))
   init_fn = lambda rng, input_shape: (input_shape, ())
   apply_fn = lambda params, inputs, **kw: math.sqrt(2) * np.sin(math.sqrt(2 * gamma) * inputs + math.pi / 4)
-  return _layer(spec, init_fn, apply_fn)
+  return _layer(spec, init_fn, apply_fn, dict(diagonal_spatial=Diagonal()))
 
 
 def SumPool(window_shape, strides=None, padding: str = 'VALID', batch_axis: int = 0, channel_axis: int = -1):
@@ -691,7 +777,7 @@ def SumPool(window_shape, strides=None, padding: str = 'VALID', batch_axis: int 
   def apply_fn(params, inputs, **kwargs):
     return _windows(inputs, w, strides, padding).sum(axis=(3, 4))
 
-  return _layer(spec, init_fn, apply_fn)
+  return _layer(spec, init_fn, apply_fn, dict(batch_axis=0, channel_axis=-1, diagonal_spatial=Diagonal(input=Bool.MAYBE)))
 
 
 def GlobalSumPool(batch_axis: int = 0, channel_axis: int = -1):
@@ -700,7 +786,7 @@ def GlobalSumPool(batch_axis: int = 0, channel_axis: int = -1):
   spec = ('gsp',)
   init_fn = lambda rng, input_shape: ((input_shape[0], input_shape[-1]), ())
   apply_fn = lambda params, inputs, **kw: inputs.sum(axis=tuple(range(1, inputs.ndim - 1)))
-  return _layer(spec, init_fn, apply_fn)
+  return _layer(spec, init_fn, apply_fn, dict(batch_axis=0, channel_axis=-1, diagonal_spatial=Diagonal(input=Bool.MAYBE, output=Bool.YES)))
 
 
 def AvgPool(window_shape, strides=None, padding: str = 'VALID', normalize_edges: bool = False,
@@ -727,7 +813,7 @@ def AvgPool(window_shape, strides=None, padding: str = 'VALID', normalize_edges:
       return out / cnt
     return out / (w[0] * w[1])
 
-  return _layer(spec, init_fn, apply_fn)
+  return _layer(spec, init_fn, apply_fn, dict(batch_axis=0, channel_axis=-1, diagonal_spatial=Diagonal(input=Bool.MAYBE)))
 
 
 def GlobalAvgPool(batch_axis: int = 0, channel_axis: int = -1):
@@ -736,7 +822,7 @@ def GlobalAvgPool(batch_axis: int = 0, channel_axis: int = -1):
   spec = ('gap',)
   init_fn = lambda rng, input_shape: ((input_shape[0], input_shape[-1]), ())
   apply_fn = lambda params, inputs, **kw: inputs.mean(axis=tuple(range(1, inputs.ndim - 1)))
-  return _layer(spec, init_fn, apply_fn)
+  return _layer(spec, init_fn, apply_fn, dict(batch_axis=0, channel_axis=-1, diagonal_spatial=Diagonal(input=Bool.MAYBE, output=Bool.YES)))
 
 
 def Flatten(batch_axis: int = 0, batch_axis_out: int = 0):
@@ -745,7 +831,7 @@ def Flatten(batch_axis: int = 0, batch_axis_out: int = 0):
   spec = ('flatten',)
   init_fn = lambda rng, input_shape: ((input_shape[0], int(np.prod(input_shape[1:]))), ())
   apply_fn = lambda params, inputs, **kw: inputs.reshape(inputs.shape[0], -1)
-  return _layer(spec, init_fn, apply_fn)
+  return _layer(spec, init_fn, apply_fn, dict(batch_axis=0, channel_axis=None, diagonal_spatial=Diagonal(output=Bool.YES)))
 
 
 def Identity():
@@ -807,7 +893,8 @@ def serial(*layers):
       inputs = f(p, inputs, **kwargs)
     return inputs
 
-  return _layer(spec, init_fn, apply_fn)
+  import operator
+  return _layer(spec, init_fn, apply_fn, _fold_input_req(kernel_fns, operator.rshift))
 
 
 def parallel(*layers):
@@ -823,4 +910,5 @@ def parallel(*layers):
   def apply_fn(params, inputs, **kwargs):
     return [f(p, x, **kwargs) for f, p, x in zip(apply_fns, params, inputs)]
 
-  return _layer(spec, init_fn, apply_fn)
+  import operator
+  return _layer(spec, init_fn, apply_fn, _fold_input_req(kernel_fns, operator.and_))

@@ -1,0 +1,19 @@
+# Round-2 evidence capture (one B200): launch list of the default bench command, ncu --set full of the cross-pair
+# stage kernels (fp32 packed stage 0 + stages 1, 2; fp64 stage 0) and of the tcgen05 input GEMM (tensor pipe),
+# bench lines.  Outputs land in gpurun_out/.
+mkdir -p gpurun_out
+B="python bench.py --steps 2 --warmup 1 --no-cpu --no-configs --strong-n 0"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r02.csv \
+    $B > gpurun_out/launches_run.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_stage -s 11 -c 3 -o gpurun_out/ncu_r02_f32 \
+    $B > gpurun_out/ncu_f32_run.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_stage -s 11 -c 1 -o gpurun_out/ncu_r02_f64 \
+    $B --dtype f64 > gpurun_out/ncu_f64_run.log 2>&1
+ncu --set full --clock-control none -k regex:k_gram_tf32x3_pipe -s 2 -c 1 -o gpurun_out/ncu_r02_gemm \
+    $B --workload fcn --block 8192 8192 > gpurun_out/ncu_gemm_run.log 2>&1
+for t in f32 f64 gemm; do
+  ncu -i gpurun_out/ncu_r02_$t.ncu-rep --page raw --csv > gpurun_out/ncu_r02_${t}_raw.csv 2>/dev/null
+  [ $t = f32 ] && ncu -i gpurun_out/ncu_r02_$t.ncu-rep --page source --csv 2>/dev/null | gzip > gpurun_out/ncu_r02_${t}_source.csv.gz
+  rm -f gpurun_out/ncu_r02_$t.ncu-rep   # gpurun_out/ is capped at 64 MiB
+done
+ls -la gpurun_out

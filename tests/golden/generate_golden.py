@@ -35,6 +35,13 @@ def main():
     x1d = jnp.asarray(x1, np.float64)
     x2d = None if x2 is None else jnp.asarray(x2, np.float64)
     res = kernel_fn(x1d, x2d, get)
+    req = getattr(kernel_fn, 'input_req', {})
+    d = req.get('diagonal_spatial')
+    # the negotiated `diagonal_spatial` requirement of the whole network (requirements.py:425-515): (input, output)
+    out[f'{name}/req_diagonal_spatial'] = np.asarray([-1, -1] if d is None or isinstance(d, bool)
+                                                      else [int(d.input), int(d.output)])
+    out[f'{name}/req_axes'] = np.asarray([-99 if req.get(k) is None else int(req.get(k))
+                                          for k in ('batch_axis', 'channel_axis')])
     if get is None:
       for f in ('nngp', 'ntk', 'cov1', 'cov2'):
         v = getattr(res, f)
