@@ -403,7 +403,7 @@ def run_ours(args):
   rank, world = B.rank, B.world
   depth, elems_net, elems_stage0 = WORKLOADS[args.workload]
   b1, b2 = args.block
-  if args.workload == 'fcn' and args.block == [96, 96]:
+  if args.workload == 'fcn' and args.block == [256, 256]:
     b1 = b2 = 1000                                                  # BASELINE configs[0]: 1000 x 1000
   flags = (lib.FLAG_NO_FUSION if args.no_fusion else 0) | (lib.FLAG_PER_LAYER if args.per_layer else 0)
   x64 = args.dtype == 'f64'
@@ -483,11 +483,12 @@ def run_ours(args):
     for wl, dt, blk, stated in (('fcn', 'f32', (1000, 1000), 'configs[0]: 1000 x 1000, 784-d (stated size)'),
                                 ('fcn', 'f64', (1000, 1000), 'configs[0] in float64 (stated size and dtype)'),
                                 ('myrtle5', 'f32', (1024, 1024), 'configs[1]: 1024 x 1024 block, 1 B200 (stated size)'),
-                                ('myrtle7', 'f32', (96, 96), 'configs[2]: one block of the 4096 x 4096 tiling'),
-                                ('myrtle10', 'f64', (96, 96), 'configs[3] FP64 path: one block of the 10000 x 10000 tiling'),
-                                ('wrn', 'f32', (96, 96), 'configs[4] Relu: one block of the 4096 x 4096 tiling'),
-                                ('wrn_erf', 'f32', (96, 96), 'configs[4] Erf: one block of the 4096 x 4096 tiling')):
-      steps_c = 1 if blk[0] >= 1024 and wl != 'fcn' else 3
+                                ('myrtle7', 'f32', (256, 256), 'configs[2]: one block of the 4096 x 4096 tiling'),
+                                ('myrtle10', 'f64', (256, 256), 'configs[3] FP64 path: one block of the 10000 x 10000 tiling'),
+                                ('wrn', 'f32', (256, 256), 'configs[4] Relu: one block of the 4096 x 4096 tiling'),
+                                ('wrn', 'f64', (256, 256), 'configs[4] Relu in float64'),
+                                ('wrn_erf', 'f32', (256, 256), 'configs[4] Erf: one block of the 4096 x 4096 tiling')):
+      steps_c = 1 if (blk[0] >= 1024 and wl != 'fcn') or dt == 'f64' else 3
       mc = measure_block(B, wl, dt, blk[0], blk[1], steps_c, 1 if steps_c == 1 else 2)
       configs.append({'workload': workload_label(wl), 'dtype': dt, 'block': list(blk), 'steps': steps_c,
                       'ms_per_step': mc['ms_dev_max'] / steps_c, 'entries_per_s': mc['value'],
@@ -635,7 +636,8 @@ def main():
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--workload', default='myrtle10', choices=sorted(WORKLOADS))
   ap.add_argument('--dtype', default='f32', choices=['f32', 'f64'])
-  ap.add_argument('--block', type=int, nargs=2, default=[96, 96])
+  ap.add_argument('--block', type=int, nargs=2, default=[256, 256],
+                  help='pairs per rank and step: [b1, b2] (65536 pairs = one tile of the size the full-Gram jobs run)')
   ap.add_argument('--e2e-batch', type=int, default=32)
   ap.add_argument('--ref-cols', type=int, default=12,
                   help='x2 columns per worker in a CPU step (about 10 s of CPU work per step on every core)')

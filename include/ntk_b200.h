@@ -62,7 +62,8 @@ enum {
   NTK_OP_IDENTITY = 9, /* `_src/stax/linear.py:107-119`    dst = src (FanOut is expressed by slot reuse) */
   NTK_OP_GELU = 10,    /* `_src/stax/elementwise.py:195-263`                                             */
   NTK_OP_SIN = 11,     /* `_src/stax/elementwise.py:266-341` a sin(b x + c): f = {a, b, c} (Cos: c + pi/2) */
-  NTK_OP_RBF = 12      /* `_src/stax/elementwise.py:344-400` f[0] = gamma                                */
+  NTK_OP_RBF = 12,     /* `_src/stax/elementwise.py:344-400` f[0] = gamma                                */
+  NTK_OP_LAYERNORM = 13 /* `_src/stax/linear.py:2476-2590` over the channel axis: f[0] = eps              */
 };
 
 /* padding modes (`_src/stax/linear.py:54-69`) */

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'libntk_b200.so')
 
 NTK_F32, NTK_F64 = 0, 1
 (OP_DENSE, OP_CONV, OP_ABRELU, OP_ERF, OP_AVGPOOL, OP_GAP, OP_FLATTEN, OP_FANINSUM, OP_IDENTITY, OP_GELU, OP_SIN,
- OP_RBF) = range(1, 13)
+ OP_RBF, OP_LAYERNORM) = range(1, 14)
 PAD = {'VALID': 0, 'SAME': 1, 'CIRCULAR': 2}
 NTK_NONE, NTK_ZERO, NTK_TENSOR = 0, 1, 2
 FLAG_NTK, FLAG_NO_FUSION, FLAG_WANT_COV, FLAG_PER_LAYER, FLAG_FULL_SQUARE, FLAG_UPPER_ONLY = 1, 2, 4, 8, 16, 32

@@ -279,6 +279,8 @@ int take_for_inplace(Env& env, TState& in, TState& out, bool steal, int t1, int 
 
 template <typename T>
 int op_act(Env& env, const ntk_op_t& op, TState& in, TState& out, bool steal, int t1, int t2) {
+  if (!in.gaussian && op.kind == NTK_OP_LAYERNORM)
+    return fail(NTK_EUNSUPPORTED, "LayerNorm only implemented for Gaussian inputs.");   // linear.py:2519-2521
   if (!in.gaussian)
     return fail(NTK_ENOTGAUSSIAN,
                 "The input to the activation function must be Gaussian, i.e. a random affine "
@@ -316,7 +318,7 @@ int op_act(Env& env, const ntk_op_t& op, TState& in, TState& out, bool steal, in
   env.unref(q1);
   env.unref(q2);
   if (stab) env.unref(stab);
-  out.gaussian = false;
+  out.gaussian = op.kind == NTK_OP_LAYERNORM;  // LayerNorm keeps a Gaussian input Gaussian; activations do not
   out.valid = true;
   return NTK_OK;
 }
@@ -414,6 +416,7 @@ int run_ops(Env& env, const ntk_program& prog, std::vector<TState>& slots, int f
       case NTK_OP_GELU:
       case NTK_OP_SIN:
       case NTK_OP_RBF:
+      case NTK_OP_LAYERNORM:
         NTK_TRY(op_act<T>(env, op, in, out, steal, t1, t2));
         break;
       case NTK_OP_DENSE:
@@ -623,6 +626,7 @@ int validate_program(ntk_program& p) {
       case NTK_OP_GELU:
       case NTK_OP_SIN:
       case NTK_OP_RBF:
+      case NTK_OP_LAYERNORM:
       case NTK_OP_GAP:
       case NTK_OP_FLATTEN:
       case NTK_OP_FANINSUM:
@@ -1061,6 +1065,9 @@ int ntk_program_output_shape(const ntk_program_t* prog, int32_t H, int32_t W,
       case NTK_OP_RBF:
         if (!in.g) return fail(NTK_ENOTGAUSSIAN, "The input to the activation function must be Gaussian");
         o.g = false;
+        break;
+      case NTK_OP_LAYERNORM:
+        if (!in.g) return fail(NTK_EUNSUPPORTED, "LayerNorm only implemented for Gaussian inputs.");
         break;
       case NTK_OP_GAP:
         if (in.H <= 0) return fail(NTK_EINVAL, "GlobalAvgPool needs spatial inputs");

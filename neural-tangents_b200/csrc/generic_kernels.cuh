@@ -350,6 +350,11 @@ __global__ void k_act(T* __restrict__ K, T* __restrict__ Tt, const T* __restrict
       erf_point<T>(k, prod, ko, dot);
       K[idx] = fma_t(aa, ko, cc);
       if (Tt) Tt[idx] = aa * (bb * Tt[idx] * dot);
+    } else if (ap.kind == NTK_OP_LAYERNORM) {
+      // linear.py:2566-2584: every kernel is divided by sqrt((eps + q1)(eps + q2)); a = eps
+      const T inv = (T)1 / sqrt_t((a + v1) * (a + v2));
+      K[idx] = k * inv;
+      if (Tt) Tt[idx] *= inv;
     } else {
       if (ap.kind == NTK_OP_GELU)
         gelu_point<T>(k, v1, v2, ko, dot);

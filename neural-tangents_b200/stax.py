@@ -26,7 +26,7 @@ import enum
 
 __all__ = ['serial', 'parallel', 'FanOut', 'FanInSum', 'Identity', 'Dense', 'Conv', 'Relu',
            'ABRelu', 'LeakyRelu', 'Abs', 'Erf', 'Sigmoid_like', 'Gelu', 'Sin', 'Cos', 'Rbf', 'AvgPool', 'SumPool',
-           'GlobalAvgPool', 'GlobalSumPool', 'Flatten', 'Padding', 'Bool', 'Diagonal']
+           'GlobalAvgPool', 'GlobalSumPool', 'Flatten', 'LayerNorm', 'Padding', 'Bool', 'Diagonal']
 
 
 class Padding(enum.Enum):
@@ -42,7 +42,7 @@ _OUT_OF_SCOPE = ('repeat', 'Elementwise', 'ElementwiseNumerical', 'Exp', 'ExpNor
                  'Gabor', 'Gaussian', 'Hermite', 'Monomial', 'Polynomial',
                  'RectifiedMonomial', 'Sign', 'Aggregate', 'ConvLocal',
                  'ConvTranspose', 'Index', 'DotGeneral', 'Dropout', 'GlobalSelfAttention',
-                 'ImageResize', 'LayerNorm', 'Slice', 'FanInConcat',
+                 'ImageResize', 'Slice', 'FanInConcat',
                  'FanInProd', 'AggregateImplementation', 'AttentionMechanism', 'PositionalEmbedding',
                  'MaskedArray', 'layer', 'requires', 'supports_masking', 'unmask_fn')
 
@@ -322,6 +322,8 @@ class _Lowered:
       return self._emit(_lib.OP_SIN, cur, (), (spec[1], spec[2], spec[3]), meta=m)
     if kind == 'rbf':
       return self._emit(_lib.OP_RBF, cur, (), (spec[1],), meta=m)
+    if kind == 'layernorm':
+      return self._emit(_lib.OP_LAYERNORM, cur, (), (spec[1],), meta=m)
     if kind in ('avgpool', 'sumpool'):
       (wh, ww), (sh, sw) = spec[1], spec[2]
       flags = (1 if spec[4] else 0) | (2 if kind == 'sumpool' else 0)   # bit 0 normalize_edges, bit 1 SumPool
@@ -370,7 +372,7 @@ def _out_shape(spec, shape):
     return [_out_shape(s, sh) for s, sh in zip(spec[1], shape)]
   if kind == 'faninsum':
     return shape[0] if isinstance(shape, list) else shape
-  if kind in ('identity', 'abrelu', 'erf', 'gelu', 'sin', 'rbf'):
+  if kind in ('identity', 'abrelu', 'erf', 'gelu', 'sin', 'rbf', 'layernorm'):
     return shape
   shape = tuple(shape)
   if kind == 'dense':
@@ -757,6 +759,24 @@ def Rbf(gamma: float = 1.0):
   init_fn = lambda rng, input_shape: (input_shape, ())
   apply_fn = lambda params, inputs, **kw: math.sqrt(2) * np.sin(math.sqrt(2 * gamma) * inputs + math.pi / 4)
   return _layer(spec, init_fn, apply_fn, dict(diagonal_spatial=Diagonal()))
+
+
+def LayerNorm(axis=-1, eps: float = 1e-12, batch_axis: int = 0, channel_axis: int = -1):
+  """`_src/stax/linear.py:2476-2590`, normalisation over the channel axis (the reference's default `axis=-1`;
+  normalising over spatial axes as well is outside the B200 hot path)."""
+  _only_supported(batch_axis=(batch_axis, (0,)), channel_axis=(channel_axis, (-1,)))
+  ax = tuple(axis) if isinstance(axis, (tuple, list)) else (axis,)
+  if ax != (-1,):
+    raise NotImplementedError('LayerNorm over axes other than the channel axis (-1) is outside the B200 hot path')
+  spec = ('layernorm', float(eps))
+  init_fn = lambda rng, input_shape: (input_shape, ())
+
+  def apply_fn(params, inputs, **kw):
+    mean = inputs.mean(axis=-1, keepdims=True)
+    var = inputs.var(axis=-1, keepdims=True)
+    return (inputs - mean) / np.sqrt(eps + var)
+
+  return _layer(spec, init_fn, apply_fn, dict(batch_axis=0, channel_axis=-1))
 
 
 def SumPool(window_shape, strides=None, padding: str = 'VALID', batch_axis: int = 0, channel_axis: int = -1):

@@ -33,7 +33,7 @@ shares no code with the product front end:
   ('erf', a, b, c)
   ('avgpool', (wh, ww), (sh, sw), 'SAME'|'VALID'|'CIRCULAR', normalize_edges)
   ('sumpool', (wh, ww), (sh, sw), padding)   ('gsp',)      # SumPool / GlobalSumPool
-  ('gelu',)  ('sin', a, b, c)  ('cos', a, b, c)  ('rbf', gamma)
+  ('gelu',)  ('sin', a, b, c)  ('cos', a, b, c)  ('rbf', gamma)  ('layernorm', eps)
   ('gap',) ('flatten',) ('identity',)
   ('fanout', n) ('parallel', [spec, ...]) ('faninsum',)
 """
@@ -370,6 +370,20 @@ def sin(st: OState, a: float, b: float, c: float) -> OState:
   return _elementwise_pairs(st, _outer_sum, f)
 
 
+def layernorm(st: OState, eps: float) -> OState:
+  """linear.py:2476-2590 with the default `axis=-1` (channel axis only): every kernel is divided by
+  sqrt((eps + q1)(eps + q2)) (`get_diagonal_outer_prods(eps + cov1, eps + cov2, ..., op.mul)`, :2566-2584)."""
+  if not st.is_gaussian:                                       # linear.py:2519-2521
+    raise NotImplementedError('LayerNorm only implemented for Gaussian inputs.')
+  q1 = eps + _diag(st.cov1)
+  q2 = q1 if st.cov2 is None else eps + _diag(st.cov2)
+  nngp = st.nngp / np.sqrt(_outer(q1, q2, True))
+  ntk = st.ntk if (st.ntk is None or st.ntk.ndim == 0) else st.ntk / np.sqrt(_outer(q1, q2, True))
+  cov1 = st.cov1 / np.sqrt(_outer(q1, q1, False))
+  cov2 = None if st.cov2 is None else st.cov2 / np.sqrt(_outer(q2, q2, False))
+  return st.replace(cov1=cov1, nngp=nngp, cov2=cov2, ntk=ntk)
+
+
 def rbf(st: OState, gamma: float) -> OState:
   """elementwise.py:344-400 (Rbf): nngp = exp(gamma (-(q1 + q2) + 2 k)), ntk *= 2 gamma nngp."""
   def f(k, sum_, t):                                           # elementwise.py:375-379
@@ -551,6 +565,8 @@ def apply_spec(spec, st):
     return sin(st, spec[1], spec[2], spec[3] + math.pi / 2)
   if kind == 'rbf':
     return rbf(st, spec[1])
+  if kind == 'layernorm':
+    return layernorm(st, spec[1])
   if kind == 'flatten':
     return flatten(st)
   raise ValueError(f'unknown spec {kind}')

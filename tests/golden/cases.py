@@ -127,6 +127,12 @@ CASES = {
                 (4, 10), (3, 10), ('nngp', 'ntk')),
     'rbf_conv_pool': (('serial', [conv(W=1., b=0.1), ('rbf', 0.5), pool(), conv(), RELU, ('gap',), ('dense', 1., 0.)]),
                       (2, 6, 6, 2), (2, 6, 6, 2), ('nngp', 'ntk')),
+    # LayerNorm over the channel axis (linear.py:2476)
+    'layernorm_conv': (('serial', [conv(W=1.3, b=0.2), ('layernorm', 1e-12), RELU, conv(W=1., b=0.1), ('layernorm', 0.1),
+                                   ('gelu',), ('gap',), ('dense', 1., 0.1)]),
+                       (2, 5, 5, 2), (3, 5, 5, 2), ('nngp', 'ntk')),
+    'layernorm_fcn_sym': (('serial', [('dense', 1.5, 0.3), ('layernorm', 1e-6), RELU, ('dense', 1., 0.)]),
+                          (4, 12), None, ('nngp', 'ntk')),
 }
 
 
@@ -168,6 +174,8 @@ def build(spec, stax):
     return stax.Cos(spec[1], spec[2], spec[3])
   if kind == 'rbf':
     return stax.Rbf(spec[1])
+  if kind == 'layernorm':
+    return stax.LayerNorm(eps=spec[1])
   if kind == 'flatten':
     return stax.Flatten()
   raise ValueError(kind)
