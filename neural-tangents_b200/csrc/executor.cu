@@ -20,6 +20,8 @@ NTK_FUSED_ERF_INSTANCES(extern, float)
 NTK_FUSED_ERF_INSTANCES(extern, double)
 NTK_FUSED_EMB_INSTANCES(extern, float)
 NTK_FUSED_EMB_INSTANCES(extern, double)
+NTK_FUSED_GEN_INSTANCES(extern, float)
+NTK_FUSED_GEN_INSTANCES(extern, double)
 NTK_RES_ERF_INSTANCES(extern, float)
 NTK_RES_ERF_INSTANCES(extern, double)
 NTK_RES_INSTANCES(extern, float)
@@ -1142,6 +1144,8 @@ int ntk_context_create(int32_t device, size_t workspace_bytes, ntk_context_t** o
   NTK_TRY((fused_configure_device<double, false>()));
   NTK_TRY((fused_configure_device<float, true>()));
   NTK_TRY((fused_configure_device<double, true>()));
+  NTK_TRY((fused_configure_device<float, 2>()));
+  NTK_TRY((fused_configure_device<double, 2>()));
   NTK_TRY(stage_packed_configure());
   NTK_TRY(stage_packed_erf_configure());
   *out = c.release();

@@ -63,7 +63,10 @@ struct FLayer {
   T eT;       // alpha_next * a^2 b^2 * 4/pi
   T eC;       // alpha_next * c^2
 };
-enum { ACT_ABRELU = 0, ACT_ERF = 1 };
+// ACT_GELU / ACT_SIN / ACT_RBF (elementwise.py:195-400) reuse the Erf fields as generic parameters:
+//   Gelu: eA = alpha_next;   Sin(a, b, c): e_in = b^2, eA = alpha_next a^2 / 2, eT = cos(2c);   Rbf: e_in = gamma, eA = alpha_next
+// and their q-maps hold the plain diagonal variance q.
+enum { ACT_ABRELU = 0, ACT_ERF = 1, ACT_GELU = 2, ACT_SIN = 3, ACT_RBF = 4 };
 
 template <typename T>
 struct StageArgs {
@@ -309,6 +312,43 @@ __device__ __forceinline__ void erf_act_point(T K, T Tn, T D1, T rD1, T D2, T rD
   To = mul_rn(mul_rn(eT, rs), Tn);
 }
 
+__device__ __forceinline__ float exp_g(float x) { return __expf(x); }
+__device__ __forceinline__ double exp_g(double x) { return exp(x); }
+__device__ __forceinline__ float atan2_g(float y, float x) { return atan2f(y, x); }
+__device__ __forceinline__ double atan2_g(double y, double x) { return atan2(y, x); }
+__device__ __forceinline__ float sqrt_g(float x) { return sqrtf(x); }
+__device__ __forceinline__ double sqrt_g(double x) { return sqrt(x); }
+
+// Gelu / Sin / Rbf on one element (elementwise.py:225-240, 294-300, 375-379), outputs pre-scaled by the next conv's
+// alpha (FLayer.eA).  The q-map kernel calls it on (K = q, q, q) for the diagonal, so duplicate pairs agree.
+template <typename T>
+__device__ __forceinline__ void gen_act_point(int kind, T K, T Tn, T q1, T q2, T e_in, T eA, T eT, T& Ko, T& To) {
+  if (kind == ACT_GELU) {
+    const T prod = q1 * q2, prod_plus_1 = (q1 + (T)1) * (q2 + (T)1);
+    const T delta_squared = prod_plus_1 - K * K;
+    const T delta = sqrt_g(delta_squared > (T)0 ? delta_squared : (T)0);
+    const T angles = atan2_g(K, delta);
+    const T inv_2pi = (T)0.15915494309189533577;
+    T nk = (K * K + prod * delta_squared) / (prod_plus_1 * delta);
+    nk = (nk + K * angles) * inv_2pi + (T)0.25 * K;
+    T first = (T)1 / delta_squared + ((T)1 - prod) / prod_plus_1 + (T)1;
+    first *= K / delta * inv_2pi;
+    const T dot = first + (T)0.25 + angles * inv_2pi;
+    Ko = eA * nk;
+    To = eA * dot * Tn;
+  } else if (kind == ACT_SIN) {
+    const T sum_ = q1 + q2;
+    const T s1 = exp_g(e_in * ((T)-0.5 * sum_ + K));
+    const T s2 = exp_g(e_in * ((T)-0.5 * sum_ - K)) * eT;
+    Ko = eA * (s1 - s2);
+    To = eA * e_in * (s1 + s2) * Tn;
+  } else {  // ACT_RBF
+    const T k = exp_g(e_in * ((T)2 * K - (q1 + q2)));
+    Ko = eA * k;
+    To = eA * (T)2 * e_in * k * Tn;
+  }
+}
+
 // Vertical link masks per row r = ch*S + h of a pair (row-major march order):
 //   .x = vU: rows r-1 and r are linked (h > 0 and h' = (h+ch) mod S did not wrap),
 //   .y = vD: rows r and r+1 are linked.
@@ -388,6 +428,12 @@ __global__ void k_qmaps(const T* __restrict__ src, int src_mode, int C, T in_sca
         T ko, to;
         erf_act_point<T>(q, (T)0, o.x, o.y, o.x, o.y, lp[l].e_in, lp[l].eA, lp[l].eT, lp[l].eC, ko, to);
         P[e] = ko;
+      } else if (lp[l].kind >= ACT_GELU) {
+        o.x = q;
+        o.y = (T)0;
+        T ko, to;
+        gen_act_point<T>(lp[l].kind, q, (T)0, q, q, lp[l].e_in, lp[l].eA, lp[l].eT, ko, to);
+        P[e] = ko;
       } else {
         o.x = q;
         o.y = q > (T)0 ? rsqrt_t(q) : (T)0;
@@ -421,11 +467,11 @@ struct StageGeom {
 // row sample x1[i] and its q-maps are staged once and shared (more resident warps per SM).
 // RC ("runtime columns"): march only the ch columns [col_start, col_start + col_count) -- used by
 // the self-pair pipeline; the cross-pair kernels keep compile-time trip counts.
-// ERF: the stage may contain Erf layers (runtime branch per layer); ERF = false instantiations carry
-// no Erf code, so the ABRelu hot path is unchanged by it.
+// ERF: 0 = pure ABRelu (no other code compiled in, the hot path); 1 = the stage may contain Erf layers (runtime branch
+// per layer); 2 = any of ABRelu / Erf / Gelu / Sin / Rbf (the general family, fused_*_gen.cu).
 // EMB: the image is RH x RW <= S x S (StageArgs): staging, link masks and the GAP epilogue use the real size and
 // the vertical masks are computed instead of read from the constant tables (which hold RH == S).
-template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN, int SH, bool RC, bool ERF,
+template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN, int SH, bool RC, int ERF,
           bool EMB = false>
 __global__ void __launch_bounds__(StageGeom<S, WPT, SH>::NT)
 k_stage(const StageArgs<T> a) {
@@ -740,7 +786,9 @@ k_stage(const StageArgs<T> a) {
           }
           const V2 qa = q1r[i];
           const V2 qb = lds_v2<T>(q2row + off2[i]);
-          if (ERF && a.lp[l].kind == ACT_ERF)
+          if (ERF == 2 && a.lp[l].kind >= ACT_GELU)
+            gen_act_point<T>(a.lp[l].kind, ck, ct, qa.x, qb.x, a.lp[l].e_in, a.lp[l].eA, a.lp[l].eT, BK[l][i], BT[l][i]);
+          else if (ERF && a.lp[l].kind == ACT_ERF)
             erf_act_point<T>(ck, ct, qa.x, qa.y, qb.x, qb.y, a.lp[l].e_in, a.lp[l].eA, a.lp[l].eT, a.lp[l].eC,
                              BK[l][i], BT[l][i]);
           else
@@ -946,7 +994,10 @@ inline FusedPlan plan_fused(const std::vector<ntk_op_t>& ops, int n_slots, int o
     return o.kind == NTK_OP_CONV && o.i[0] == 3 && o.i[1] == 3 && o.i[2] == 1 && o.i[3] == 1 &&
            o.i[4] == NTK_PAD_SAME;
   };
-  auto is_act = [](const ntk_op_t& o) { return (o.kind == NTK_OP_ABRELU && o.i[0] == 0) || o.kind == NTK_OP_ERF; };
+  auto is_act = [](const ntk_op_t& o) {
+    return (o.kind == NTK_OP_ABRELU && o.i[0] == 0) || o.kind == NTK_OP_ERF || o.kind == NTK_OP_GELU ||
+           o.kind == NTK_OP_SIN || o.kind == NTK_OP_RBF;
+  };
   auto is_pool = [](const ntk_op_t& o) {
     return o.kind == NTK_OP_AVGPOOL && o.i[0] == 2 && o.i[1] == 2 && o.i[2] == 2 && o.i[3] == 2 &&
            o.i[4] != NTK_PAD_CIRCULAR && !(o.i[4] == NTK_PAD_SAME && pool_normalize_edges(o) && !pool_is_sum(o));
@@ -979,8 +1030,9 @@ inline FusedPlan plan_fused(const std::vector<ntk_op_t>& ops, int n_slots, int o
         st.b2[l] = c.i[5] ? c.f[1] : 0.0;
         st.a[l] = act.f[0];
         st.b[l] = act.f[1];
-        st.c[l] = act.kind == NTK_OP_ERF ? act.f[2] : 0.0;
-        st.kind[l] = act.kind == NTK_OP_ERF ? ACT_ERF : ACT_ABRELU;
+        st.c[l] = (act.kind == NTK_OP_ERF || act.kind == NTK_OP_SIN) ? act.f[2] : 0.0;
+        st.kind[l] = act.kind == NTK_OP_ERF ? ACT_ERF : act.kind == NTK_OP_GELU ? ACT_GELU
+                     : act.kind == NTK_OP_SIN ? ACT_SIN : act.kind == NTK_OP_RBF ? ACT_RBF : ACT_ABRELU;
       }
       st.epi = EPI_STORE;
       plan.stages.push_back(st);
@@ -1075,7 +1127,7 @@ size_t stage_smem_bytes() {
   return (size_t)G::GROUPS * (xs1 + xs2 + 2 * qm + stg) * sizeof(T);
 }
 
-template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN, bool ERF, int SH = 1, bool RC = false,
+template <typename T, int S, int WPT, int L, int IN, int EPI, bool NTK, int CIN, int ERF, int SH = 1, bool RC = false,
           bool EMB = false>
 int launch_stage_impl(cudaStream_t stream, int64_t* launches, const StageArgs<T>& a) {
   using G = StageGeom<S, WPT, SH>;
@@ -1090,7 +1142,7 @@ int launch_stage_impl(cudaStream_t stream, int64_t* launches, const StageArgs<T>
   return NTK_OK;
 }
 
-template <typename T, int S, int L, int IN, bool NTK, int CIN, bool ERF, bool EMB = false>
+template <typename T, int S, int L, int IN, bool NTK, int CIN, int ERF, bool EMB = false>
 int launch_stage_epi(cudaStream_t stream, int64_t* launches, int epi, const StageArgs<T>& a) {
   constexpr int WPT = StageCfg<T, S>::WPT;
   // (An SH = 3 variant -- three column samples sharing one row sample per CTA, 12 instead of 8 resident
@@ -1116,7 +1168,7 @@ int launch_stage_epi(cudaStream_t stream, int64_t* launches, int epi, const Stag
   }
 }
 
-template <typename T, int S, int IN, bool NTK, int CIN, bool ERF, bool EMB = false>
+template <typename T, int S, int IN, bool NTK, int CIN, int ERF, bool EMB = false>
 int launch_stage_L(cudaStream_t stream, int64_t* launches, int L, int epi, const StageArgs<T>& a) {
   switch (L) {
     case 1:
@@ -1172,7 +1224,7 @@ inline int launch_stage_packed_any(cudaStream_t stream, int64_t* launches, int S
 
 // The unpacked stage kernels: ERF = false (pure ABRelu) and ERF = true (Erf-capable) families are
 // instantiated in separate translation units (fused_*.cu / fused_*_erf.cu).
-template <typename T, bool NTK, bool ERF>
+template <typename T, bool NTK, int ERF>
 int launch_stage_k(cudaStream_t stream, int64_t* launches, int S, int L, int from_x, int C, int epi,
                    const StageArgs<T>& a) {
   if (from_x) {
@@ -1197,17 +1249,21 @@ bool stage_is_packed(int S, int C, int n_erf, int L) {
 template <typename T, bool NTK>
 int launch_stage(cudaStream_t stream, int64_t* launches, int S, int L, int from_x, int C, int epi,
                  const StageArgs<T>& a, bool emb = false) {
-  int n_erf = 0;
-  for (int l = 0; l < L; ++l) n_erf += a.lp[l].kind == ACT_ERF;
+  int n_erf = 0, n_gen = 0;
+  for (int l = 0; l < L; ++l) {
+    n_erf += a.lp[l].kind == ACT_ERF;
+    n_gen += a.lp[l].kind >= ACT_GELU;
+  }
   const bool any_erf = n_erf > 0;
   if (emb) {
-    if (any_erf) return fail(NTK_EUNSUPPORTED, "the embedded-size stage kernels are ABRelu only");
+    if (any_erf || n_gen) return fail(NTK_EUNSUPPORTED, "the embedded-size stage kernels are ABRelu only");
     return launch_stage_emb<T, NTK>(stream, launches, S, L, from_x, C, epi, a);
   }
+  if (n_gen) return launch_stage_k<T, NTK, 2>(stream, launches, S, L, from_x, C, epi, a);
   if (stage_is_packed<T>(S, from_x ? C : 3, n_erf, L))
     return launch_stage_packed_any(stream, launches, S, L, from_x, epi, NTK, any_erf, a);
-  if (any_erf) return launch_stage_k<T, NTK, true>(stream, launches, S, L, from_x, C, epi, a);
-  return launch_stage_k<T, NTK, false>(stream, launches, S, L, from_x, C, epi, a);
+  if (any_erf) return launch_stage_k<T, NTK, 1>(stream, launches, S, L, from_x, C, epi, a);
+  return launch_stage_k<T, NTK, 0>(stream, launches, S, L, from_x, C, epi, a);
 }
 
 template <typename T>
@@ -1229,7 +1285,7 @@ int launch_qmaps(cudaStream_t stream, int64_t* launches, int S, const T* src, in
 // Uploads the vertical link masks to the current device (once per context).  Templated on the
 // dtype and kernel family so that each translation unit (fused_f32.cu, fused_f32_erf.cu, ...)
 // uploads its own copy of the `static __constant__` tables.
-template <typename T, bool ERF>
+template <typename T, int ERF>
 int fused_configure_device() {
   for (int S : {32, 16, 8}) {
     std::vector<float2> m((size_t)S * S);
@@ -1278,6 +1334,16 @@ void stage_constants(const FusedPlan& plan, size_t s, FLayer<T>* lp, double* nex
       lp[l].eA = (T)(an * ea * ea * 2.0 / pi);
       lp[l].eT = (T)(an * ea * ea * eb * eb * 4.0 / pi);
       lp[l].eC = (T)(an * ec * ec);
+      if (st.kind[l] == ACT_GELU) {
+        lp[l].eA = (T)an;
+      } else if (st.kind[l] == ACT_SIN) {  // a sin(b x + c)
+        lp[l].e_in = (T)(eb * eb);
+        lp[l].eA = (T)(an * ea * ea / 2.0);
+        lp[l].eT = (T)cos(2.0 * ec);
+      } else if (st.kind[l] == ACT_RBF) {  // gamma travels in `a`
+        lp[l].e_in = (T)ea;
+        lp[l].eA = (T)an;
+      }
     }
     if (l + 1 == st.L) *next_alpha_out = alpha_next;
   }
@@ -1497,9 +1563,12 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
           if (epi == EPI_POOL) {
             // the packed kernels zero their own (pre-accumulation) output while other CTAs compute
             // -- DRAM is idle in this kernel -- instead of a 4.8 GB memset in front of every launch
-            int n_erf = 0;
-            for (int l = 0; l < plan.stages[s].L; ++l) n_erf += plan.stages[s].kind[l] == ACT_ERF;
-            a.zero_out = (!emb && stage_is_packed<T>(S, s == 0 ? C : 3, n_erf, plan.stages[s].L)) ? 1 : 0;
+            int n_erf = 0, n_gen = 0;
+            for (int l = 0; l < plan.stages[s].L; ++l) {
+              n_erf += plan.stages[s].kind[l] == ACT_ERF;
+              n_gen += plan.stages[s].kind[l] >= ACT_GELU;
+            }
+            a.zero_out = (!emb && !n_gen && stage_is_packed<T>(S, s == 0 ? C : 3, n_erf, plan.stages[s].L)) ? 1 : 0;
             if (!a.zero_out)
               NTK_CUDA(cudaMemsetAsync(nxt, 0, (size_t)P * out_per * sizeof(T) * (want_ntk ? 2 : 1), stream));
           }

@@ -14,6 +14,14 @@
                                                  const StageArgs<T>&);                                     \
   KW template int fused_configure_device<T, true>();
 
+// launch_stage_k<T, NTK, ERF = 2> (general family: ABRelu / Erf / Gelu / Sin / Rbf) lives in fused_*_gen.cu
+#define NTK_FUSED_GEN_INSTANCES(KW, T)                                                                     \
+  KW template int launch_stage_k<T, true, 2>(cudaStream_t, int64_t*, int, int, int, int, int,              \
+                                             const StageArgs<T>&);                                         \
+  KW template int launch_stage_k<T, false, 2>(cudaStream_t, int64_t*, int, int, int, int, int,             \
+                                              const StageArgs<T>&);                                        \
+  KW template int fused_configure_device<T, 2>();
+
 // launch_stage_emb<T, NTK> (embedded-size scalar stage kernels, C in {1, 3}) lives in fused_*_emb.cu
 #define NTK_FUSED_EMB_INSTANCES(KW, T)                                                                     \
   KW template int launch_stage_emb<T, true>(cudaStream_t, int64_t*, int, int, int, int, int,               \

@@ -240,5 +240,8 @@ def test_fused_path_covers_grey_nonsquare_and_mnist_sizes(lib):
   # SumPool / GlobalSumPool ride the same kernels (epilogue scales)
   sp = ('serial', [cases.conv(), cases.RELU, ('sumpool', (2, 2), (2, 2), 'VALID'), cases.conv(), cases.RELU, ('gsp',)])
   assert path(sp, 32, 32, 3) == 'fused' and path(sp, 28, 28, 1) == 'fused'
-  # Gelu / Sin / Rbf run on the per-op path
-  assert path(cases.CASES['gelu_conv'][0], 32, 32, 3) == 'generic'
+  # Gelu / Sin / Rbf stages: the general family of the fused stage kernels at the native sizes, per-op elsewhere
+  assert path(cases.CASES['gelu_conv'][0], 32, 32, 3) == 'fused'
+  assert path(cases.CASES['rbf_conv_pool'][0], 16, 16, 3) == 'fused'
+  assert path(cases.CASES['gelu_conv'][0], 28, 28, 1) == 'generic'
+  assert path(cases.CASES['layernorm_conv'][0], 32, 32, 3) == 'generic'

@@ -394,3 +394,36 @@ def test_sum_pools_on_the_fused_kernels(nt):
       np.testing.assert_allclose(out.nngp, ref[0], rtol=RTOL[x64])
       np.testing.assert_allclose(out.ntk, ref[1], rtol=RTOL[x64])
   nt.config.update('enable_x64', False)
+
+
+@pytest.mark.parametrize('size', [32, 16])
+def test_gelu_sin_rbf_in_the_fused_stage_kernels(nt, size):
+  """Gelu / Sin / Cos / Rbf closed forms (elementwise.py:195-400) inside the fused stage kernels
+  (general family), alone and mixed with Relu / Erf in one stage, against the oracle and the per-op path."""
+  from oracle import ntk_oracle as O
+  specs = {
+      'gelu': ('serial', [cases.conv(W=1.2, b=0.1), ('gelu',), cases.conv(W=1.1, b=0.), ('gelu',), cases.pool(),
+                          cases.conv(), ('gelu',), ('gap',), ('dense', 1., 0.1)]),
+      'sin_cos_rbf': ('serial', [cases.conv(W=1.1, b=0.2), ('sin', 1.2, 0.7, 0.3), cases.conv(W=1., b=0.1),
+                                 ('cos', 0.9, 1.1, 0.2), cases.pool(), cases.conv(W=1., b=0.1), ('rbf', 0.5),
+                                 ('gap',), ('dense', 1., 0.)]),
+      'mixed': ('serial', [cases.conv(W=1.3, b=0.1), cases.RELU, cases.conv(), ('gelu',), cases.conv(), ('erf', 1., 1., 0.),
+                           cases.pool(), cases.conv(), ('rbf', 0.8), cases.conv(), cases.RELU, ('gap',), ('dense', 1.1, 0.)]),
+  }
+  for name, spec in specs.items():
+    _, _, kernel_fn = cases.build(spec, nt.stax)
+    low = nt.stax._lowered(nt.stax._strip(kernel_fn._spec), False, False, True)
+    assert low.program.path(size, size, 3) == 'fused', name
+    x1 = np.random.default_rng(51).standard_normal((3, size, size, 3)).astype(np.float32)
+    x2 = np.random.default_rng(52).standard_normal((2, size, size, 3)).astype(np.float32)
+    ref = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'))
+    sref = O.kernel_fn(spec, x1, None, ('nngp', 'ntk'))
+    for x64 in (False, True):
+      nt.config.update('enable_x64', x64)
+      out = kernel_fn(x1, x2, ('nngp', 'ntk'))
+      np.testing.assert_allclose(out.nngp, ref[0], rtol=RTOL[x64], err_msg=name)
+      np.testing.assert_allclose(out.ntk, ref[1], rtol=RTOL[x64], err_msg=name)
+      sym = kernel_fn(x1, None, ('nngp', 'ntk'))
+      _check_sym(sym.nngp, sref[0], x64)
+      _check_sym(sym.ntk, sref[1], x64)
+  nt.config.update('enable_x64', False)
