@@ -82,6 +82,11 @@ int launch_p_epi(cudaStream_t stream, int64_t* launches, int epi, const StageArg
         if (variant() != 7 && no_bias)
           return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false, 1, 2, true, 2>(stream, launches, a);
       }
+      // the same bias-free instantiation for the two-layer first stage of Myrtle-5 / Myrtle-7 (BASELINE configs[1], [2])
+      if constexpr (!NTK_PACKED_ERF && L == 2 && IN == IN_FROM_X && NTK && S == 32) {
+        if (variant() != 7 && a.lp[0].bias == 0.f && a.lp[1].bias == 0.f)
+          return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false, 1, 2, true, 2>(stream, launches, a);
+      }
       return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false>(stream, launches, a);
     default:
       return launch_p_impl<S, L, IN, EPI_GAP, NTK, CIN, false>(stream, launches, a);
