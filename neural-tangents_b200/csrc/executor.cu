@@ -704,6 +704,9 @@ int fcn_gram(ntk_context* ctx, Env& env, const FcnProg& fp, const T* x1, int n1,
   // fp32: split x into TF32 hi / lo parts once, then the pipelined tcgen05 GEMM (gemm_kernels.cuh)
   static const bool no_tc = getenv("NTK_B200_NO_TC") != nullptr;
   static const bool no_pipe = getenv("NTK_B200_NO_GEMM_PIPE") != nullptr;
+  // TMA-fed warp-specialised GEMM (gemm_tma.cu) is the default: 8192 x 8192 x 784 Gram + chain 3.39 -> 1.88 ms, results
+  // bit-identical to the cp.async pipeline (profiles/check_gemm_tma.py); NTK_B200_GEMM_CPASYNC=1 switches back for A/B runs.
+  static const bool use_tma = getenv("NTK_B200_GEMM_CPASYNC") == nullptr;
   float *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
   const int d_pad = gram_pad_k(C);
   bool pipe = false;
@@ -737,8 +740,12 @@ int fcn_gram(ntk_context* ctx, Env& env, const FcnProg& fp, const T* x1, int n1,
     if constexpr (std::is_same<T, float>::value) {
       if (pipe) {
         env.launches++;
-        NTK_TRY(launch_gram_tc_pipe(env.stream, a_hi + (size_t)r0 * d_pad, a_lo + (size_t)r0 * d_pad, a1, b_hi, b_lo,
-                                    n2, C, K0, (long long)n2));
+        if (use_tma)
+          NTK_TRY(launch_gram_tc_tma(env.stream, a_hi + (size_t)r0 * d_pad, a_lo + (size_t)r0 * d_pad, a1, b_hi, b_lo,
+                                     n2, C, K0, (long long)n2));
+        else
+          NTK_TRY(launch_gram_tc_pipe(env.stream, a_hi + (size_t)r0 * d_pad, a_lo + (size_t)r0 * d_pad, a1, b_hi, b_lo,
+                                      n2, C, K0, (long long)n2));
       }
     }
     if (!pipe)

@@ -377,6 +377,10 @@ k_gram_tf32x3_pipe(const float* __restrict__ a_hi, const float* __restrict__ a_l
 
 inline int gram_pad_k(int d) { return (d + kGemmBK - 1) / kGemmBK * kGemmBK; }
 
+// TMA-fed, warp-specialised variant of k_gram_tf32x3_pipe (gemm_tma.cu: its own translation unit)
+int launch_gram_tc_tma(cudaStream_t stream, const float* a_hi, const float* a_lo, int n1, const float* b_hi,
+                       const float* b_lo, int n2, int d, float* out, long long ld_out);
+
 // hi/lo: [n, gram_pad_k(d)] each
 inline int launch_split_tf32(cudaStream_t stream, const float* x, long long n, int d, float* hi, float* lo) {
   const int d_pad = gram_pad_k(d);
