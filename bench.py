@@ -217,6 +217,24 @@ def make_cpu_pool(cores):
   return mp.get_context('spawn').Pool(cores)
 
 
+def make_config(args, world, b1, b2):
+  """`config` of the JSON line: the workload both arms are quoted on (the reference arm runs a bounded sample of it,
+  described in its `cpu_baseline.sample`)."""
+  return {'workload': workload_label(args.workload), 'block_per_gpu': [b1, b2],
+          'parallelism': (f'x1-row partition over {world} rank(s): x1 / x2 broadcast from rank 0 (NCCL), contiguous row '
+                          'slabs, slabs all-gathered (no reduction collective)') if world > 1 else 'one rank',
+          'l2': 'flushed (256 MiB memset) between timed steps',
+          'fusion': ('per-layer stencil kernels' if args.per_layer else not args.no_fusion),
+          'symmetric_x2_none': bool(args.symmetric)}
+
+
+def block_of(args):
+  b1, b2 = args.block
+  if args.workload == 'fcn' and args.block == [256, 256]:
+    b1 = b2 = 1000                                                  # BASELINE configs[0]: 1000 x 1000
+  return b1, b2
+
+
 def run_reference(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
@@ -241,8 +259,7 @@ def run_reference(args):
       'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
       'ms_per_step': 1e3 * t_tot / args.steps, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-      'config': {'workload': workload_label(args.workload),
-                 'block': [cores, args.ref_cols]},
+      'config': make_config(args, args.gpus, *block_of(args)),
       'cpu_baseline': {'value': value, 'unit': 'entries/s', 'cores': cores, 'kind': 'port',
                        'sample': sample},
       'e2e': {'value': value, 'unit': 'entries/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -402,9 +419,7 @@ def run_ours(args):
   nt, lib = B.nt, B.lib
   rank, world = B.rank, B.world
   depth, elems_net, elems_stage0 = WORKLOADS[args.workload]
-  b1, b2 = args.block
-  if args.workload == 'fcn' and args.block == [256, 256]:
-    b1 = b2 = 1000                                                  # BASELINE configs[0]: 1000 x 1000
+  b1, b2 = block_of(args)
   flags = (lib.FLAG_NO_FUSION if args.no_fusion else 0) | (lib.FLAG_PER_LAYER if args.per_layer else 0)
   x64 = args.dtype == 'f64'
   sz = 8 if x64 else 4
@@ -574,13 +589,9 @@ def run_ours(args):
       'vs_baseline': (value / world / PUBLISHED[(args.workload, args.dtype)]
                       if (args.workload, args.dtype) in PUBLISHED else None),
       'dtype': args.dtype, 'data': 'synthetic',
-      'config': {'workload': workload_label(args.workload), 'block_per_gpu': [b1, b2],
-                 'parallelism': (f'distributed.gram_resident over {world} rank(s): NCCL broadcast of x1 / x2 from rank 0, '
-                                 'contiguous row slabs, NCCL all-gather (no reduction collective)') if world > 1
-                 else 'one rank: ntk_gram_device on the context stream',
-                 'l2': 'flushed (256 MiB memset) between timed steps',
-                 'fusion': ('per-layer stencil kernels' if args.per_layer else not args.no_fusion),
-                 'symmetric_x2_none': bool(args.symmetric), 'host_framework': 'NumPy + ctypes (no torch)'},
+      'config': make_config(args, world, b1, b2),
+      'host_framework': 'NumPy + ctypes over libntk_b200.so (no torch, no jax); multi-GPU = distributed.gram_resident',
+      'impl': 'ours',
       'e2e': {'value': e2e_value, 'unit': 'entries/s',
               'h2d_bytes_per_step': int(x1_h.nbytes + x2_h.nbytes),
               'd2h_bytes_per_step': int(2 * entries_per_step * sz) * (world if world > 1 else 1),
