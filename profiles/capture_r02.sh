@@ -9,7 +9,7 @@ ncu --set full --clock-control none --import-source on -k regex:k_stage -s 11 -c
     $B > gpurun_out/ncu_f32_run.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_stage -s 11 -c 1 -o gpurun_out/ncu_r02_f64 \
     $B --dtype f64 > gpurun_out/ncu_f64_run.log 2>&1
-ncu --set full --clock-control none -k regex:k_gram_tf32x3_pipe -s 2 -c 1 -o gpurun_out/ncu_r02_gemm \
+ncu --set full --clock-control none -k regex:k_gram_tf32x3_tma -s 2 -c 1 -o gpurun_out/ncu_r02_gemm \
     $B --workload fcn --block 8192 8192 > gpurun_out/ncu_gemm_run.log 2>&1
 for t in f32 f64 gemm; do
   ncu -i gpurun_out/ncu_r02_$t.ncu-rep --page raw --csv > gpurun_out/ncu_r02_${t}_raw.csv 2>/dev/null
