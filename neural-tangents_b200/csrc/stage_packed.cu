@@ -28,11 +28,11 @@ inline int variant() {
 }
 
 template <int S, int L, int IN, int EPI, bool NTK, int CIN, bool RC, int LAG = 1, int MINB = 2, bool Q2P = true,
-          int VAR = 0>
+          int VAR = 0, int WPT = 8>
 int launch_p_impl(cudaStream_t stream, int64_t* launches, const StageArgs<float>& a) {
-  using G = PGeom<S>;
-  auto kern = k_stage_p<S, L, IN, EPI, NTK, CIN, RC, LAG, MINB, Q2P, NTK_PACKED_ERF != 0, VAR>;
-  const size_t smem = stage_p_smem_bytes<S, L, IN, EPI, NTK, CIN, Q2P>();
+  using G = PGeom<S, WPT>;
+  auto kern = k_stage_p<S, L, IN, EPI, NTK, CIN, RC, LAG, MINB, Q2P, NTK_PACKED_ERF != 0, VAR, WPT>;
+  const size_t smem = stage_p_smem_bytes<S, L, IN, EPI, NTK, CIN, Q2P, WPT>();
   NTK_TRY(ensure_dynamic_smem((const void*)kern, smem));
   const long long blocks = (a.P + G::GROUPS - 1) / G::GROUPS;
   (*launches)++;
@@ -76,6 +76,10 @@ int launch_p_epi(cudaStream_t stream, int64_t* launches, int epi, const StageArg
       // loss of the exact duplicate-pair diagonal (the self-pair runs keep the degree-8 kernel): not the default.
       if constexpr (!NTK_PACKED_ERF && L == 3 && IN == IN_FROM_X && NTK && S == 32) {
         const bool no_bias = a.lp[0].bias == 0.f && a.lp[1].bias == 0.f && a.lp[2].bias == 0.f;
+        if (variant() == 20 && no_bias)  // 4 w per thread: 256 threads per pair, 4 warps per scheduler
+          return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false, 1, 2, true, 2, 4>(stream, launches, a);
+        if (variant() == 21 && no_bias)
+          return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false, 2, 2, true, 2, 4>(stream, launches, a);
         if (variant() == 4) return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false, 1, 2, true, 1>(stream, launches, a);
         if (variant() == 6 && no_bias)
           return launch_p_impl<S, L, IN, EPI_POOL, NTK, CIN, false, 1, 2, true, 3>(stream, launches, a);

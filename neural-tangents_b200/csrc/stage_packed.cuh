@@ -162,9 +162,9 @@ __device__ __forceinline__ void act_pair_erf(float2 K, float2 U, float2 q1, floa
   if (NTK) Uo = __ffma2_rn(__fmul2_rn(f2s(eT), rs), U, Ko);
 }
 
-template <int S>
+template <int S, int WPT_ = 8>
 struct PGeom {
-  static constexpr int WPT = 8;
+  static constexpr int WPT = WPT_;
   static constexpr int TPP = S * S / WPT;          // threads per pair
   static constexpr int NT = TPP < 128 ? 128 : TPP; // threads per CTA
   static constexpr int GROUPS = NT / TPP;
@@ -174,15 +174,17 @@ struct PGeom {
   static constexpr int NR = S * S;
 };
 
-// position of column w inside a permuted q1 row: pairs (i, i+4) of each 8-block are adjacent
+// position of column w inside a permuted q1 row: pairs (i, i + WPT/2) of each WPT-block are adjacent
+template <int WPT = 8>
 __host__ __device__ __forceinline__ int perm8(int w) {
-  const int i = w & 7;
-  return (w & ~7) + ((i & 3) << 1) + (i >> 2);
+  constexpr int NP = WPT / 2;
+  const int i = w % WPT;
+  return (w - i) + ((i % NP) << 1) + (i / NP);
 }
 
-template <int S, int L, int IN, int EPI, bool NTK, int CIN, bool Q2P = true>
+template <int S, int L, int IN, int EPI, bool NTK, int CIN, bool Q2P = true, int WPT = 8>
 size_t stage_p_smem_bytes() {
-  using G = PGeom<S>;
+  using G = PGeom<S, WPT>;
   const int xs1 = IN == IN_FROM_X ? S * S * CIN : 0;
   const int xs2 = IN == IN_FROM_X ? S * S * 4 : 0;
   const int q1 = L * S * S, q2 = (Q2P ? 2 : 1) * L * S * S;
@@ -202,11 +204,11 @@ size_t stage_p_smem_bytes() {
 //         default for the dominant kernel when b_std = 0); bit 0: degree-7 fit of G, an unmeasured round-2
 //         candidate reachable only through NTK_B200_PVAR (stage_packed.cu)
 template <int S, int L, int IN, int EPI, bool NTK, int CIN, bool RC, int LAG = 1, int MINB = 2, bool Q2P = true,
-          bool ERF = false, int VAR = 0>
-__global__ void __launch_bounds__(PGeom<S>::NT, MINB)
+          bool ERF = false, int VAR = 0, int WPT = 8>
+__global__ void __launch_bounds__(PGeom<S, WPT>::NT, MINB)
 k_stage_p(const StageArgs<float> a) {
-  using G = PGeom<S>;
-  constexpr int WPT = 8, NP = 4;  // 4 pairs (i, i+4)
+  using G = PGeom<S, WPT>;
+  constexpr int NP = WPT / 2;  // NP pairs (i, i + NP)
   constexpr int TPP = G::TPP, LPG = G::LPG, NWB = G::NWB, LW = G::LW, NR = G::NR;
   constexpr int SO = S / 2;
   constexpr int SP = S + 1;
@@ -275,11 +277,11 @@ k_stage_p(const StageArgs<float> a) {
     const float2* g2 = reinterpret_cast<const float2*>(a.qm2) + (long long)sj * L * S * S;
     for (int e = tg; e < L * S * S; e += TPP) {
       const int w = e % S, row = e / S;
-      q1A[row * S + perm8(w)] = fmaxf(__ldg(&g1[e].x), kQFloor);
+      q1A[row * S + perm8<WPT>(w)] = fmaxf(__ldg(&g1[e].x), kQFloor);
       const float nq = -fmaxf(__ldg(&g2[e].x), kQFloor);
       if (Q2P) {
         q2B[(row * S + w) * 2] = nq;
-        q2B[(row * S + ((w + S - 4) % S)) * 2 + 1] = nq;
+        q2B[(row * S + ((w + S - NP) % S)) * 2 + 1] = nq;
       } else {
         q2B[row * S + w] = nq;
       }
@@ -300,7 +302,7 @@ k_stage_p(const StageArgs<float> a) {
   }
   float2 mL[NP + 1];  // mL[j] = (lk[j], lk[j+4]): masks of the left links of pair j == right links of pair j-1
 #pragma unroll
-  for (int j = 0; j <= NP; ++j) mL[j] = f2(lk[j], lk[j + 4]);
+  for (int j = 0; j <= NP; ++j) mL[j] = f2(lk[j], lk[j + NP]);
   int off2[WPT];      // (w0 + i + cw) mod S
 #pragma unroll
   for (int i = 0; i < WPT; ++i) off2[i] = (w0 + i + cw) % S;
@@ -378,12 +380,12 @@ k_stage_p(const StageArgs<float> a) {
         acc[i] = v;
       }
 #pragma unroll
-      for (int j = 0; j < NP; ++j) PK[j] = f2(acc[j], acc[j + 4]);
+      for (int j = 0; j < NP; ++j) PK[j] = f2(acc[j], acc[j + NP]);
     } else {
 #pragma unroll
       for (int j = 0; j < NP; ++j) {
-        PK[j] = f2(nK[j], nK[j + 4]);
-        if (NTK) PU[j] = f2(__fadd_rn(nK[j], nT[j]), __fadd_rn(nK[j + 4], nT[j + 4]));
+        PK[j] = f2(nK[j], nK[j + NP]);
+        if (NTK) PU[j] = f2(__fadd_rn(nK[j], nT[j]), __fadd_rn(nK[j + NP], nT[j + NP]));
       }
       fetch(t + 1);
     }
@@ -441,8 +443,13 @@ k_stage_p(const StageArgs<float> a) {
       // ---- finish the vertical sum, add the bias, apply the activation ---------------------
       {
         const float4* q1r = reinterpret_cast<const float4*>(q1A + (l * S + h) * S + w0);
-        const float4 qa01 = q1r[0], qa23 = q1r[1];
-        const float2 q1p[NP] = {f2(qa01.x, qa01.y), f2(qa01.z, qa01.w), f2(qa23.x, qa23.y), f2(qa23.z, qa23.w)};
+        float2 q1p[NP];
+#pragma unroll
+        for (int j = 0; j < NP; j += 2) {
+          const float4 qa = q1r[j / 2];
+          q1p[j] = f2(qa.x, qa.y);
+          q1p[j + 1] = f2(qa.z, qa.w);
+        }
         const unsigned q2row = q2base + (unsigned)((l * S + h2) * S * (Q2P ? 8 : 4));
         const float2 coef2 = f2s(a.lp[l].coef), hab2 = f2s(a.lp[l].hab2);
         const float bias = a.lp[l].bias;
@@ -461,7 +468,7 @@ k_stage_p(const StageArgs<float> a) {
             nq2 = lds_f2(q2row + (unsigned)off2[j] * 8u);
           } else {
             nq2.x = lds_f1(q2row + (unsigned)off2[j] * 4u);
-            nq2.y = lds_f1(q2row + (unsigned)off2[j + 4] * 4u);
+            nq2.y = lds_f1(q2row + (unsigned)off2[j + NP] * 4u);
           }
           if (ERF && a.lp[l].kind == ACT_ERF)
             act_pair_erf<NTK>(ck, cu, q1p[j], nq2, a.lp[l].e_in, a.lp[l].eA, a.lp[l].eT, a.lp[l].eC, BK[l][j], BU[l][j]);
@@ -483,10 +490,10 @@ k_stage_p(const StageArgs<float> a) {
 #pragma unroll
           for (int j = 0; j < NP; ++j) {
             a.outK[base + (long long)j * S] = BK[L - 1][j].x;
-            a.outK[base + (long long)(j + 4) * S] = BK[L - 1][j].y;
+            a.outK[base + (long long)(j + NP) * S] = BK[L - 1][j].y;
             if (NTK) {
               a.outT[base + (long long)j * S] = __fsub_rn(BU[L - 1][j].x, BK[L - 1][j].x);
-              a.outT[base + (long long)(j + 4) * S] = __fsub_rn(BU[L - 1][j].y, BK[L - 1][j].y);
+              a.outT[base + (long long)(j + NP) * S] = __fsub_rn(BU[L - 1][j].y, BK[L - 1][j].y);
             }
           }
         }
@@ -502,10 +509,10 @@ k_stage_p(const StageArgs<float> a) {
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
           sK[(w0 + j) * SP + cw] = BK[L - 1][j].x;
-          sK[(w0 + j + 4) * SP + cw] = BK[L - 1][j].y;
+          sK[(w0 + j + NP) * SP + cw] = BK[L - 1][j].y;
           if (NTK) {
             sU[(w0 + j) * SP + cw] = BU[L - 1][j].x;
-            sU[(w0 + j + 4) * SP + cw] = BU[L - 1][j].y;
+            sU[(w0 + j + NP) * SP + cw] = BU[L - 1][j].y;
           }
         }
         if (TPP > 32)
