@@ -10,7 +10,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libntk_b200.so')
+LIB_PATH = os.environ.get('NTK_B200_LIB') or os.path.join(_HERE, 'libntk_b200.so')  # override: A/B builds (profiles/)
 
 NTK_F32, NTK_F64 = 0, 1
 (OP_DENSE, OP_CONV, OP_ABRELU, OP_ERF, OP_AVGPOOL, OP_GAP, OP_FLATTEN, OP_FANINSUM, OP_IDENTITY, OP_GELU, OP_SIN,

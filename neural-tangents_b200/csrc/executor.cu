@@ -174,13 +174,40 @@ int op_conv(Env& env, const ntk_op_t& op, const TState& in, TState& out, int t1,
     return NTK_OK;
   };
   const long long P = (long long)t1 * t2;
-  NTK_TRY(run(in.nngp, nullptr, P, scale, shift, &out.nngp));
+  const bool k3 = kh == 3 && kw == 3 && pad != NTK_PAD_CIRCULAR;
+  auto run3 = [&](Buf* srcK, Buf* srcT, long long np, Buf** dstK, Buf** dstT) -> int {
+    Buf* ok = env.alloc((size_t)(np * per_o) * sizeof(T), &st);
+    if (!ok) return st;
+    Buf* ot = nullptr;
+    if (srcT) {
+      ot = env.alloc((size_t)(np * per_o) * sizeof(T), &st);
+      if (!ot) return st;
+    }
+    LAUNCH(env, k_conv3<T>, grid_for(np * per_o), kThreads, 0, (const T*)srcK->p, srcT ? (const T*)srcT->p : (const T*)nullptr,
+           (T*)ok->p, ot ? (T*)ot->p : (T*)nullptr, np, g, scale, shift);
+    *dstK = ok;
+    if (dstT) *dstT = ot;
+    return NTK_OK;
+  };
   out.ntk_mode = in.ntk_mode;
-  if (in.ntk_mode == NTK_NTK_TENSOR) {
-    NTK_TRY(run(in.ntk, out.nngp, P, scale, (T)0, &out.ntk));  // linear.py:1396-1398
-  } else if (in.ntk_mode == NTK_NTK_ZERO) {
+  if (k3) {
+    NTK_TRY(run3(in.nngp, in.ntk_mode == NTK_NTK_TENSOR ? in.ntk : nullptr, P, &out.nngp, &out.ntk));
+  } else {
+    NTK_TRY(run(in.nngp, nullptr, P, scale, shift, &out.nngp));
+    if (in.ntk_mode == NTK_NTK_TENSOR) NTK_TRY(run(in.ntk, out.nngp, P, scale, (T)0, &out.ntk));  // linear.py:1396-1398
+  }
+  if (in.ntk_mode == NTK_NTK_ZERO) {
     NTK_TRY(copy_buf<T>(env, out.nngp, (size_t)(P * per_o) * sizeof(T), &out.ntk));
     out.ntk_mode = NTK_NTK_TENSOR;
+  }
+  if (k3) {
+    NTK_TRY(run3(in.cov1, nullptr, t1, &out.cov1, nullptr));
+    NTK_TRY(run3(in.cov2, nullptr, t2, &out.cov2, nullptr));
+    out.H = g.Ho;
+    out.W = g.Wo;
+    out.gaussian = true;
+    out.valid = true;
+    return NTK_OK;
   }
   NTK_TRY(run(in.cov1, nullptr, t1, scale, shift, &out.cov1));
   NTK_TRY(run(in.cov2, nullptr, t2, scale, shift, &out.cov2));
@@ -311,12 +338,16 @@ int op_act(Env& env, const ntk_op_t& op, TState& in, TState& out, bool steal, in
   }
   const T* sp = stab ? (const T*)stab->p : (const T*)nullptr;
   T* tt = out.ntk_mode == NTK_NTK_TENSOR ? (T*)out.ntk->p : (T*)nullptr;
-  LAUNCH(env, k_act<T>, grid_for(P * per), kThreads, 0, (T*)out.nngp->p, tt, (const T*)q1->p,
-         (const T*)q2->p, P, PairMap{t2, 0}, H, W, ap, sp);
-  LAUNCH(env, k_act<T>, grid_for(t1 * per), kThreads, 0, (T*)out.cov1->p, (T*)nullptr,
-         (const T*)q1->p, (const T*)q1->p, (long long)t1, PairMap{1, 1}, H, W, ap, sp);
-  LAUNCH(env, k_act<T>, grid_for(t2 * per), kThreads, 0, (T*)out.cov2->p, (T*)nullptr,
-         (const T*)q2->p, (const T*)q2->p, (long long)t2, PairMap{1, 1}, H, W, ap, sp);
+  auto act = [&](T* kk, T* ttp, const T* qa, const T* qb, long long np, PairMap pm) -> int {
+    if (W % 4 == 0)  // 4 consecutive w' per lane
+      LAUNCH(env, (k_act<T, 4>), grid_for(np * per / 4), kThreads, 0, kk, ttp, qa, qb, np, pm, H, W, ap, sp);
+    else
+      LAUNCH(env, (k_act<T, 1>), grid_for(np * per), kThreads, 0, kk, ttp, qa, qb, np, pm, H, W, ap, sp);
+    return NTK_OK;
+  };
+  NTK_TRY(act((T*)out.nngp->p, tt, (const T*)q1->p, (const T*)q2->p, P, PairMap{t2, 0}));
+  NTK_TRY(act((T*)out.cov1->p, (T*)nullptr, (const T*)q1->p, (const T*)q1->p, (long long)t1, PairMap{1, 1}));
+  NTK_TRY(act((T*)out.cov2->p, (T*)nullptr, (const T*)q2->p, (const T*)q2->p, (long long)t2, PairMap{1, 1}));
   env.unref(q1);
   env.unref(q2);
   if (stab) env.unref(stab);

@@ -57,30 +57,50 @@ inline int grid_for(long long n, int threads = kThreads) {
   return (int)b;
 }
 
+// Row decomposition shared by the per-op kernels: a tensor [P, A, A, B, B] is walked as rows (p, a, a') by groups of
+// G = min(32, pow2ceil(B * B)) lanes, the lanes of a group stride over the (b, b') plane.  The 64-bit divisions are paid
+// once per row instead of once per element (round 1: ~200 integer instructions per element, the per-op path ran at 12 %
+// of its own HBM traffic bound); consecutive lanes still touch consecutive b' (coalesced).
+struct RowWalk {
+  long long row, nrows, stride;
+  int e0, G;
+  // `items` = work items per row handled by the lanes of a group (B * B elements, or B * B / 4 quads)
+  __device__ __forceinline__ RowWalk(long long P, int A, int B, int items = 0) {
+    const int bb = items > 0 ? items : B * B;
+    G = 32;
+    while (G > 1 && (G >> 1) >= bb) G >>= 1;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    row = t / G;
+    e0 = (int)(t % G);
+    stride = (long long)gridDim.x * blockDim.x / G;
+    nrows = P * A * A;
+  }
+};
+
 // ---- input layer: requirements.py:542-553 (cross) / 529-539 (self) -----------
 // out[p,h,h',w,w'] = (1/C) sum_c x1[i,h,w,c] * x2[j,h',w',c]
 template <typename T>
 __global__ void k_input_cov(const T* __restrict__ x1, const T* __restrict__ x2, T* __restrict__ out,
                             long long P, PairMap pm, int H, int W, int C, T inv_c) {
-  const long long per = (long long)H * H * W * W;
-  const long long total = P * per;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    long long p = idx / per;
-    int r = (int)(idx % per);
-    int w2 = r % W;
-    r /= W;
-    int w = r % W;
-    r /= W;
-    int h2 = r % H;
-    int h = r / H;
+  RowWalk rw(P, H, W);
+  const int ww = W * W;
+  for (long long row = rw.row; row < rw.nrows; row += rw.stride) {
+    const long long p = row / ((long long)H * H);
+    const int r = (int)(row - p * ((long long)H * H));
+    const int h = r / H, h2 = r - h * H;
     int i, j;
     pm.ij(p, i, j);
-    const T* a = x1 + (((long long)i * H + h) * W + w) * C;
-    const T* b = x2 + (((long long)j * H + h2) * W + w2) * C;
-    T acc = 0;
-    for (int c = 0; c < C; ++c) acc = fma_t(a[c], b[c], acc);
-    out[idx] = acc * inv_c;
+    const T* arow = x1 + ((long long)i * H + h) * W * C;
+    const T* brow = x2 + ((long long)j * H + h2) * W * C;
+    T* orow = out + row * ww;
+    for (int e = rw.e0; e < ww; e += rw.G) {
+      const int w = e / W, w2 = e - w * W;
+      const T* a = arow + w * C;
+      const T* b = brow + w2 * C;
+      T acc = 0;
+      for (int c = 0; c < C; ++c) acc = fma_t(a[c], b[c], acc);
+      orow[e] = acc * inv_c;
+    }
   }
 }
 
@@ -115,43 +135,100 @@ struct ConvGeom {
 template <typename T>
 __global__ void k_conv(const T* __restrict__ in, const T* __restrict__ addend, T* __restrict__ out,
                        long long P, ConvGeom g, T scale, T shift) {
-  const long long per_o = (long long)g.Ho * g.Ho * g.Wo * g.Wo;
   const long long per_i = (long long)g.Hi * g.Hi * g.Wi * g.Wi;
-  const long long total = P * per_o;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    long long p = idx / per_o;
-    int r = (int)(idx % per_o);
-    int b2 = r % g.Wo;
-    r /= g.Wo;
-    int b = r % g.Wo;
-    r /= g.Wo;
-    int a2 = r % g.Ho;
-    int a = r / g.Ho;
+  const int ww = g.Wo * g.Wo;
+  RowWalk rw(P, g.Ho, g.Wo);
+  // Without wrap-around the valid taps of an output are the index ranges [ilo, ihi) x [jlo, jhi) and their addresses an
+  // arithmetic progression: tap (i, j) sits at base + i * SI + j * SJ (both members move together along the diagonal).
+  const int SI = (g.Hi + 1) * g.Wi * g.Wi, SJ = g.Wi + 1;
+  for (long long row = rw.row; row < rw.nrows; row += rw.stride) {
+    const long long p = row / ((long long)g.Ho * g.Ho);
+    const int r = (int)(row - p * ((long long)g.Ho * g.Ho));
+    const int a = r / g.Ho, a2 = r - a * g.Ho;
     const T* src = in + p * per_i;
-    T acc = 0;
-    for (int i = 0; i < g.kh; ++i) {
-      int h = g.sh * a + i - g.loh, h2 = g.sh * a2 + i - g.loh;
-      if (g.circular) {
-        h = ((h % g.Hi) + g.Hi) % g.Hi;
-        h2 = ((h2 % g.Hi) + g.Hi) % g.Hi;
-      } else if (h < 0 || h >= g.Hi || h2 < 0 || h2 >= g.Hi) {
-        continue;
-      }
-      for (int j = 0; j < g.kw; ++j) {
-        int w = g.sw * b + j - g.low, w2 = g.sw * b2 + j - g.low;
-        if (g.circular) {
-          w = ((w % g.Wi) + g.Wi) % g.Wi;
-          w2 = ((w2 % g.Wi) + g.Wi) % g.Wi;
-        } else if (w < 0 || w >= g.Wi || w2 < 0 || w2 >= g.Wi) {
-          continue;
+    const T* arow = addend ? addend + row * ww : nullptr;
+    T* orow = out + row * ww;
+    if (!g.circular) {
+      const int h0 = g.sh * a - g.loh, h20 = g.sh * a2 - g.loh;
+      const int ilo = max(0, max(-h0, -h20)), ihi = min(g.kh, min(g.Hi - h0, g.Hi - h20));
+      const T* rbase = src + ((long long)h0 * g.Hi + h20) * (g.Wi * g.Wi);  // may point before `src`: only valid taps are read
+      for (int e = rw.e0; e < ww; e += rw.G) {
+        const int b = e / g.Wo, b2 = e - b * g.Wo;
+        const int w0 = g.sw * b - g.low, w20 = g.sw * b2 - g.low;
+        const int jlo = max(0, max(-w0, -w20)), jhi = min(g.kw, min(g.Wi - w0, g.Wi - w20));
+        const T* ebase = rbase + (w0 * g.Wi + w20);
+        T acc = 0;
+        for (int i = ilo; i < ihi; ++i) {
+          const T* tp = ebase + i * SI + jlo * SJ;
+          for (int j = jlo; j < jhi; ++j, tp += SJ) acc += __ldg(tp);
         }
-        acc += src[(((long long)h * g.Hi + h2) * g.Wi + w) * g.Wi + w2];
+        T v = fma_t(acc, scale, shift);
+        if (arow) v += arow[e];
+        orow[e] = v;
       }
+      continue;
     }
-    T v = fma_t(acc, scale, shift);
-    if (addend) v += addend[idx];
-    out[idx] = v;
+    for (int e = rw.e0; e < ww; e += rw.G) {
+      const int b = e / g.Wo, b2 = e - b * g.Wo;
+      T acc = 0;
+      for (int i = 0; i < g.kh; ++i) {
+        const int h = (((g.sh * a + i - g.loh) % g.Hi) + g.Hi) % g.Hi;
+        const int h2 = (((g.sh * a2 + i - g.loh) % g.Hi) + g.Hi) % g.Hi;
+        const T* plane = src + ((long long)h * g.Hi + h2) * g.Wi * g.Wi;
+        for (int j = 0; j < g.kw; ++j) {
+          const int w = (((g.sw * b + j - g.low) % g.Wi) + g.Wi) % g.Wi;
+          const int w2 = (((g.sw * b2 + j - g.low) % g.Wi) + g.Wi) % g.Wi;
+          acc += plane[w * g.Wi + w2];
+        }
+      }
+      T v = fma_t(acc, scale, shift);
+      if (arow) v += arow[e];
+      orow[e] = v;
+    }
+  }
+}
+
+// 3 x 3 filters without wrap-around (every SAME / VALID 3 x 3 conv, any stride): the nine taps unrolled and predicated, nngp
+// and ntk in ONE pass -- the ntk's addend is the nngp value just computed (linear.py:1396-1398), so it is never re-read.
+// Same tap order and the same roundings as k_conv.
+template <typename T>
+__global__ void k_conv3(const T* __restrict__ inK, const T* __restrict__ inT, T* __restrict__ outK,
+                        T* __restrict__ outT, long long P, ConvGeom g, T scale, T shift) {
+  const int WW = g.Wi * g.Wi;
+  const long long per_i = (long long)g.Hi * g.Hi * WW;
+  const int ww = g.Wo * g.Wo;
+  const int SI = (g.Hi + 1) * WW, SJ = g.Wi + 1;
+  const bool has_t = inT != nullptr;
+  RowWalk rw(P, g.Ho, g.Wo);
+  for (long long row = rw.row; row < rw.nrows; row += rw.stride) {
+    const long long p = row / ((long long)g.Ho * g.Ho);
+    const int r = (int)(row - p * ((long long)g.Ho * g.Ho));
+    const int a = r / g.Ho, a2 = r - a * g.Ho;
+    const int h0 = g.sh * a - g.loh, h20 = g.sh * a2 - g.loh;
+    bool vi[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) vi[i] = h0 + i >= 0 && h0 + i < g.Hi && h20 + i >= 0 && h20 + i < g.Hi;
+    const long long rb = p * per_i + ((long long)h0 * g.Hi + h20) * WW;
+    for (int e = rw.e0; e < ww; e += rw.G) {
+      const int b = e / g.Wo, b2 = e - b * g.Wo;
+      const int w0 = g.sw * b - g.low, w20 = g.sw * b2 - g.low;
+      bool vj[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) vj[j] = w0 + j >= 0 && w0 + j < g.Wi && w20 + j >= 0 && w20 + j < g.Wi;
+      const long long eb = rb + (w0 * g.Wi + w20);
+      T ak = 0, at = 0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          if (vi[i] && vj[j]) {
+            ak += __ldg(inK + eb + (i * SI + j * SJ));
+            if (has_t) at += __ldg(inT + eb + (i * SI + j * SJ));
+          }
+      const T k = fma_t(ak, scale, shift);
+      outK[row * ww + e] = k;
+      if (has_t) outT[row * ww + e] = fma_t(at, scale, (T)0) + k;
+    }
   }
 }
 
@@ -163,67 +240,55 @@ struct PoolGeom {
 
 template <typename T>
 __global__ void k_pool(const T* __restrict__ in, T* __restrict__ out, long long P, PoolGeom g) {
-  const long long per_o = (long long)g.Ho * g.Ho * g.Wo * g.Wo;
   const long long per_i = (long long)g.Hi * g.Hi * g.Wi * g.Wi;
-  const long long total = P * per_o;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    long long p = idx / per_o;
-    int r = (int)(idx % per_o);
-    int b2 = r % g.Wo;
-    r /= g.Wo;
-    int b = r % g.Wo;
-    r /= g.Wo;
-    int a2 = r % g.Ho;
-    int a = r / g.Ho;
+  const int ww = g.Wo * g.Wo;
+  RowWalk rw(P, g.Ho, g.Wo);
+  // window members inside the input along one axis (all of them under CIRCULAR padding)
+  auto count = [&](int o, int s, int win, int lo, int n) {
+    int c = 0;
+    for (int i = 0; i < win; ++i) {
+      const int v = s * o + i - lo;
+      if (g.circular || (v >= 0 && v < n)) ++c;
+    }
+    return c;
+  };
+  for (long long row = rw.row; row < rw.nrows; row += rw.stride) {
+    const long long p = row / ((long long)g.Ho * g.Ho);
+    const int r = (int)(row - p * ((long long)g.Ho * g.Ho));
+    const int a = r / g.Ho, a2 = r - a * g.Ho;
     const T* src = in + p * per_i;
-    T acc = 0;
-    int cnt_h = 0, cnt_h2 = 0, cnt_w = 0, cnt_w2 = 0;
-    for (int i = 0; i < g.wh; ++i) {
-      int h = g.sh * a + i - g.loh;
-      if (g.circular) h = ((h % g.Hi) + g.Hi) % g.Hi;
-      if (h >= 0 && h < g.Hi) ++cnt_h;
-    }
-    for (int i = 0; i < g.wh; ++i) {
-      int h = g.sh * a2 + i - g.loh;
-      if (g.circular) h = ((h % g.Hi) + g.Hi) % g.Hi;
-      if (h >= 0 && h < g.Hi) ++cnt_h2;
-    }
-    for (int i = 0; i < g.ww; ++i) {
-      int w = g.sw * b + i - g.low;
-      if (g.circular) w = ((w % g.Wi) + g.Wi) % g.Wi;
-      if (w >= 0 && w < g.Wi) ++cnt_w;
-    }
-    for (int i = 0; i < g.ww; ++i) {
-      int w = g.sw * b2 + i - g.low;
-      if (g.circular) w = ((w % g.Wi) + g.Wi) % g.Wi;
-      if (w >= 0 && w < g.Wi) ++cnt_w2;
-    }
-    for (int i = 0; i < g.wh; ++i) {
-      int h = g.sh * a + i - g.loh;
-      if (g.circular) h = ((h % g.Hi) + g.Hi) % g.Hi;
-      if (h < 0 || h >= g.Hi) continue;
-      for (int i2 = 0; i2 < g.wh; ++i2) {
-        int h2 = g.sh * a2 + i2 - g.loh;
-        if (g.circular) h2 = ((h2 % g.Hi) + g.Hi) % g.Hi;
-        if (h2 < 0 || h2 >= g.Hi) continue;
-        for (int j = 0; j < g.ww; ++j) {
-          int w = g.sw * b + j - g.low;
-          if (g.circular) w = ((w % g.Wi) + g.Wi) % g.Wi;
-          if (w < 0 || w >= g.Wi) continue;
-          const T* row = src + (((long long)h * g.Hi + h2) * g.Wi + w) * g.Wi;
-          for (int j2 = 0; j2 < g.ww; ++j2) {
-            int w2 = g.sw * b2 + j2 - g.low;
-            if (g.circular) w2 = ((w2 % g.Wi) + g.Wi) % g.Wi;
-            if (w2 < 0 || w2 >= g.Wi) continue;
-            acc += row[w2];
+    T* orow = out + row * ww;
+    const int cnt_h = count(a, g.sh, g.wh, g.loh, g.Hi), cnt_h2 = count(a2, g.sh, g.wh, g.loh, g.Hi);
+    for (int e = rw.e0; e < ww; e += rw.G) {
+      const int b = e / g.Wo, b2 = e - b * g.Wo;
+      T acc = 0;
+      for (int i = 0; i < g.wh; ++i) {
+        int h = g.sh * a + i - g.loh;
+        if (g.circular) h = ((h % g.Hi) + g.Hi) % g.Hi;
+        if (h < 0 || h >= g.Hi) continue;
+        for (int i2 = 0; i2 < g.wh; ++i2) {
+          int h2 = g.sh * a2 + i2 - g.loh;
+          if (g.circular) h2 = ((h2 % g.Hi) + g.Hi) % g.Hi;
+          if (h2 < 0 || h2 >= g.Hi) continue;
+          for (int j = 0; j < g.ww; ++j) {
+            int w = g.sw * b + j - g.low;
+            if (g.circular) w = ((w % g.Wi) + g.Wi) % g.Wi;
+            if (w < 0 || w >= g.Wi) continue;
+            const T* rowp = src + (((long long)h * g.Hi + h2) * g.Wi + w) * g.Wi;
+            for (int j2 = 0; j2 < g.ww; ++j2) {
+              int w2 = g.sw * b2 + j2 - g.low;
+              if (g.circular) w2 = ((w2 % g.Wi) + g.Wi) % g.Wi;
+              if (w2 < 0 || w2 >= g.Wi) continue;
+              acc += rowp[w2];
+            }
           }
         }
       }
+      T norm = (T)((long long)g.wh * g.wh * g.ww * g.ww);
+      if (g.normalize_edges)
+        norm = (T)((long long)cnt_h * cnt_h2 * count(b, g.sw, g.ww, g.low, g.Wi) * count(b2, g.sw, g.ww, g.low, g.Wi));
+      orow[e] = g.sum ? acc : acc / norm;
     }
-    T norm = g.normalize_edges ? (T)((long long)cnt_h * cnt_h2 * cnt_w * cnt_w2)
-                               : (T)((long long)g.wh * g.wh * g.ww * g.ww);
-    out[idx] = g.sum ? acc : acc / norm;
   }
 }
 
@@ -305,12 +370,17 @@ __device__ __forceinline__ void erf_point(T k, T prod, T& k_out, T& dot) {
 // In-place on K (and Tt when non-null).  q1/q2 are the diagonal maps of cov1/cov2
 // taken BEFORE this activation.  `stab` (device scalar, nullable) is the
 // do_stabilize factor of elementwise.py:430-436.
-template <typename T>
+template <typename T, int VEC>
+struct alignas(sizeof(T) * VEC) ActPack {
+  T v[VEC];
+};
+
+// VEC = 4 (W % 4 == 0): a lane owns 4 consecutive w' (one 16 / 32-byte access per tensor); VEC = 1 otherwise.
+template <typename T, int VEC>
 __global__ void k_act(T* __restrict__ K, T* __restrict__ Tt, const T* __restrict__ q1,
                       const T* __restrict__ q2, long long P, PairMap pm, int H, int W, ActParams ap,
                       const T* __restrict__ stab) {
-  const long long per = (long long)H * H * W * W;
-  const long long total = P * per;
+  using Pack = ActPack<T, VEC>;
   const T a = (T)ap.a, b = (T)ap.b;
   const T coef_s = (a - b) * (a - b) / ((T)2 * Consts<T>::pi());
   const T half_ab = (a * a + b * b) / (T)2;
@@ -318,21 +388,9 @@ __global__ void k_act(T* __restrict__ K, T* __restrict__ Tt, const T* __restrict
   const T cos2c = ap.kind == NTK_OP_SIN ? (T)cos(2.0 * ap.c) : (T)0;
   T factor = (T)1;
   if (stab) factor = max_t(*stab, (T)1e-12);
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    long long p = idx / per;
-    int r = (int)(idx % per);
-    int w2 = r % W;
-    r /= W;
-    int w = r % W;
-    r /= W;
-    int h2 = r % H;
-    int h = r / H;
-    int i, j;
-    pm.ij(p, i, j);
-    T v1 = q1[((long long)i * H + h) * W + w];
-    T v2 = q2[((long long)j * H + h2) * W + w2];
-    T k = K[idx];
+  const bool has_t = Tt != nullptr;
+  // one element: k, t in / out
+  auto point = [&](T& k, T& t, T v1, T v2) {
     T ko, dot;
     if (ap.kind == NTK_OP_ABRELU) {
       if (stab) {
@@ -342,19 +400,19 @@ __global__ void k_act(T* __restrict__ K, T* __restrict__ Tt, const T* __restrict
       }
       abrelu_point<T>(k, v1 * v2, coef_s, half_ab, ko, dot);
       if (stab) ko *= factor;
-      K[idx] = ko;
-      if (Tt) Tt[idx] *= dot;
+      k = ko;
+      t *= dot;
     } else if (ap.kind == NTK_OP_ERF) {
       k *= bb;
       T prod = ((T)1 + (T)2 * bb * v1) * ((T)1 + (T)2 * bb * v2);
       erf_point<T>(k, prod, ko, dot);
-      K[idx] = fma_t(aa, ko, cc);
-      if (Tt) Tt[idx] = aa * (bb * Tt[idx] * dot);
+      k = fma_t(aa, ko, cc);
+      t = aa * (bb * t * dot);
     } else if (ap.kind == NTK_OP_LAYERNORM) {
       // linear.py:2566-2584: every kernel is divided by sqrt((eps + q1)(eps + q2)); a = eps
       const T inv = (T)1 / sqrt_t((a + v1) * (a + v2));
-      K[idx] = k * inv;
-      if (Tt) Tt[idx] *= inv;
+      k = k * inv;
+      t *= inv;
     } else {
       if (ap.kind == NTK_OP_GELU)
         gelu_point<T>(k, v1, v2, ko, dot);
@@ -362,8 +420,36 @@ __global__ void k_act(T* __restrict__ K, T* __restrict__ Tt, const T* __restrict
         sin_point<T>(k, v1 + v2, aa / (T)2, bb, cos2c, ko, dot);
       else
         rbf_point<T>(k, v1 + v2, a, ko, dot);
-      K[idx] = ko;
-      if (Tt) Tt[idx] *= dot;
+      k = ko;
+      t *= dot;
+    }
+  };
+  const int items = W * W / VEC;
+  RowWalk rw(P, H, W, items);
+  for (long long row = rw.row; row < rw.nrows; row += rw.stride) {
+    const long long p = row / ((long long)H * H);
+    const int r = (int)(row - p * ((long long)H * H));
+    const int h = r / H, h2 = r - h * H;
+    int i, j;
+    pm.ij(p, i, j);
+    const T* q1row = q1 + ((long long)i * H + h) * W;
+    const T* q2row = q2 + ((long long)j * H + h2) * W;
+    Pack* krow = reinterpret_cast<Pack*>(K + row * (long long)(W * W));
+    Pack* trow = has_t ? reinterpret_cast<Pack*>(Tt + row * (long long)(W * W)) : nullptr;
+    for (int e = rw.e0; e < items; e += rw.G) {
+      const int w = (e * VEC) / W, w2 = e * VEC - w * W;
+      const T v1 = q1row[w];
+      const Pack v2 = *reinterpret_cast<const Pack*>(q2row + w2);
+      Pack k = krow[e], t;
+      if (has_t) t = trow[e];
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) {
+        T tt = has_t ? t.v[c] : (T)0;
+        point(k.v[c], tt, v1, v2.v[c]);
+        t.v[c] = tt;
+      }
+      krow[e] = k;
+      if (has_t) trow[e] = t;
     }
   }
 }

@@ -82,11 +82,26 @@ struct ResGeom {
 // form); pure-ABRelu networks run the ERF = false instantiation, which carries no Erf code.
 template <typename T>
 struct ResWpt {
-  static constexpr int value = sizeof(T) == 8 ? 4 : 8;
+#ifndef NTK_RES_WPT_F32
+#define NTK_RES_WPT_F32 8
+#endif
+  static constexpr int value = sizeof(T) == 8 ? 4 : NTK_RES_WPT_F32;
 };
 
+// Input rows of a LOADing kernel travel through a per-thread ring in shared memory, filled with cp.async one marched row
+// ahead (round 2: the direct __ldg rows were consumed at once -- 43 % of the warp stalls were long-scoreboard waits on
+// them); the ring keeps the last kResRing rows, so the identity shortcut (row t - 2) is read from it instead of from L2.
+constexpr int kResRing = 4;
+
+template <int BYTES>
+__device__ __forceinline__ void res_cp_async(void* dst_smem, const void* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(src), "n"(BYTES) : "memory");
+}
+
 template <typename T, int S, int IN, bool NTK, int CIN, bool ERF>
-__global__ void __launch_bounds__((ResGeom<S, ResWpt<T>::value>::NT))
+__global__ void __launch_bounds__((ResGeom<S, ResWpt<T>::value>::NT),
+                                  (sizeof(T) == 4 && ResWpt<T>::value == 4 ? 512 / ResGeom<S, ResWpt<T>::value>::NT : 1))
 k_res(const ResArgs<T> a) {
   using G = ResGeom<S, ResWpt<T>::value>;
   using V2 = typename Vec2<T>::type;
@@ -96,7 +111,8 @@ k_res(const ResArgs<T> a) {
   constexpr int XS1 = IN == IN_FROM_X ? S * S * CIN : 0;
   constexpr int XS2 = IN == IN_FROM_X ? S * S * 4 : 0;
   constexpr int QM = 2 * S * S * 2;  // two activation layers
-  constexpr int PER_GROUP = XS1 + XS2 + 2 * QM;
+  constexpr int RG = IN == IN_LOAD ? kResRing * 2 * WPT * TPP : 0;  // input-row ring [slot][K|T][i][thread]
+  constexpr int PER_GROUP = XS1 + XS2 + 2 * QM + RG;
   const int tid = threadIdx.x;
   const int grp = tid / TPP, tg = tid % TPP;
   T* sm = reinterpret_cast<T*>(smem_raw) + (size_t)grp * PER_GROUP;
@@ -104,6 +120,7 @@ k_res(const ResArgs<T> a) {
   T* x2s = x1s + XS1;
   V2* q1m = reinterpret_cast<V2*>(x2s + XS2);
   V2* q2m = q1m + 2 * S * S;
+  T* ring = reinterpret_cast<T*>(q2m + 2 * S * S);
 
   const int lig = tg % LPG, wig = tg / 32;
   const int wblk = lig / LW, cwsub = lig % LW;
@@ -215,6 +232,31 @@ k_res(const ResArgs<T> a) {
     }
   };
 
+  auto ring_at = [&](int r, int kt, int i) -> T* {
+    return ring + (((r & (kResRing - 1)) * 2 + kt) * WPT + i) * TPP + tg;
+  };
+  // start the copy of input row r into its ring slot (one commit group per row)
+  auto issue_row = [&](int r) {
+    if (IN == IN_LOAD) {
+      int h, ch;
+      const int rc = r < 0 ? 0 : (r > nrows - 1 ? nrows - 1 : r);
+      const long long ro = row_off(rc, h, ch) + (long long)w0 * ncw + kw;
+#pragma unroll
+      for (int i = 0; i < WPT; ++i) {
+        res_cp_async<sizeof(T)>(ring_at(r, 0, i), inK + ro + (long long)i * ncw);
+        if (NTK) res_cp_async<sizeof(T)>(ring_at(r, 1, i), inT + ro + (long long)i * ncw);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  };
+  auto ring_row = [&](int r, T* dk, T* dt) {
+#pragma unroll
+    for (int i = 0; i < WPT; ++i) {
+      dk[i] = *ring_at(r, 0, i);
+      dt[i] = NTK ? *ring_at(r, 1, i) : (T)0;
+    }
+  };
+
   // one conv unit: vertical taps of the old rows, horizontal taps of the new row (in place),
   // finish; returns the conv row (pre-bias) in ok/ot
   auto conv_unit = [&](const int u, const int slot, const T* pk, const T* pt, const bool has_t,
@@ -302,7 +344,9 @@ k_res(const ResArgs<T> a) {
         XT[i] = (T)0;
       }
     } else {
-      load_row(inK, inT, t, XK, XT);
+      issue_row(t + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");  // row t has landed (row t + 1 may be in flight)
+      ring_row(t, XK, XT);
     }
     // ---- side (shortcut) conv on the raw rows: emits row t - 1 -----------------------------
     T SK[WPT], ST[WPT];
@@ -349,9 +393,9 @@ k_res(const ResArgs<T> a) {
       r_out = t - 2;
     }
     // ---- residual (FanInSum, branching.py:87-93) -------------------------------------------
-    if (a.res == RES_INPUT) {
+    if (a.res == RES_INPUT && IN == IN_LOAD) {
       T RKr[WPT], RTr[WPT];
-      load_row(inK, inT, r_out, RKr, RTr);  // the block input, two rows back (L1/L2 hit)
+      ring_row(r_out, RKr, RTr);  // the block input, one or two rows back: still in the ring
 #pragma unroll
       for (int i = 0; i < WPT; ++i) {
         YK[i] = add_rn(YK[i], RKr[i]);
@@ -414,6 +458,7 @@ k_res(const ResArgs<T> a) {
     }
   };
 
+  issue_row(0);
   const int nsteps0 = nrows + n_units;
   const int nsteps = nsteps0 + (nsteps0 & 1);
   for (int t0 = 0; t0 < nsteps; t0 += 2) {
@@ -700,8 +745,9 @@ int launch_res(cudaStream_t stream, int64_t* launches, int S, bool from_x, const
     return NTK_OK;
   };
   auto smem_for = [&](int s, bool fx) {
-    const size_t per = (fx ? (size_t)s * s * 3 + (size_t)s * s * 4 : 0) + 2 * (size_t)(2 * s * s * 2);
     const int tpp = s * s / ResWpt<T>::value, nt = tpp < 128 ? 128 : tpp;
+    const size_t per = (fx ? (size_t)s * s * 3 + (size_t)s * s * 4 : (size_t)kResRing * 2 * ResWpt<T>::value * tpp) +
+                       2 * (size_t)(2 * s * s * 2);
     return per * (nt / tpp) * sizeof(T);
   };
 #define NTK_RES_CASE(SS)                                                                              \
