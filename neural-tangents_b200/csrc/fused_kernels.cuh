@@ -91,6 +91,11 @@ struct StageArgs {
   // EMB kernels: the RH x RW image sits in the top-left corner of the S x S shear (MNIST 28x28 in 32x32, any
   // H, W <= 32); positions outside are cut off by the link masks and never reach a result.  RH == RW == S otherwise.
   int RH, RW;
+  // VALID convs (round 2): the kernels compute the SAME stencil everywhere; the meaningful region after l VALID layers is
+  // the box [l, RH0 - l) x [l, RW0 - l) in both members -- its entries read only meaningful entries of the layer before
+  // (linear.py:3341-3378 without padding), everything outside is finite don't-care data.  The GAP epilogue sums the box
+  // of the stage's last layer: origin box_o (both axes), size box_h x box_w.  SAME networks: box_o = 0, box = RH x RW.
+  int box_o, box_h, box_w;
 };
 
 // Upper-triangular pair enumeration of a W x W block: row l holds the W - l pairs (l, l..W-1)
@@ -622,9 +627,12 @@ k_stage(const StageArgs<T> a) {
     const int wl = w0 + i - 1, wr = w0 + i;
     lk[i] = (wl >= 0 && wr <= RWc - 1 && ((wl + cw) % S) + 1 <= RWc - 1) ? (T)1 : (T)0;
   }
-  bool inw[WPT];  // EMB + GAP: element (w0 + i, w' = w0 + i + cw) lies inside the RW-wide image
+  bool inw[WPT];  // EMB + GAP: element (w0 + i, w' = w0 + i + cw) lies inside the box of the last layer
 #pragma unroll
-  for (int i = 0; i < WPT; ++i) inw[i] = !EMB || (w0 + i < RWc && ((w0 + i + cw) % S) < RWc);
+  for (int i = 0; i < WPT; ++i) {
+    const int wa = w0 + i - a.box_o, wb = ((w0 + i + cw) % S) - a.box_o;
+    inw[i] = !EMB || (wa >= 0 && wa < a.box_w && wb >= 0 && wb < a.box_w);
+  }
 #pragma unroll
   for (int i = 0; i < WPT; ++i) off2[i] = ((w0 + i + cw) % S) * (int)sizeof(V2);
   const unsigned q2base = (unsigned)__cvta_generic_to_shared(q2m);
@@ -813,7 +821,8 @@ k_stage(const StageArgs<T> a) {
           }
         }
       } else if (EPI == EPI_GAP) {
-        const bool row_in = !EMB || (h < RHc && ((h + ch) % S) < RHc);
+        const int ha = h - a.box_o, hb = ((h + ch) % S) - a.box_o;
+        const bool row_in = !EMB || (ha >= 0 && ha < a.box_h && hb >= 0 && hb < a.box_h);
 #pragma unroll
         for (int i = 0; i < WPT; ++i) {
           if (EMB && !(row_in && inw[i])) continue;
@@ -973,7 +982,36 @@ struct FusedPlan {
   int tail_pools = 0;
   bool tail_flatten = false, tail_gsum = false, tail_same = false;
   double tail_mul = 1.0;
+  bool valid_convs = false;  // every conv is 3x3 / 1 / VALID (all SAME otherwise; mixtures are not planned)
 };
+
+// Meaningful region of the maps: origin `o` (the same on both axes) and size h x w, in the coordinates of the stage's shear.
+struct FusedBox {
+  int o, h, w;
+};
+
+// Walks the boxes through the stages.  in_box[s]: region entering stage s; *last: region after the last stage's layers.
+// false: a map would be empty, or a pool would not be aligned with the box (odd origin).
+inline bool fused_walk_boxes(const FusedPlan& plan, int H, int W, std::vector<FusedBox>* in_box, FusedBox* last) {
+  FusedBox b{0, H, W};
+  for (size_t s = 0; s + 1 < plan.stages.size(); ++s) {
+    const FusedStage& st = plan.stages[s];
+    if (in_box) in_box->push_back(b);
+    if (plan.valid_convs) {
+      b.o += st.L;
+      b.h -= 2 * st.L;
+      b.w -= 2 * st.L;
+      if (b.h < 1 || b.w < 1) return false;
+    }
+    if (st.epi == EPI_POOL) {
+      if (b.o & 1) return false;  // the kernels pool rows / columns (2b, 2b + 1) of the shear
+      if (b.h < 2 || b.w < 2) return false;
+      b = FusedBox{b.o / 2, b.h / 2, b.w / 2};
+    }
+  }
+  if (last) *last = b;
+  return true;
+}
 
 // AvgPool / SumPool op flags: i[5] bit 0 = normalize_edges, bit 1 = SumPool; GAP: i[0] = 1 for GlobalSumPool
 inline bool pool_is_sum(const ntk_op_t& o) { return (o.i[5] & 2) != 0; }
@@ -990,9 +1028,16 @@ inline FusedPlan plan_fused(const std::vector<ntk_op_t>& ops, int n_slots, int o
     if (ops[k].src != (k == 0 ? 0 : ops[k - 1].dst)) return plan;
   }
   if (n == 0 || ops[n - 1].dst != out_slot) return plan;
-  auto is_conv = [](const ntk_op_t& o) {
-    return o.kind == NTK_OP_CONV && o.i[0] == 3 && o.i[1] == 3 && o.i[2] == 1 && o.i[3] == 1 &&
-           o.i[4] == NTK_PAD_SAME;
+  int pad0 = -1;  // padding of the first conv; every conv must use it
+  for (int k = 0; k < n; ++k)
+    if (ops[k].kind == NTK_OP_CONV) {
+      pad0 = ops[k].i[4];
+      break;
+    }
+  if (pad0 != NTK_PAD_SAME && pad0 != NTK_PAD_VALID) return plan;
+  plan.valid_convs = pad0 == NTK_PAD_VALID;
+  auto is_conv = [pad0](const ntk_op_t& o) {
+    return o.kind == NTK_OP_CONV && o.i[0] == 3 && o.i[1] == 3 && o.i[2] == 1 && o.i[3] == 1 && o.i[4] == pad0;
   };
   auto is_act = [](const ntk_op_t& o) {
     return (o.kind == NTK_OP_ABRELU && o.i[0] == 0) || o.kind == NTK_OP_ERF || o.kind == NTK_OP_GELU ||
@@ -1086,8 +1131,10 @@ bool fused_supported(const FusedPlan& plan, int H, int W, int C) {
   int S = fused_shear_size(H, W);
   if (S == 0) return false;
   if (C != 3 && C != 1) return false;  // FROM_X stages are instantiated for grey and RGB inputs
-  const bool emb = fused_needs_emb(H, W, C);
-  int RH = H, RW = W;
+  const bool emb = fused_needs_emb(H, W, C) || plan.valid_convs;  // VALID convs need the box-aware (EMB) epilogues
+  FusedBox last{0, H, W};
+  std::vector<FusedBox> in_box;
+  if (!fused_walk_boxes(plan, H, W, &in_box, &last)) return false;
   for (size_t s = 0; s + 1 < plan.stages.size(); ++s) {
     const FusedStage& st = plan.stages[s];
     if (emb)
@@ -1096,13 +1143,12 @@ bool fused_supported(const FusedPlan& plan, int H, int W, int C) {
     if (st.epi == EPI_POOL) {
       if (S <= 8) return false;  // S = 4 stages are not instantiated
       // VALID drops an odd last row (floor); SAME pads it with zeros the garbage outside the image cannot provide
-      if (st.pool_same && ((RH | RW) & 1)) return false;
-      if (RH < 2 || RW < 2) return false;
+      const int bh = in_box[s].h - (plan.valid_convs ? 2 * st.L : 0), bw = in_box[s].w - (plan.valid_convs ? 2 * st.L : 0);
+      if (st.pool_same && ((bh | bw) & 1)) return false;
       S /= 2;
-      RH /= 2;
-      RW /= 2;
     }
   }
+  const int RH = last.h, RW = last.w;
   // the tail pools + global reduction are computed as one global mean: every tail pool must tile the map exactly
   const int pools = plan.tail_pools;
   if (RH % (1 << pools) != 0 || RW % (1 << pools) != 0) return false;
@@ -1357,7 +1403,7 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
                int W0, int C, bool want_ntk, T* out_nngp, T* out_ntk, long long ld,
                bool full_square = false, bool upper = false) {
   const int S0 = fused_shear_size(H0, W0);
-  const bool emb = fused_needs_emb(H0, W0, C);
+  const bool emb = fused_needs_emb(H0, W0, C) || plan.valid_convs;
   const size_t xrow = (size_t)H0 * W0 * C;  // elements per input sample
   // `upper` (NTK_FLAG_UPPER_ONLY): x1 holds the same samples as x2[0:n1]; only entries (i, j >= i) are wanted.
   upper = upper && !symmetric && n2 >= n1;
@@ -1368,21 +1414,22 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
   // qm[s][set]: [n][L][S][S][2]
   std::vector<T*> qm1(n_st), qm2(n_st);
   std::vector<int> Ss(n_st), RHs(n_st), RWs(n_st);
+  // RHs / RWs: extent of the region the link masks keep connected at stage s (SAME: the image; VALID: origin + size
+  // of the box entering the stage -- the masks are don't-care there, see StageArgs::box_o)
   int RH_last = H0, RW_last = W0;
+  FusedBox last_box{0, H0, W0};
   {
-    int S = S0, RH = H0, RW = W0;
+    std::vector<FusedBox> in_box;
+    if (!fused_walk_boxes(plan, H0, W0, &in_box, &last_box)) return fail(NTK_EINVAL, "fused plan does not fit the input size");
+    int S = S0;
     for (size_t s = 0; s < n_st; ++s) {
       Ss[s] = S;
-      RHs[s] = RH;
-      RWs[s] = RW;
-      if (plan.stages[s].epi == EPI_POOL) {
-        S /= 2;
-        RH /= 2;
-        RW /= 2;
-      }
+      RHs[s] = in_box[s].o + in_box[s].h;
+      RWs[s] = in_box[s].o + in_box[s].w;
+      if (plan.stages[s].epi == EPI_POOL) S /= 2;
     }
-    RH_last = RHs[n_st - 1];
-    RW_last = RWs[n_st - 1];
+    RH_last = last_box.h;
+    RW_last = last_box.w;
   }
   for (size_t s = 0; s < n_st; ++s) {
     const size_t per = (size_t)plan.stages[s].L * Ss[s] * Ss[s] * 2 * sizeof(T);
@@ -1442,6 +1489,9 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
         StageArgs<T> a{};
         a.RH = RHs[s];
         a.RW = RWs[s];
+        a.box_o = 0;  // self pairs never end in a GAP epilogue
+        a.box_h = RHs[s];
+        a.box_w = RWs[s];
         a.x1 = a.x2 = x + (size_t)c0 * xrow;
         a.inK = cur;
         a.inT = nullptr;
@@ -1544,6 +1594,9 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
         StageArgs<T> a{};
         a.RH = RHs[s];
         a.RW = RWs[s];
+        a.box_o = last_box.o;  // read by the GAP epilogue (last stage) only
+        a.box_h = last_box.h;
+        a.box_w = last_box.w;
         a.x1 = x1 + (size_t)r0 * xrow;
         a.x2 = x2 + (size_t)c0 * xrow;
         const int epi = plan.stages[s].epi;

@@ -502,13 +502,15 @@ k_res(const ResArgs<T> a) {
 // recording (q, 1/sqrt q) in front of every activation.  One CTA per sample.
 // ---------------------------------------------------------------------------------------
 enum { Q_CONV = 0, Q_ACT = 1, Q_COPY = 2, Q_ADD = 3, Q_INPUT = 4 };
+constexpr int kQValid = 3;  // QOp::stride code of a VALID conv (linear.py:3341-3378 with no padding: every tap is inside)
+__host__ __device__ __forceinline__ int qconv_out_size(int S, int st) { return st == kQValid ? S - 2 : (S + st - 1) / st; }
 // A 3x3 / stride-2 / SAME conv on a size-S axis (lax.padtype_to_pads): out = ceil(S/2), total padding
 // (out-1)*2 + 3 - S = 1 (S even: lo = 0, window centred at 2a+1) or 2 (S odd: lo = 1, centred at 2a).
 __host__ __device__ __forceinline__ int strided_center_offset(int S) { return (S & 1) ? 0 : 1; }
 struct QOp {
   int kind;
   int dst, src;  // image buffers 0..2
-  int stride;    // Q_CONV: 1 or 2
+  int stride;    // Q_CONV: 1 or 2 (SAME), kQValid = 3x3 / stride 1 / VALID (out = S - 2, window centred at a + 1)
   int act_id;    // Q_ACT: q-map layer written
   double alpha, bias, kd0;
   int akind = ACT_ABRELU;  // Q_ACT: ABRelu(a = alpha, b = bias) or Erf(a = alpha, b = bias, c = erf_c)
@@ -569,12 +571,13 @@ __global__ void k_qprog(const T* __restrict__ x, int S0, int C, T in_scale, cons
       }
       __syncthreads();
       const int st = prog.stride[op];
-      const int So = (S + st - 1) / st;           // SAME: ceil(S / stride)
+      const int So = qconv_out_size(S, st);       // SAME: ceil(S / stride); VALID: S - 2
       const int o2 = strided_center_offset(S);    // window centre of a stride-2 conv: 2a+1 (S even), 2a (S odd)
       T* D = img + d * S0 * S0;
       for (int e = threadIdx.x; e < So * So; e += blockDim.x) {
         const int a_ = e / So, b_ = e % So;
-        const int h = st == 2 ? 2 * a_ + o2 : a_, w = st == 2 ? 2 * b_ + o2 : b_;
+        const int h = st == 2 ? 2 * a_ + o2 : (st == kQValid ? a_ + 1 : a_);
+        const int w = st == 2 ? 2 * b_ + o2 : (st == kQValid ? b_ + 1 : b_);
         const T vU = h > 0 ? (T)1 : (T)0, vD = h < S - 1 ? (T)1 : (T)0;
         const T box = fma_t(vD, scratch[(h < S - 1 ? h + 1 : h) * S + w],
                             fma_t(vU, scratch[(h > 0 ? h - 1 : h) * S + w], scratch[h * S + w]));
@@ -1126,11 +1129,12 @@ k_diagnet(const T* __restrict__ x1, const T* __restrict__ x2, int S0, int C, T i
         }
         __syncthreads();
         const int st = prog.stride[op];
-        const int So = (S + st - 1) / st;
+        const int So = qconv_out_size(S, st);
         const int o2 = strided_center_offset(S);
         for (int e = threadIdx.x; e < So * So; e += blockDim.x) {
           const int a_ = e / So, b_ = e % So;
-          const int h = st == 2 ? 2 * a_ + o2 : a_, w = st == 2 ? 2 * b_ + o2 : b_;
+          const int h = st == 2 ? 2 * a_ + o2 : (st == kQValid ? a_ + 1 : a_);
+          const int w = st == 2 ? 2 * b_ + o2 : (st == kQValid ? b_ + 1 : b_);
           const T vU = h > 0 ? (T)1 : (T)0, vD = h < S - 1 ? (T)1 : (T)0;
           const int eu = (h > 0 ? h - 1 : h) * S + w, ed = (h < S - 1 ? h + 1 : h) * S + w;
           const T k = fma_t(fma_t(vD, scK[ed], fma_t(vU, scK[eu], scK[h * S + w])), prog.alpha[op],
@@ -1256,12 +1260,12 @@ inline DiagPlan plan_diag(const std::vector<ntk_op_t>& ops, const std::vector<in
       return b;
     };
     if (o.kind == NTK_OP_CONV) {
-      if (!(o.i[0] == 3 && o.i[1] == 3 && o.i[2] == o.i[3] && (o.i[2] == 1 || o.i[2] == 2) &&
-            o.i[4] == NTK_PAD_SAME))
-        return DiagPlan();
+      const bool same = o.i[4] == NTK_PAD_SAME && (o.i[2] == 1 || o.i[2] == 2);
+      const bool valid = o.i[4] == NTK_PAD_VALID && o.i[2] == 1;  // round 2: VALID 3x3 / 1 on the diagonal column
+      if (!(o.i[0] == 3 && o.i[1] == 3 && o.i[2] == o.i[3] && (same || valid))) return DiagPlan();
       const int b = dst_buf(o.src, src_dies);
       if (b < 0) return DiagPlan();
-      plan.ops.push_back(QOp{Q_CONV, b, b, o.i[2], 0, o.f[0] / 9.0, o.i[5] ? o.f[1] : 0.0, 0.0});
+      plan.ops.push_back(QOp{Q_CONV, b, b, valid ? kQValid : o.i[2], 0, o.f[0] / 9.0, o.i[5] ? o.f[1] : 0.0, 0.0});
       buf_of[o.dst] = b;
     } else if (o.kind == NTK_OP_ABRELU || o.kind == NTK_OP_ERF) {
       if (o.kind == NTK_OP_ABRELU && o.i[0]) return DiagPlan();
@@ -1333,7 +1337,7 @@ int diag_gram(const DiagPlan& plan, Arena& arena, cudaStream_t stream, int64_t* 
       qp.akind[i] = ACT_ABRELU;
       qp.e_in[i] = qp.eA[i] = qp.eT[i] = qp.eC[i] = (T)0;
       if (o.kind == Q_CONV) {
-        Sb[o.dst] = (Sb[o.src] + o.stride - 1) / o.stride;  // SAME: ceil
+        Sb[o.dst] = qconv_out_size(Sb[o.src], o.stride);  // SAME: ceil; VALID: S - 2
         if (Sb[o.dst] < 1) return fail(NTK_EINVAL, "Conv output would be empty");
       } else if (o.kind == Q_COPY) {
         Sb[o.dst] = Sb[o.src];

@@ -133,6 +133,18 @@ CASES = {
                        (2, 5, 5, 2), (3, 5, 5, 2), ('nngp', 'ntk')),
     'layernorm_fcn_sym': (('serial', [('dense', 1.5, 0.3), ('layernorm', 1e-6), RELU, ('dense', 1., 0.)]),
                           (4, 12), None, ('nngp', 'ntk')),
+    # 3x3 / 1 / VALID convs (linear.py:3341-3378 without padding): Flatten tail (diagonal-column kernels), and pools + a
+    # GlobalAvgPool tail (stage kernels: 16 -> 12 -pool-> 6 -> 4, the box origin is even at the pool)
+    'valid_flatten': (('serial', [conv(pad='VALID', W=1.3, b=0.1), RELU, conv(pad='VALID'), ('abrelu', 0.1, 1., False),
+                                  conv(pad='VALID', W=1.1, b=0.05), RELU, ('flatten',), ('dense', 1., 0.1)]),
+                      (3, 12, 12, 3), (2, 12, 12, 3), ('nngp', 'ntk')),
+    'valid_pool_gap': (('serial', [conv(pad='VALID', W=1.3, b=0.1), RELU, conv(pad='VALID'), RELU, pool(),
+                                   conv(pad='VALID', W=1.1, b=0.2), ('abrelu', 0.2, 1., False), ('gap',),
+                                   ('dense', 1.2, 0.1)]),
+                       (2, 16, 16, 3), (3, 16, 16, 3), ('nngp', 'ntk')),
+    'valid_pool_gap_mnist_sym': (('serial', [conv(pad='VALID'), RELU, conv(pad='VALID'), RELU, pool(),
+                                             conv(pad='VALID'), RELU, conv(pad='VALID'), RELU, ('gap',), ('dense', SQ2, 0.)]),
+                                 (3, 28, 28, 1), None, ('nngp', 'ntk')),
 }
 
 

@@ -375,6 +375,54 @@ def test_embedded_sizes_fused_path_vs_oracle(nt, shape):
   nt.config.update('enable_x64', False)
 
 
+def test_valid_convs_run_on_the_diagonal_and_stage_kernels(nt):
+  """3x3 / 1 / VALID convs: pool-free Flatten nets on the diagonal-column kernels, pooled / GlobalAvgPool
+  nets on the stage kernels (the SAME stencil everywhere, epilogues restricted to the shrinking box), against the oracle
+  and the per-op path; a pool behind an odd number of VALID convs is not box-aligned and stays on the per-op path."""
+  from oracle import ntk_oracle as O
+  V = lambda **kw: cases.conv(pad='VALID', **kw)
+  nets = [
+      # (spec, shapes, expected path)
+      (('serial', [V(W=1.3, b=0.1), cases.RELU, V(), ('abrelu', 0.1, 1., False), V(W=1.1, b=0.05), cases.RELU,
+                   ('flatten',), ('dense', 1., 0.1)]), [(12, 12, 3), (28, 28, 1), (9, 9, 2)], 'diag'),
+      (('serial', [V(W=1.3, b=0.1), cases.RELU, V(), cases.RELU, cases.pool(), V(W=1.1, b=0.2), cases.RELU, V(), cases.RELU,
+                   ('gap',), ('dense', 1.2, 0.1)]), [(32, 32, 3), (28, 28, 1), (30, 26, 3)], 'fused'),
+      # four layers: two chunks with a STORE boundary in between (box origin 3 entering the second chunk)
+      (('serial', [V(W=1.2, b=0.1), cases.RELU] + [V(), cases.RELU] * 3 + [('gap',), ('dense', 1., 0.)]),
+       [(16, 16, 3), (20, 14, 1)], 'fused'),
+      # tail pools + Flatten at 1x1: 8 -> 6 -> 4 -pool-> 2 -pool-> 1
+      (('serial', [V(b=0.1), cases.RELU, V(), cases.RELU, cases.pool(), cases.pool(), ('flatten',), ('dense', 1., 0.1)]),
+       [(8, 8, 3)], 'fused'),
+      # pool behind three VALID convs: origin 3 is odd
+      (('serial', [V(), cases.RELU] * 3 + [cases.pool(), V(), cases.RELU, ('gap',), ('dense', 1., 0.)]), [(16, 16, 3)],
+       'generic'),
+  ]
+  for spec, shapes, path in nets:
+    _, _, kernel_fn = cases.build(spec, nt.stax)
+    low = nt.stax._lowered(nt.stax._strip(kernel_fn._spec), False, False, True)
+    for shape in shapes:
+      assert low.program.path(*shape) == path, (shape, low.program.path(*shape), path)
+      x1 = np.random.default_rng(51).standard_normal((3,) + shape).astype(np.float32)
+      x2 = np.random.default_rng(52).standard_normal((2,) + shape).astype(np.float32)
+      ref = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'))
+      sref = O.kernel_fn(spec, x1, None, ('nngp', 'ntk'))
+      for x64 in (False, True):
+        nt.config.update('enable_x64', x64)
+        out = kernel_fn(x1, x2, ('nngp', 'ntk'))
+        np.testing.assert_allclose(out.nngp, ref[0], rtol=RTOL[x64], err_msg=f'{path} {shape}')
+        np.testing.assert_allclose(out.ntk, ref[1], rtol=RTOL[x64], err_msg=f'{path} {shape}')
+        np.testing.assert_allclose(kernel_fn(x1, x2, 'nngp'), ref[0], rtol=RTOL[x64])
+        sym = kernel_fn(x1, None, ('nngp', 'ntk'))
+        if path == 'generic':   # full square, pair (j, i) sums the transposed tensor in another order: no exact symmetry
+          off = ~np.eye(3, dtype=bool)
+          np.testing.assert_allclose(sym.ntk[off], sref[1][off], rtol=RTOL[x64])
+          np.testing.assert_allclose(np.diag(sym.ntk), np.diag(sref[1]), rtol=RTOL_DUP[x64])
+          continue
+        _check_sym(sym.nngp, sref[0], x64)
+        _check_sym(sym.ntk, sref[1], x64)
+  nt.config.update('enable_x64', False)
+
+
 def test_sum_pools_on_the_fused_kernels(nt):
   """SumPool / GlobalSumPool (linear.py:1503, 1674) are epilogue scales of the fused kernels."""
   from oracle import ntk_oracle as O
