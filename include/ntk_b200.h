@@ -272,6 +272,23 @@ int ntk_matmul_f64(ntk_context_t* ctx, int32_t dtype_a, const void* a_dev, int32
 const double* ntk_chol_factor_ptr(const ntk_chol_t* f);
 void ntk_chol_destroy(ntk_chol_t* f);
 
+/* Finite training times work in the eigenbasis of the regularised train-train matrix (`_get_fns_in_eigenbasis`,
+ * `_src/predict.py:1243-1290`: `np.linalg.eigh`).  `ntk_eigh_compute` widens a symmetric [n, n] device matrix of `dtype`
+ * to float64, adds diag_reg * (absolute ? 1 : trace(K) / n) to the diagonal and diagonalises it on the device with a
+ * parallel cyclic Jacobi method (one pass over the matrix per round of n / 2 disjoint rotations); it stops when the
+ * off-diagonal Frobenius mass is <= tol * ||A||_F (tol <= 0: 1e-15) or after max_sweeps (<= 0: 40) sweeps.
+ * Eigenvalues ascending (NumPy order); V is [n, n] float64 row-major with eigenvector k in COLUMN k, Vt its transpose;
+ * both stay on the device for `ntk_matmul_f64`.  Synchronises the context stream once per sweep. */
+typedef struct ntk_eigh ntk_eigh_t;
+int ntk_eigh_compute(ntk_context_t* ctx, int32_t dtype, const void* k_dev, int32_t n, int64_t ld, double diag_reg,
+                     int32_t absolute, int32_t max_sweeps, double tol, ntk_eigh_t** out);
+int ntk_eigh_info(const ntk_eigh_t* e, int32_t* sweeps, double* off_over_norm);
+int ntk_eigh_values(const ntk_eigh_t* e, double* w_host);        /* n doubles, host */
+const double* ntk_eigh_values_ptr(const ntk_eigh_t* e);          /* n doubles, device */
+const double* ntk_eigh_vectors_ptr(const ntk_eigh_t* e);         /* V  [n, n], device */
+const double* ntk_eigh_vectors_t_ptr(const ntk_eigh_t* e);       /* V^T [n, n], device */
+void ntk_eigh_destroy(ntk_eigh_t* e);
+
 /* ---- device memory helpers (so a host language needs no CUDA binding) ---- */
 int ntk_device_malloc(int32_t device, size_t bytes, void** ptr);
 int ntk_device_free(int32_t device, void* ptr);

@@ -39,7 +39,9 @@ EXPORTED_SYMBOLS = (
     'ntk_host_free', 'ntk_event_create', 'ntk_event_record', 'ntk_event_elapsed_ms', 'ntk_event_destroy',
     'ntk_stream_create', 'ntk_stream_synchronize', 'ntk_stream_query', 'ntk_stream_destroy',
     'ntk_chol_factor', 'ntk_chol_info', 'ntk_chol_solve', 'ntk_matmul_f64', 'ntk_chol_factor_ptr',
-    'ntk_chol_destroy')
+    'ntk_chol_destroy',
+    'ntk_eigh_compute', 'ntk_eigh_info', 'ntk_eigh_values', 'ntk_eigh_values_ptr', 'ntk_eigh_vectors_ptr',
+    'ntk_eigh_vectors_t_ptr', 'ntk_eigh_destroy')
 
 
 class NtkOp(ctypes.Structure):
@@ -160,6 +162,14 @@ def load():
     lib.ntk_chol_factor_ptr.restype = vp
     lib.ntk_chol_destroy.argtypes = [vp]
     lib.ntk_chol_destroy.restype = None
+    lib.ntk_eigh_compute.argtypes = [vp, i32, vp, i32, i64, ctypes.c_double, i32, i32, ctypes.c_double, P(vp)]
+    lib.ntk_eigh_info.argtypes = [vp, P(i32), P(ctypes.c_double)]
+    lib.ntk_eigh_values.argtypes = [vp, vp]
+    for f in (lib.ntk_eigh_values_ptr, lib.ntk_eigh_vectors_ptr, lib.ntk_eigh_vectors_t_ptr):
+      f.argtypes = [vp]
+      f.restype = vp
+    lib.ntk_eigh_destroy.argtypes = [vp]
+    lib.ntk_eigh_destroy.restype = None
     _lib = lib
     return lib
 
@@ -642,6 +652,76 @@ class DeviceCholesky:
   def close(self):
     if self._h:
       self._lib.ntk_chol_destroy(self._h)
+      self._h = ctypes.c_void_p()
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
+
+
+class DeviceEigh:
+  """Eigendecomposition of a regularised device-resident symmetric matrix (`ntk_eigh_*`, parallel Jacobi in float64 on
+  the GPU that holds K): `w` ascending on the host, V / V^T stay in HBM.  `project(x)` = V^T x and `expand(z)` = V z
+  take / return host matrices [n, k]; `expand_through(a_ptr, ...)` = A (V z) for a device matrix A (K_test_train)."""
+
+  def __init__(self, ctx, dtype, k_ptr, n, ld, diag_reg=0., absolute=False, max_sweeps=0, tol=0.):
+    self._lib, self.ctx, self.n = load(), ctx, int(n)
+    self._h = ctypes.c_void_p()
+    with ctx.lock:
+      check(self._lib.ntk_eigh_compute(ctx.handle, dtype_code(dtype), ctypes.c_void_p(k_ptr), n, ld, float(diag_reg),
+                                       int(bool(absolute)), int(max_sweeps), float(tol), ctypes.byref(self._h)))
+    sweeps, off = ctypes.c_int32(), ctypes.c_double()
+    check(self._lib.ntk_eigh_info(self._h, ctypes.byref(sweeps), ctypes.byref(off)))
+    self.sweeps, self.off_over_norm = sweeps.value, off.value
+    self.w = np.empty(self.n, np.float64)
+    check(self._lib.ntk_eigh_values(self._h, self.w.ctypes.data_as(ctypes.c_void_p)))
+
+  def _mm(self, a_dtype, a_ptr, m, k, lda, x):
+    x2 = np.ascontiguousarray(np.asarray(x, np.float64).reshape(k, -1))
+    nrhs = x2.shape[1]
+    dx, do = self.ctx.malloc(x2.nbytes), self.ctx.malloc(m * nrhs * 8)
+    try:
+      self.ctx.h2d(dx, x2)
+      with self.ctx.lock:
+        check(self._lib.ntk_matmul_f64(self.ctx.handle, dtype_code(a_dtype), ctypes.c_void_p(a_ptr), m, k, lda,
+                                       ctypes.c_void_p(dx), nrhs, nrhs, ctypes.c_void_p(do), nrhs))
+      return self.ctx.d2h(np.empty((m, nrhs), np.float64), do)
+    finally:
+      self.ctx.free(dx)
+      self.ctx.free(do)
+
+  def project(self, x):
+    return self._mm(np.float64, self._lib.ntk_eigh_vectors_t_ptr(self._h), self.n, self.n, self.n, x)
+
+  def expand(self, z):
+    return self._mm(np.float64, self._lib.ntk_eigh_vectors_ptr(self._h), self.n, self.n, self.n, z)
+
+  def expand_through(self, a_dtype, a_ptr, m, lda, z):
+    """A (V z) with A [m, n] on the device, z [n, k] on the host -> host [m, k]; V z never leaves the device."""
+    z2 = np.ascontiguousarray(np.asarray(z, np.float64).reshape(self.n, -1))
+    k = z2.shape[1]
+    dz, du, do = self.ctx.malloc(z2.nbytes), self.ctx.malloc(z2.nbytes), self.ctx.malloc(m * k * 8)
+    try:
+      self.ctx.h2d(dz, z2)
+      with self.ctx.lock:
+        check(self._lib.ntk_matmul_f64(self.ctx.handle, NTK_F64, ctypes.c_void_p(self._lib.ntk_eigh_vectors_ptr(self._h)),
+                                       self.n, self.n, self.n, ctypes.c_void_p(dz), k, k, ctypes.c_void_p(du), k))
+        check(self._lib.ntk_matmul_f64(self.ctx.handle, dtype_code(a_dtype), ctypes.c_void_p(a_ptr), m, self.n, lda,
+                                       ctypes.c_void_p(du), k, k, ctypes.c_void_p(do), k))
+      return self.ctx.d2h(np.empty((m, k), np.float64), do)
+    finally:
+      for d in (dz, du, do):
+        self.ctx.free(d)
+
+  def vectors(self):
+    """V as a host array (tests)."""
+    return self.ctx.d2h(np.empty((self.n, self.n), np.float64), self._lib.ntk_eigh_vectors_ptr(self._h))
+
+  def close(self):
+    if self._h:
+      self._lib.ntk_eigh_destroy(self._h)
       self._h = ctypes.c_void_p()
 
   def __del__(self):

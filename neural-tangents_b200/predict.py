@@ -7,8 +7,9 @@
 The Gram matrices come from `kernel_fn` (libntk_b200.so on the GPU).  `gradient_descent_mse_ensemble(t=None)`
 means -- the common case, `K_td (K_dd + reg I)^-1 y` -- never leave the GPU: the train-train Gram stays in HBM,
 is factorised there in float64 (`ntk_chol_factor`: blocked Cholesky on the fp64 tensor cores), and only the
-[n_test, n_out] predictions are copied back (`_DeviceMeans`).  Posterior covariances and finite times use host
-float64 linear algebra (Cholesky / one symmetric eigendecomposition), as the reference does with `jax.scipy.linalg`.
+[n_test, n_out] predictions are copied back (`_DeviceMeans`).  Finite-time means can stay on the device as well
+(`device_solve=True`: `ntk_eigh_*`, parallel Jacobi in float64); by default they, and the posterior covariances, use
+host float64 linear algebra (Cholesky / one symmetric eigendecomposition), as the reference does with `jax.scipy.linalg`.
 """
 import collections
 from typing import Callable, Optional
@@ -158,7 +159,7 @@ class _DeviceMeans:
   def __init__(self, kernel_fn, x_train, y, diag_reg, absolute):
     self.kernel_fn, self.x_train, self.y = kernel_fn, x_train, y
     self.diag_reg, self.absolute = diag_reg, absolute
-    self.chol, self.alpha = {}, {}
+    self.chol, self.alpha, self.eig = {}, {}, {}
 
   def _factor(self, name):
     from . import _lib, stax
@@ -182,6 +183,41 @@ class _DeviceMeans:
       k_td.free()
 
 
+  def _eigh(self, name):
+    """Eigenbasis of the regularised train-train matrix, computed where the Gram kernels left it (`ntk_eigh_*`)."""
+    from . import _lib, stax
+    if name not in self.eig:
+      k = stax._gram_on_device(self.kernel_fn, self.x_train, None, (name,))[name]
+      try:
+        self.eig[name] = _lib.DeviceEigh(k.ctx, k.dtype, k.ptr, k.shape[0], k.shape[1], self.diag_reg, self.absolute)
+      finally:
+        k.free()
+    return self.eig[name]
+
+  def mean_t(self, name, x_test, ts, norm):
+    """Finite-time means (`_src/predict.py:944-1005`): train set V (1 - e^{-lambda t / |y|}) V^T y, test set
+    K_td V ((1 - e^{-lambda t / |y|}) / |lambda|) V^T y for every t in `ts` ([T], already times the learning rate).
+    The [n, n] matrices (Gram, V) never leave the device; [n, T * out] panels do."""
+    from . import stax
+    e = self._eigh(name)
+    n = e.n
+    lam = np.maximum(e.w, 0.)
+    coef = -np.expm1(-np.outer(ts, lam) / norm)                    # [T, n]
+    if x_test is not None:
+      coef = coef / np.abs(e.w)[None, :]
+    vty = e.project(self.y)                                         # [n, out]
+    z = np.moveaxis(coef[:, :, None] * vty[None], 0, 1).reshape(n, -1)   # [n, T * out]
+    if x_test is None:
+      out = e.expand(z)
+    else:
+      k_td = stax._gram_on_device(self.kernel_fn, x_test, self.x_train, (name,))[name]
+      try:
+        out = e.expand_through(k_td.dtype, k_td.ptr, k_td.shape[0], k_td.shape[1], z)
+      finally:
+        k_td.free()
+    return np.moveaxis(out.reshape(out.shape[0], len(ts), -1), 1, 0)    # [T, m, out]
+
+
 def gradient_descent_mse_ensemble(kernel_fn, x_train, y_train, learning_rate: float = 1., diag_reg: float = 0.,
                                   diag_reg_absolute_scale: bool = False, trace_axes=(-1,), device_solve=None,
                                   **kernel_fn_train_train_kwargs) -> Callable:
@@ -195,8 +231,9 @@ def gradient_descent_mse_ensemble(kernel_fn, x_train, y_train, learning_rate: fl
   y = _check_targets(y_train, trace_axes)
   norm = float(y.size)
   cache, eig, inf = {}, {}, {}
-  # `device_solve`: None = on the GPU whenever `kernel_fn` is a B200 kernel_fn called without extra kwargs,
-  # False = host SciPy (the round-1 path), True = require the device path.
+  # `device_solve`: None = infinite-time means on the GPU (Cholesky) whenever `kernel_fn` is a B200 kernel_fn called
+  # without extra kwargs, finite times on the host; False = host SciPy everywhere (the round-1 path); True = require
+  # the device path, finite-time means included (Jacobi eigh on the device).
   native = hasattr(kernel_fn, '_spec') and not kernel_fn_train_train_kwargs and isinstance(x_train, np.ndarray)
   if device_solve and not native:
     raise ValueError('device_solve=True needs a kernel_fn built by neural_tangents_b200.stax and no extra kwargs')
@@ -239,6 +276,16 @@ def gradient_descent_mse_ensemble(kernel_fn, x_train, y_train, learning_rate: fl
     if dev is not None and t is None and not compute_cov and not kernel_fn_test_test_kwargs:
       # infinite time, means only: Gram -> Cholesky -> K_td alpha, all in HBM
       vals = [y.copy() if x_test is None else dev.mean(g, x_test) for g in names]
+      return _pack(get, names, vals)
+    if dev is not None and device_solve and t is not None and not compute_cov and not kernel_fn_test_test_kwargs:
+      # finite times, means only, on request (device_solve=True): Gram -> Jacobi eigh -> V f(lambda, t) V^T y (-> K_td ...)
+      # with every [n, n] matrix in HBM.  Not the default: the HBM-bound Jacobi sweeps (5.3 TB/s effective) take 2x the
+      # time of 16-core LAPACK `dsyevd` on a host copy (profiles/eigh_r02.json), and the copy is only n^2 * 4 bytes.
+      t_arr = np.asarray(t, dtype=np.float64) * learning_rate
+      vals = []
+      for g in names:
+        m = dev.mean_t(g, x_test, t_arr.reshape(-1), norm)
+        vals.append(m.reshape(t_arr.shape + m.shape[1:]))
       return _pack(get, names, vals)
     k_dd = k_train_train(dep)
     kw = dict(kernel_fn_train_train_kwargs)

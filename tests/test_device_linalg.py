@@ -96,3 +96,65 @@ def test_ensemble_means_on_device_equal_host_solve(nt, x64):
     np.testing.assert_allclose(small(t=None, x_test=x_test[:3], get='ntk'), k_td @ np.linalg.solve(A, ys), rtol=1e-7,
                                atol=1e-9)
   nt.config.update('enable_x64', False)
+
+
+@pytest.mark.parametrize('n', [1, 2, 5, 64, 129, 500])
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_jacobi_eigh_matches_numpy(nt, n, dtype):
+  """`ntk_eigh_*` (parallel cyclic Jacobi in float64 on the device, eigh.cu) against `np.linalg.eigh`: eigenvalues,
+  orthogonality, reconstruction and the V^T x / V z / A V z products `predict` uses, incl. odd n (a bye per round)."""
+  from neural_tangents_b200 import _lib
+  ctx = _lib.get_context()
+  a = _spd(n, 100 + n, cond=1e6).astype(dtype)
+  a64 = a.astype(np.float64)
+  d = ctx.malloc(a.nbytes)
+  ctx.h2d(d, a)
+  for diag_reg, absolute in ((0., False), (1e-3, False), (0.25, True)):
+    ref = a64 + np.eye(n) * (diag_reg if absolute else diag_reg * np.trace(a64) / n)
+    w_ref = np.linalg.eigvalsh(ref)
+    e = _lib.DeviceEigh(ctx, dtype, d, n, n, diag_reg, absolute)
+    scale = np.abs(w_ref).max()
+    np.testing.assert_allclose(e.w, w_ref, rtol=0, atol=1e-12 * scale)
+    assert np.all(np.diff(e.w) >= 0)
+    v = e.vectors()
+    np.testing.assert_allclose(v.T @ v, np.eye(n), atol=1e-12)
+    np.testing.assert_allclose((v * e.w) @ v.T, ref, atol=1e-11 * scale)
+    x = np.random.default_rng(n).standard_normal((n, 7))
+    np.testing.assert_allclose(e.project(x), v.T @ x, atol=1e-12 * np.abs(x).max() * max(n, 1) ** 0.5)
+    np.testing.assert_allclose(e.expand(x), v @ x, atol=1e-12 * np.abs(x).max() * max(n, 1) ** 0.5)
+    ktd = np.random.default_rng(3).standard_normal((11, n)).astype(dtype)
+    dk = ctx.malloc(ktd.nbytes)
+    ctx.h2d(dk, ktd)
+    np.testing.assert_allclose(e.expand_through(dtype, dk, 11, n, x), ktd.astype(np.float64) @ (v @ x), rtol=1e-10,
+                               atol=1e-11 * max(n, 1))
+    ctx.free(dk)
+    assert e.sweeps <= 20 and e.off_over_norm <= 1e-14
+    e.close()
+  ctx.free(d)
+
+
+@pytest.mark.parametrize('x64', [False, True])
+def test_ensemble_finite_time_means_on_device_equal_host_eigh(nt, x64):
+  """Finite-t means: Gram -> Jacobi eigh -> V f(lambda, t) V^T y -> K_td ... with every [n, n] matrix in HBM
+  (device_solve) == the host `np.linalg.eigh` path on copies of the same Grams; t -> infinity meets the Cholesky means."""
+  nt.config.update('enable_x64', x64)
+  spec = cases.myrtle(5, 'gap')
+  _, _, kernel_fn = cases.build(spec, nt.stax)
+  rng = np.random.default_rng(8)
+  x_train = rng.standard_normal((48, 32, 32, 3)).astype(np.float32)
+  x_test = rng.standard_normal((7, 32, 32, 3)).astype(np.float32)
+  y = rng.standard_normal((48, 3))
+  dev = nt.predict.gradient_descent_mse_ensemble(kernel_fn, x_train, y, diag_reg=1e-4, device_solve=True)
+  host = nt.predict.gradient_descent_mse_ensemble(kernel_fn, x_train, y, diag_reg=1e-4, device_solve=False)
+  ts = np.array([[0., 1.], [10., 1e3]])
+  tol = 1e-9 if x64 else 2e-4
+  for xt in (x_test, None):
+    a = dev(t=ts, x_test=xt, get=('nngp', 'ntk'))
+    b = host(t=ts, x_test=xt, get=('nngp', 'ntk'))
+    assert a.ntk.shape == b.ntk.shape == (2, 2, 48 if xt is None else 7, 3)
+    np.testing.assert_allclose(a.nngp, b.nngp, rtol=tol, atol=tol)
+    np.testing.assert_allclose(a.ntk, b.ntk, rtol=tol, atol=tol)
+    np.testing.assert_allclose(dev(t=5., x_test=xt, get='ntk'), host(t=5., x_test=xt, get='ntk'), rtol=tol, atol=tol)
+  inf = dev(t=None, x_test=x_test, get='ntk')
+  np.testing.assert_allclose(dev(t=1e12, x_test=x_test, get='ntk'), inf, rtol=1e-6 if x64 else 2e-3, atol=1e-6 if x64 else 2e-3)
+  nt.config.update('enable_x64', False)
