@@ -54,6 +54,9 @@ inline int ensure_dynamic_smem(const void* func, size_t bytes) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return fail(NTK_ECUDA, "cudaGetDevice -> %s", cudaGetErrorString(e));
+  // never below the 48 KB every launch may use without the attribute: a small first request must not make a later
+  // unconfigured launch of the same kernel (<= 48 KB) fail with "invalid argument"
+  if (bytes < (size_t)48 * 1024) bytes = (size_t)48 * 1024;
   std::lock_guard<std::mutex> lock(mu);
   auto it = done.find({dev, func});
   if (it != done.end() && it->second >= bytes) return NTK_OK;

@@ -80,12 +80,12 @@ struct ResGeom {
 
 // ERF: the network contains Erf activations (a runtime branch per activation row picks the closed
 // form); pure-ABRelu networks run the ERF = false instantiation, which carries no Erf code.
-template <typename T>
+// fp32: 8 w per thread for ABRelu networks, 4 for networks with Erf (measured on B200 with the input ring, WideResNet
+// block 96 x 96: Relu 436.6 k entries/s at 8 w vs 376.1 k at 4 w; Erf 320.6 k at 8 w vs 349.3 k at 4 w -- the Erf rows carry
+// more live values per element, at 8 w the kernel sits at 255 registers).
+template <typename T, bool ERF>
 struct ResWpt {
-#ifndef NTK_RES_WPT_F32
-#define NTK_RES_WPT_F32 8
-#endif
-  static constexpr int value = sizeof(T) == 8 ? 4 : NTK_RES_WPT_F32;
+  static constexpr int value = sizeof(T) == 8 ? 4 : (ERF ? 4 : 8);
 };
 
 // Input rows of a LOADing kernel travel through a per-thread ring in shared memory, filled with cp.async one marched row
@@ -100,10 +100,10 @@ __device__ __forceinline__ void res_cp_async(void* dst_smem, const void* src) {
 }
 
 template <typename T, int S, int IN, bool NTK, int CIN, bool ERF>
-__global__ void __launch_bounds__((ResGeom<S, ResWpt<T>::value>::NT),
-                                  (sizeof(T) == 4 && ResWpt<T>::value == 4 ? 512 / ResGeom<S, ResWpt<T>::value>::NT : 1))
+__global__ void __launch_bounds__((ResGeom<S, ResWpt<T, ERF>::value>::NT),
+                                  (sizeof(T) == 4 && ResWpt<T, ERF>::value == 4 ? 512 / ResGeom<S, ResWpt<T, ERF>::value>::NT : 1))
 k_res(const ResArgs<T> a) {
-  using G = ResGeom<S, ResWpt<T>::value>;
+  using G = ResGeom<S, ResWpt<T, ERF>::value>;
   using V2 = typename Vec2<T>::type;
   constexpr int WPT = G::WPT, TPP = G::TPP, LPG = G::LPG, NWB = G::NWB, LW = G::LW;
 
@@ -748,14 +748,14 @@ int launch_res(cudaStream_t stream, int64_t* launches, int S, bool from_x, const
     return NTK_OK;
   };
   auto smem_for = [&](int s, bool fx) {
-    const int tpp = s * s / ResWpt<T>::value, nt = tpp < 128 ? 128 : tpp;
-    const size_t per = (fx ? (size_t)s * s * 3 + (size_t)s * s * 4 : (size_t)kResRing * 2 * ResWpt<T>::value * tpp) +
+    const int tpp = s * s / ResWpt<T, ERF>::value, nt = tpp < 128 ? 128 : tpp;
+    const size_t per = (fx ? (size_t)s * s * 3 + (size_t)s * s * 4 : (size_t)kResRing * 2 * ResWpt<T, ERF>::value * tpp) +
                        2 * (size_t)(2 * s * s * 2);
     return per * (nt / tpp) * sizeof(T);
   };
 #define NTK_RES_CASE(SS)                                                                              \
   if (S == SS) {                                                                                      \
-    using G = ResGeom<SS, ResWpt<T>::value>;                                                          \
+    using G = ResGeom<SS, ResWpt<T, ERF>::value>;                                                          \
     if (from_x) return go(k_res<T, SS, IN_FROM_X, NTK, 3, ERF>, G::NT, G::GROUPS, smem_for(SS, true)); \
     return go(k_res<T, SS, IN_LOAD, NTK, 1, ERF>, G::NT, G::GROUPS, smem_for(SS, false));             \
   }
@@ -858,6 +858,7 @@ int res_gram(const ResPlan& plan, Arena& arena, cudaStream_t stream, int64_t* la
   NTK_CUDA(cudaMemcpyAsync(off_d, act_off.data(), act_off.size() * sizeof(long long), cudaMemcpyHostToDevice, stream));
   NTK_CUDA(cudaStreamSynchronize(stream));  // qp / act_off live on the host stack
   const T in_scale = (T)(plan.w0 / 9.0 / (double)C);
+  NTK_TRY(ensure_dynamic_smem((const void*)k_qprog<T>, (size_t)4 * S0 * S0 * sizeof(T)));
   for (int set = 0; set < (symmetric ? 1 : 2); ++set) {
     (*launches)++;
     k_qprog<T><<<set == 0 ? n1 : n2, 256, (size_t)4 * S0 * S0 * sizeof(T), stream>>>(
