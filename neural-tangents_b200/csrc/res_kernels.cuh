@@ -427,7 +427,7 @@ k_res(const ResArgs<T> a) {
 #pragma unroll
         for (int i = 0; i < WPT; ++i) {
           a.outK[base + (long long)i * ncw] = YK[i];
-          if (NTK) a.outT[base + (long long)i * ncw] = YT[i];
+          if (NTK && a.outT) a.outT[base + (long long)i * ncw] = YT[i];  // outT == nullptr: the ntk equals the nngp (stem)
         }
       } else if (a.epi == REPI_SUB) {
         // stride-2 SAME conv == stride-1 box filter sampled at odd (h, w); output at S/2 keeps the
@@ -941,7 +941,9 @@ int res_gram(const ResPlan& plan, Arena& arena, cudaStream_t stream, int64_t* la
         a.epi = REPI_STORE;
         a.lp[0].bias = (T)plan.b0;
         a.outK = buf[cur];
-        a.outT = want_ntk ? buf[cur] + (size_t)P * tsize(S, cws) : nullptr;
+        // the ntk behind the first conv IS the nngp (linear.py:1396-1398 with ntk = 0): it is stored once and the first
+        // block reads both of its inputs from the same tensor (half the stem's writes, half the first block's DRAM reads)
+        a.outT = nullptr;
         NTK_TRY(run(S, true, a));
       }
       int act = 0;
@@ -955,7 +957,7 @@ int res_gram(const ResPlan& plan, Arena& arena, cudaStream_t stream, int64_t* la
           ResArgs<T> a = base_args();
           a.cws = cws;
           a.inK = buf[cur];
-          a.inT = want_ntk ? buf[cur] + (size_t)P * tsize(S, cws) : nullptr;
+          a.inT = want_ntk ? (b == 0 ? buf[cur] : buf[cur] + (size_t)P * tsize(S, cws)) : nullptr;
           a.act_in = 1;
           a.n_units = 2;
           a.side = B.conv_shortcut ? 1 : 0;
@@ -983,7 +985,7 @@ int res_gram(const ResPlan& plan, Arena& arena, cudaStream_t stream, int64_t* la
           ResArgs<T> a = base_args();
           a.cws = cws;
           a.inK = buf[cur];
-          a.inT = want_ntk ? buf[cur] + (size_t)P * tsize(S, cws) : nullptr;
+          a.inT = want_ntk ? (b == 0 ? buf[cur] : buf[cur] + (size_t)P * tsize(S, cws)) : nullptr;
           a.act_in = 1;
           a.n_units = 1;
           a.side = 1;
