@@ -390,6 +390,49 @@ struct Vec2<double> {
 //   src_mode 0: diag0[h,w] = in_scale * sum_c x[h,w,c]^2      (FROM_X stages)
 //   src_mode 1: diag0[h,w] = selfK[n][ch=0][h][w][cw=0]        (sheared self-pair tensor)
 // ---------------------------------------------------------------------------------------
+// Sheared input covariance for inputs whose channel count has no FROM_X instantiation (C not in {1, 3}; round 2):
+//   out[p][ch][h][w][cw] = sum_c (x1[i, h, w, c] * in_scale) * x2[j, (h + ch) % S, (w + cw) % S, c]     (0 outside RH x RW)
+// in the layout the LOADing stage kernels read, with the roundings of the FROM_X kernels and of k_qmaps (requirements.py:
+// 542-553; a duplicate pair reproduces its diagonal bit for bit).  One CTA row per (pair, ch, h); a thread owns (w, cw).
+template <typename T>
+__global__ void k_input_shear(const T* __restrict__ x1, const T* __restrict__ x2, T* __restrict__ out, long long P,
+                              int n2, int self, int tri, int S, int RH, int RW, int C, T in_scale) {
+  const long long nrows = P * S * S;
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const long long p = row / (S * S);
+    const int r = (int)(row - p * (S * S));
+    const int ch = r / S, h = r - ch * S;
+    const int h2 = (h + ch) % S;
+    int si, sj;
+    if (self) {
+      si = sj = (int)p;
+    } else if (tri) {
+      int off;
+      tri_unrank(p, n2, si, off);
+      sj = si + off;
+    } else {
+      si = (int)(p / n2);
+      sj = (int)(p % n2);
+    }
+    const bool row_in = h < RH && h2 < RH;
+    const T* a = x1 + ((long long)si * RH + h) * RW * C;
+    const T* b = x2 + ((long long)sj * RH + h2) * RW * C;
+    T* o = out + row * (long long)(S * S);
+    for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+      const int w = e / S, cw = e - w * S;
+      const int w2 = (w + cw) % S;
+      T v = (T)0;
+      if (row_in && w < RW && w2 < RW) {
+        const T* xa = a + w * C;
+        const T* xb = b + w2 * C;
+        v = mul_rn(mul_rn(xa[0], in_scale), xb[0]);
+        for (int c = 1; c < C; ++c) v = fma_t(mul_rn(xa[c], in_scale), xb[c], v);
+      }
+      o[e] = v;
+    }
+  }
+}
+
 // RH x RW: the real image size (<= S; the image sits in the top-left corner of the S x S map, see StageArgs).
 template <typename T, int S>
 __global__ void k_qmaps(const T* __restrict__ src, int src_mode, int C, T in_scale, int L,
@@ -668,7 +711,9 @@ k_stage(const StageArgs<T> a) {
 
   T gap_k = (T)0, gap_t = (T)0;
   const T* inK = IN == IN_LOAD ? a.inK + p * (long long)NR * S * S + (long long)w0 * S + cw : nullptr;
-  const T* inT = (IN == IN_LOAD && NTK) ? a.inT + p * (long long)NR * S * S + (long long)w0 * S + cw : nullptr;
+  // inT == nullptr on a LOADing ntk stage: the input is the sheared input covariance of k_input_shear (ntk = 0)
+  const bool has_inT = IN == IN_LOAD && NTK && a.inT != nullptr;
+  const T* inT = has_inT ? a.inT + p * (long long)NR * S * S + (long long)w0 * S + cw : nullptr;
 
   // next input row (software prefetch for LOAD)
   T nK[WPT], nT[WPT];
@@ -679,9 +724,14 @@ k_stage(const StageArgs<T> a) {
 #pragma unroll
       for (int i = 0; i < WPT; ++i) nK[i] = __ldg(gk + i * S);
       if (NTK) {
-        const T* gt = inT + (long long)rc * S * S;
+        if (has_inT) {
+          const T* gt = inT + (long long)rc * S * S;
 #pragma unroll
-        for (int i = 0; i < WPT; ++i) nT[i] = __ldg(gt + i * S);
+          for (int i = 0; i < WPT; ++i) nT[i] = __ldg(gt + i * S);
+        } else {
+#pragma unroll
+          for (int i = 0; i < WPT; ++i) nT[i] = (T)0;
+        }
       }
     }
   };
@@ -1123,14 +1173,19 @@ inline int fused_shear_size(int H, int W) {
 }
 
 // Images that are not S x S RGB run the EMB family of the scalar stage kernels (pure ABRelu stages only).
-inline bool fused_needs_emb(int H, int W, int C) { return !(H == W && (H == 32 || H == 16 || H == 8) && C == 3); }
+// Other channel counts (round 2) go through k_input_shear and LOADing first stages, which exist in every family.
+inline bool fused_needs_prepass(int C) { return C != 1 && C != 3; }
+inline bool fused_needs_emb(int H, int W, int C) {
+  const bool square = H == W && (H == 32 || H == 16 || H == 8);
+  return !(square && C != 1);
+}
 
 template <typename T>
 bool fused_supported(const FusedPlan& plan, int H, int W, int C) {
   if (!plan.ok || H < 1 || W < 1) return false;
   int S = fused_shear_size(H, W);
   if (S == 0) return false;
-  if (C != 3 && C != 1) return false;  // FROM_X stages are instantiated for grey and RGB inputs
+  if (C < 1) return false;  // C = 1, 3: FROM_X stages; any other C: k_input_shear + LOADing first stage
   const bool emb = fused_needs_emb(H, W, C) || plan.valid_convs;  // VALID convs need the box-aware (EMB) epilogues
   FusedBox last{0, H, W};
   std::vector<FusedBox> in_box;
@@ -1404,6 +1459,7 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
                bool full_square = false, bool upper = false) {
   const int S0 = fused_shear_size(H0, W0);
   const bool emb = fused_needs_emb(H0, W0, C) || plan.valid_convs;
+  const bool prepass = fused_needs_prepass(C);  // stage 0 LOADs the sheared input covariance written by k_input_shear
   const size_t xrow = (size_t)H0 * W0 * C;  // elements per input sample
   // `upper` (NTK_FLAG_UPPER_ONLY): x1 holds the same samples as x2[0:n1]; only entries (i, j >= i) are wanted.
   upper = upper && !symmetric && n2 >= n1;
@@ -1464,10 +1520,12 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
         need = std::max(need, (size_t)So * So * So * So);
       }
     }
+    T* bufX = nullptr;  // prepass: sheared self covariance entering stage 0
     if (need > 0) {
       bufA = (T*)arena.alloc(need * chunk * sizeof(T));
       bufB = (T*)arena.alloc(need * chunk * sizeof(T));
-      if (!bufA || !bufB) return fail(NTK_ENOMEM, "workspace too small for the self-pair pipeline");
+      if (prepass) bufX = (T*)arena.alloc((size_t)S0 * S0 * S0 * S0 * chunk * sizeof(T));
+      if (!bufA || !bufB || (prepass && !bufX)) return fail(NTK_ENOMEM, "workspace too small for the self-pair pipeline");
     }
     for (int c0 = 0; c0 < n; c0 += chunk) {
       const int m = std::min(chunk, n - c0);
@@ -1485,6 +1543,13 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
           NTK_TRY(launch_qmaps<T>(stream, launches, S, cur, 1, m, C, (T)1, plan.stages[s].L, lp, qm, RHs[s],
                                   RWs[s]));
         if (s + 1 == n_st) break;  // the last stage's self tensors are never needed
+        if (s == 0 && prepass) {
+          (*launches)++;
+          k_input_shear<T><<<(unsigned)std::min<long long>((long long)m * S * S, (long long)kNumSMs * 64), 256, 0, stream>>>(
+              x + (size_t)c0 * xrow, x + (size_t)c0 * xrow, bufX, m, 1, 1, 0, S, RHs[0], RWs[0], C, in_scale);
+          NTK_CUDA(cudaGetLastError());
+          cur = bufX;
+        }
         // run the stage on the self pairs (nngp only) to get the next boundary
         StageArgs<T> a{};
         a.RH = RHs[s];
@@ -1511,10 +1576,12 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
         for (int l = 0; l < plan.stages[s].L; ++l) a.lp[l] = lp[l];
         if (epi == EPI_POOL)
           NTK_CUDA(cudaMemsetAsync(nxt, 0, (size_t)m * So * So * So * So * sizeof(T), stream));
-        NTK_TRY((launch_stage<T, false>(stream, launches, S, plan.stages[s].L, s == 0, C, epi, a, emb)));
+        NTK_TRY((launch_stage<T, false>(stream, launches, S, plan.stages[s].L, s == 0 && !prepass, prepass ? 3 : C, epi, a,
+                                        emb)));
         cur = nxt;
       }
     }
+    if (bufX) arena.release(bufX);
     if (bufA) arena.release(bufA);
     if (bufB) arena.release(bufB);
   }
@@ -1524,6 +1591,7 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
   size_t max_b = 0, sum2 = 0;
   {
     std::vector<size_t> bsz;
+    if (prepass) bsz.push_back((size_t)S0 * S0 * S0 * S0 * sizeof(T));  // the sheared input covariance (nngp only)
     for (size_t s = 0; s + 1 < n_st; ++s) {
       const int So = plan.stages[s].epi == EPI_POOL ? Ss[s] / 2 : Ss[s];
       bsz.push_back((size_t)So * So * So * So * sizeof(T) * (want_ntk ? 2 : 1));
@@ -1586,6 +1654,14 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
       const int a2 = tri_tile ? n2 - r0 : std::min(t2, n2 - c0);
       const long long P = tri_tile ? tri_prefix(a1, a2) : (long long)a1 * a2;
       T* cur = nullptr;
+      if (prepass) {
+        (*launches)++;
+        k_input_shear<T><<<(unsigned)std::min<long long>(P * S0 * S0, (long long)kNumSMs * 64), 256, 0, stream>>>(
+            x1 + (size_t)r0 * xrow, x2 + (size_t)c0 * xrow, bnd[0], P, a2, 0, tri_tile ? 1 : 0, S0, RHs[0], RWs[0], C,
+            in_scale);
+        NTK_CUDA(cudaGetLastError());
+        cur = bnd[0];
+      }
       for (size_t s = 0; s < n_st; ++s) {
         const int S = Ss[s];
         FLayer<T> lp[kMaxFusedLayers];
@@ -1603,7 +1679,7 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
         const int So = epi == EPI_POOL ? S / 2 : S;
         const size_t in_per = (size_t)S * S * S * S, out_per = (size_t)So * So * So * So;
         a.inK = cur;
-        a.inT = (cur && want_ntk) ? cur + (size_t)P * in_per : nullptr;
+        a.inT = (cur && want_ntk && !(s == 0 && prepass)) ? cur + (size_t)P * in_per : nullptr;  // prepass: ntk = 0
         T* nxt = (cur == bnd[0]) ? bnd[1] : bnd[0];
         if (epi == EPI_GAP) {
           a.outK = resK;
@@ -1621,7 +1697,7 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
               n_erf += plan.stages[s].kind[l] == ACT_ERF;
               n_gen += plan.stages[s].kind[l] >= ACT_GELU;
             }
-            a.zero_out = (!emb && !n_gen && stage_is_packed<T>(S, s == 0 ? C : 3, n_erf, plan.stages[s].L)) ? 1 : 0;
+            a.zero_out = (!emb && !n_gen && stage_is_packed<T>(S, (s == 0 && !prepass) ? C : 3, n_erf, plan.stages[s].L)) ? 1 : 0;
             if (!a.zero_out)
               NTK_CUDA(cudaMemsetAsync(nxt, 0, (size_t)P * out_per * sizeof(T) * (want_ntk ? 2 : 1), stream));
           }
@@ -1643,10 +1719,11 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
           NTK_CUDA(cudaEventCreate(&ev1));
           NTK_CUDA(cudaEventRecord(ev0, stream));
         }
+        const int from_x = (s == 0 && !prepass) ? 1 : 0, cin = prepass ? 3 : C;
         if (want_ntk)
-          NTK_TRY((launch_stage<T, true>(stream, launches, S, plan.stages[s].L, s == 0, C, epi, a, emb)));
+          NTK_TRY((launch_stage<T, true>(stream, launches, S, plan.stages[s].L, from_x, cin, epi, a, emb)));
         else
-          NTK_TRY((launch_stage<T, false>(stream, launches, S, plan.stages[s].L, s == 0, C, epi, a, emb)));
+          NTK_TRY((launch_stage<T, false>(stream, launches, S, plan.stages[s].L, from_x, cin, epi, a, emb)));
         if (timed) {
           NTK_CUDA(cudaEventRecord(ev1, stream));
           prof->pending[s].push_back({ev0, ev1});

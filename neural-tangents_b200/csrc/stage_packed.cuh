@@ -332,7 +332,8 @@ k_stage_p(const StageArgs<float> a) {
 
   float2 gap_k = f2s(0.f), gap_u = f2s(0.f);
   const float* inK = IN == IN_LOAD ? a.inK + p * (long long)NR * S * S + (long long)w0 * S + cw : nullptr;
-  const float* inT = (IN == IN_LOAD && NTK) ? a.inT + p * (long long)NR * S * S + (long long)w0 * S + cw : nullptr;
+  const bool has_inT = IN == IN_LOAD && NTK && a.inT != nullptr;  // nullptr: sheared input covariance, ntk = 0
+  const float* inT = has_inT ? a.inT + p * (long long)NR * S * S + (long long)w0 * S + cw : nullptr;
 
   float nK[WPT], nT[WPT];
   auto fetch = [&](int r) {
@@ -342,9 +343,14 @@ k_stage_p(const StageArgs<float> a) {
 #pragma unroll
       for (int i = 0; i < WPT; ++i) nK[i] = __ldg(gk + i * S);
       if (NTK) {
-        const float* gt = inT + (long long)rc * S * S;
+        if (has_inT) {
+          const float* gt = inT + (long long)rc * S * S;
 #pragma unroll
-        for (int i = 0; i < WPT; ++i) nT[i] = __ldg(gt + i * S);
+          for (int i = 0; i < WPT; ++i) nT[i] = __ldg(gt + i * S);
+        } else {
+#pragma unroll
+          for (int i = 0; i < WPT; ++i) nT[i] = 0.f;
+        }
       }
     }
   };

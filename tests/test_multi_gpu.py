@@ -423,6 +423,37 @@ def test_valid_convs_run_on_the_diagonal_and_stage_kernels(nt):
   nt.config.update('enable_x64', False)
 
 
+@pytest.mark.parametrize('shape', [(32, 32, 4), (16, 16, 2), (28, 28, 2), (20, 24, 5)])
+def test_any_channel_count_on_the_fused_path(nt, shape):
+  """Channel counts without a FROM_X instantiation (C not in {1, 3}): `k_input_shear` writes the sheared input covariance and
+  the first stage LOADs it (ntk = 0) -- packed / scalar kernels on 32 / 16 px, the EMB family on other sizes -- against the
+  oracle; duplicate pairs keep their exact diagonal (same roundings as k_qmaps)."""
+  from oracle import ntk_oracle as O
+  H, W, C = shape
+  spec = cases.myrtle(5, 'gap') if min(H, W) >= 20 else ('serial', [cases.conv(W=1.3, b=0.1), cases.RELU, cases.conv(), cases.RELU,
+                                                                    cases.pool(), cases.conv(), cases.RELU, ('gap',),
+                                                                    ('dense', 1.1, 0.1)])
+  _, _, kernel_fn = cases.build(spec, nt.stax)
+  low = nt.stax._lowered(nt.stax._strip(kernel_fn._spec), False, False, True)
+  assert low.program.path(H, W, C) == 'fused'
+  x1 = np.random.default_rng(61).standard_normal((3, H, W, C)).astype(np.float32)
+  x2 = np.random.default_rng(62).standard_normal((2, H, W, C)).astype(np.float32)
+  ref = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'))
+  sref = O.kernel_fn(spec, x1, None, ('nngp', 'ntk'))
+  for x64 in (False, True):
+    nt.config.update('enable_x64', x64)
+    out = kernel_fn(x1, x2, ('nngp', 'ntk'))
+    np.testing.assert_allclose(out.nngp, ref[0], rtol=RTOL[x64])
+    np.testing.assert_allclose(out.ntk, ref[1], rtol=RTOL[x64])
+    np.testing.assert_allclose(kernel_fn(x1, x2, 'nngp'), ref[0], rtol=RTOL[x64])
+    sym = kernel_fn(x1, None, ('nngp', 'ntk'))
+    _check_sym(sym.nngp, sref[0], x64)
+    _check_sym(sym.ntk, sref[1], x64)
+    dup = kernel_fn(x1, x1.copy(), 'ntk')
+    np.testing.assert_array_equal(np.diag(dup), np.diag(sym.ntk))
+  nt.config.update('enable_x64', False)
+
+
 def test_sum_pools_on_the_fused_kernels(nt):
   """SumPool / GlobalSumPool (linear.py:1503, 1674) are epilogue scales of the fused kernels."""
   from oracle import ntk_oracle as O
