@@ -394,14 +394,23 @@ struct Vec2<double> {
 //   out[p][ch][h][w][cw] = sum_c (x1[i, h, w, c] * in_scale) * x2[j, (h + ch) % S, (w + cw) % S, c]     (0 outside RH x RW)
 // in the layout the LOADing stage kernels read, with the roundings of the FROM_X kernels and of k_qmaps (requirements.py:
 // 542-553; a duplicate pair reproduces its diagonal bit for bit).  One CTA row per (pair, ch, h); a thread owns (w, cw).
-template <typename T>
+// One WARP per row (pair, ch, h): it stages the two image rows in its own slice of shared memory and writes the S x S
+// (w, cw) plane (S = 32: one w per iteration, lane = cw, 128-byte stores); the warps of a CTA are independent, so the
+// short global reads of one row hide behind the stores of the others (the first version -- one CTA per row, two CTA
+// barriers per 4 KB of output -- ran at 1.7 TB/s).
+template <typename T, int S>
 __global__ void k_input_shear(const T* __restrict__ x1, const T* __restrict__ x2, T* __restrict__ out, long long P,
-                              int n2, int self, int tri, int S, int RH, int RW, int C, T in_scale) {
+                              int n2, int self, int tri, int RH, int RW, int C, T in_scale) {
+  extern __shared__ __align__(16) unsigned char shear_raw[];
+  const int CP = C | 1;  // odd row pitch: the w' = (w + cw) % S gather is bank-conflict free
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  T* xa = reinterpret_cast<T*>(shear_raw) + (size_t)warp * 2 * S * CP;  // [S][CP]  x1 row h, pre-scaled, zero outside
+  T* xb = xa + S * CP;                                                  // [S][CP]  x2 row h'
   const long long nrows = P * S * S;
-  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+  for (long long row = (long long)blockIdx.x * nwarps + warp; row < nrows; row += (long long)gridDim.x * nwarps) {
     const long long p = row / (S * S);
     const int r = (int)(row - p * (S * S));
-    const int ch = r / S, h = r - ch * S;
+    const int ch = r / S, h = r % S;
     const int h2 = (h + ch) % S;
     int si, sj;
     if (self) {
@@ -414,23 +423,49 @@ __global__ void k_input_shear(const T* __restrict__ x1, const T* __restrict__ x2
       si = (int)(p / n2);
       sj = (int)(p % n2);
     }
-    const bool row_in = h < RH && h2 < RH;
     const T* a = x1 + ((long long)si * RH + h) * RW * C;
     const T* b = x2 + ((long long)sj * RH + h2) * RW * C;
+    __syncwarp();
+    for (int e = lane; e < S * C; e += 32) {
+      const int w = e / C, c = e - w * C;
+      xa[w * CP + c] = (h < RH && w < RW) ? mul_rn(a[e], in_scale) : (T)0;
+      xb[w * CP + c] = (h2 < RH && w < RW) ? b[e] : (T)0;
+    }
+    __syncwarp();
     T* o = out + row * (long long)(S * S);
-    for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
-      const int w = e / S, cw = e - w * S;
-      const int w2 = (w + cw) % S;
-      T v = (T)0;
-      if (row_in && w < RW && w2 < RW) {
-        const T* xa = a + w * C;
-        const T* xb = b + w2 * C;
-        v = mul_rn(mul_rn(xa[0], in_scale), xb[0]);
-        for (int c = 1; c < C; ++c) v = fma_t(mul_rn(xa[c], in_scale), xb[c], v);
-      }
+    for (int e = lane; e < S * S; e += 32) {
+      const int w = e / S, cw = e % S;
+      const T* pa = xa + w * CP;
+      const T* pb = xb + ((w + cw) % S) * CP;
+      T v = mul_rn(pa[0], pb[0]);
+      for (int c = 1; c < C; ++c) v = fma_t(pa[c], pb[c], v);
       o[e] = v;
     }
   }
+}
+
+template <typename T>
+int launch_input_shear(cudaStream_t stream, int64_t* launches, int S, const T* x1, const T* x2, T* out, long long P, int n2,
+                       int self, int tri, int RH, int RW, int C, T in_scale) {
+  (*launches)++;
+  const size_t per_warp = (size_t)2 * S * (C | 1) * sizeof(T);
+  int nwarps = 8;
+  while (nwarps > 1 && per_warp * nwarps > (size_t)96 * 1024) nwarps >>= 1;
+  const size_t smem = per_warp * nwarps;
+  if (smem > (size_t)200 * 1024) return fail(NTK_EUNSUPPORTED, "k_input_shear: %d channels do not fit shared memory", C);
+  const unsigned grid = (unsigned)std::min<long long>((P * S * S + nwarps - 1) / nwarps, (long long)kNumSMs * 8);
+  if (S == 32) {
+    NTK_TRY(ensure_dynamic_smem((const void*)k_input_shear<T, 32>, smem));
+    k_input_shear<T, 32><<<grid, 32 * nwarps, smem, stream>>>(x1, x2, out, P, n2, self, tri, RH, RW, C, in_scale);
+  } else if (S == 16) {
+    NTK_TRY(ensure_dynamic_smem((const void*)k_input_shear<T, 16>, smem));
+    k_input_shear<T, 16><<<grid, 32 * nwarps, smem, stream>>>(x1, x2, out, P, n2, self, tri, RH, RW, C, in_scale);
+  } else {
+    NTK_TRY(ensure_dynamic_smem((const void*)k_input_shear<T, 8>, smem));
+    k_input_shear<T, 8><<<grid, 32 * nwarps, smem, stream>>>(x1, x2, out, P, n2, self, tri, RH, RW, C, in_scale);
+  }
+  NTK_CUDA(cudaGetLastError());
+  return NTK_OK;
 }
 
 // RH x RW: the real image size (<= S; the image sits in the top-left corner of the S x S map, see StageArgs).
@@ -1174,10 +1209,24 @@ inline int fused_shear_size(int H, int W) {
 
 // Images that are not S x S RGB run the EMB family of the scalar stage kernels (pure ABRelu stages only).
 // Other channel counts (round 2) go through k_input_shear and LOADing first stages, which exist in every family.
-inline bool fused_needs_prepass(int C) { return C != 1 && C != 3; }
-inline bool fused_needs_emb(int H, int W, int C) {
+// Which kernel family and input mode a plan runs with.  FROM_X stages exist for C = 3 (every family) and C = 1 (EMB family).
+//   emb      images that are not a shear size, VALID convs (box-aware epilogues), and grey inputs of pure-ABRelu networks
+//            (measured on B200, grey 32 x 32 Myrtle-10 / Myrtle-5: EMB FROM_X 181 k / 299 k entries/s against 116 k / 142 k
+//            through the round-2 pre-pass + packed kernels, `profiles/grey_ab_r02.log`)
+//   prepass  every other channel count: k_input_shear + LOADing first stage; also grey shear-size inputs of networks the
+//            ABRelu-only EMB family cannot run (Erf, Gelu, ...)
+struct FusedRoute {
+  bool emb, prepass;
+};
+inline FusedRoute fused_route(const FusedPlan& plan, int H, int W, int C) {
   const bool square = H == W && (H == 32 || H == 16 || H == 8);
-  return !(square && C != 1);
+  bool pure_abrelu = true;
+  for (size_t s = 0; s + 1 < plan.stages.size(); ++s)
+    for (int l = 0; l < plan.stages[s].L; ++l) pure_abrelu = pure_abrelu && plan.stages[s].kind[l] == ACT_ABRELU;
+  FusedRoute r;
+  r.emb = !square || plan.valid_convs || (C == 1 && pure_abrelu);
+  r.prepass = r.emb ? (C != 1 && C != 3) : C != 3;
+  return r;
 }
 
 template <typename T>
@@ -1186,7 +1235,7 @@ bool fused_supported(const FusedPlan& plan, int H, int W, int C) {
   int S = fused_shear_size(H, W);
   if (S == 0) return false;
   if (C < 1) return false;  // C = 1, 3: FROM_X stages; any other C: k_input_shear + LOADing first stage
-  const bool emb = fused_needs_emb(H, W, C) || plan.valid_convs;  // VALID convs need the box-aware (EMB) epilogues
+  const bool emb = fused_route(plan, H, W, C).emb;
   FusedBox last{0, H, W};
   std::vector<FusedBox> in_box;
   if (!fused_walk_boxes(plan, H, W, &in_box, &last)) return false;
@@ -1458,8 +1507,8 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
                int W0, int C, bool want_ntk, T* out_nngp, T* out_ntk, long long ld,
                bool full_square = false, bool upper = false) {
   const int S0 = fused_shear_size(H0, W0);
-  const bool emb = fused_needs_emb(H0, W0, C) || plan.valid_convs;
-  const bool prepass = fused_needs_prepass(C);  // stage 0 LOADs the sheared input covariance written by k_input_shear
+  const bool emb = fused_route(plan, H0, W0, C).emb;
+  const bool prepass = fused_route(plan, H0, W0, C).prepass;  // stage 0 LOADs the sheared input covariance of k_input_shear
   const size_t xrow = (size_t)H0 * W0 * C;  // elements per input sample
   // `upper` (NTK_FLAG_UPPER_ONLY): x1 holds the same samples as x2[0:n1]; only entries (i, j >= i) are wanted.
   upper = upper && !symmetric && n2 >= n1;
@@ -1544,10 +1593,8 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
                                   RWs[s]));
         if (s + 1 == n_st) break;  // the last stage's self tensors are never needed
         if (s == 0 && prepass) {
-          (*launches)++;
-          k_input_shear<T><<<(unsigned)std::min<long long>((long long)m * S * S, (long long)kNumSMs * 64), 256, 0, stream>>>(
-              x + (size_t)c0 * xrow, x + (size_t)c0 * xrow, bufX, m, 1, 1, 0, S, RHs[0], RWs[0], C, in_scale);
-          NTK_CUDA(cudaGetLastError());
+          NTK_TRY(launch_input_shear<T>(stream, launches, S, x + (size_t)c0 * xrow, x + (size_t)c0 * xrow, bufX, m, 1, 1, 0,
+                                        RHs[0], RWs[0], C, in_scale));
           cur = bufX;
         }
         // run the stage on the self pairs (nngp only) to get the next boundary
@@ -1655,11 +1702,8 @@ int fused_gram(const FusedPlan& plan, Arena& arena, cudaStream_t stream, int64_t
       const long long P = tri_tile ? tri_prefix(a1, a2) : (long long)a1 * a2;
       T* cur = nullptr;
       if (prepass) {
-        (*launches)++;
-        k_input_shear<T><<<(unsigned)std::min<long long>(P * S0 * S0, (long long)kNumSMs * 64), 256, 0, stream>>>(
-            x1 + (size_t)r0 * xrow, x2 + (size_t)c0 * xrow, bnd[0], P, a2, 0, tri_tile ? 1 : 0, S0, RHs[0], RWs[0], C,
-            in_scale);
-        NTK_CUDA(cudaGetLastError());
+        NTK_TRY(launch_input_shear<T>(stream, launches, S0, x1 + (size_t)r0 * xrow, x2 + (size_t)c0 * xrow, bnd[0], P, a2, 0,
+                                      tri_tile ? 1 : 0, RHs[0], RWs[0], C, in_scale));
         cur = bnd[0];
       }
       for (size_t s = 0; s < n_st; ++s) {

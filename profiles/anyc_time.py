@@ -1,0 +1,10 @@
+import sys, time, json, numpy as np
+sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests/golden')
+import cases, neural_tangents_b200 as nt
+for C in (3, 1, 4, 16):
+  _, _, k = cases.build(cases.myrtle(10, 'gap'), nt.stax)
+  x1 = np.random.default_rng(1).standard_normal((96, 32, 32, C)).astype(np.float32)
+  x2 = np.random.default_rng(2).standard_normal((96, 32, 32, C)).astype(np.float32)
+  k(x1[:8], x2[:8], ('nngp', 'ntk'))
+  t0 = time.perf_counter(); r = k(x1, x2, ('nngp', 'ntk')); dt = time.perf_counter() - t0
+  print(json.dumps(dict(C=C, entries_per_s=round(96 * 96 / dt))))

@@ -238,6 +238,7 @@ def test_fused_path_covers_grey_nonsquare_and_mnist_sizes(lib):
   assert path(same_pool, 15, 15, 3) == 'generic'              # SAME pads an odd size with zeros
   erf5 = ('serial', [('erf', 1., 1., 0.) if l == cases.RELU else l for l in gap5[1]])
   assert path(erf5, 32, 32, 3) == 'fused' and path(erf5, 28, 28, 1) == 'generic'
+  assert path(erf5, 32, 32, 1) == 'fused' and path(erf5, 32, 32, 5) == 'fused'   # shear sizes, any C: pre-pass + Erf family
   # SumPool / GlobalSumPool ride the same kernels (epilogue scales)
   sp = ('serial', [cases.conv(), cases.RELU, ('sumpool', (2, 2), (2, 2), 'VALID'), cases.conv(), cases.RELU, ('gsp',)])
   assert path(sp, 32, 32, 3) == 'fused' and path(sp, 28, 28, 1) == 'fused'

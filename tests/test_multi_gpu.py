@@ -454,6 +454,27 @@ def test_any_channel_count_on_the_fused_path(nt, shape):
   nt.config.update('enable_x64', False)
 
 
+def test_grey_erf_network_runs_on_the_fused_path_through_the_prepass(nt):
+  """Grey shear-size inputs of networks the ABRelu-only EMB family cannot run (Erf): k_input_shear + the Erf families."""
+  from oracle import ntk_oracle as O
+  erf = ('erf', 1., 1.1, 0.1)
+  spec = ('serial', [cases.conv(W=1.2, b=0.1), erf, cases.conv(), erf, cases.pool(), cases.conv(), cases.RELU, ('gap',),
+                     ('dense', 1., 0.1)])
+  _, _, kernel_fn = cases.build(spec, nt.stax)
+  low = nt.stax._lowered(nt.stax._strip(kernel_fn._spec), False, False, True)
+  for shape in ((32, 32, 1), (16, 16, 2)):
+    assert low.program.path(*shape) == 'fused'
+    x1 = np.random.default_rng(71).standard_normal((3,) + shape).astype(np.float32)
+    x2 = np.random.default_rng(72).standard_normal((2,) + shape).astype(np.float32)
+    ref = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'))
+    for x64 in (False, True):
+      nt.config.update('enable_x64', x64)
+      out = kernel_fn(x1, x2, ('nngp', 'ntk'))
+      np.testing.assert_allclose(out.nngp, ref[0], rtol=RTOL[x64])
+      np.testing.assert_allclose(out.ntk, ref[1], rtol=RTOL[x64])
+  nt.config.update('enable_x64', False)
+
+
 def test_sum_pools_on_the_fused_kernels(nt):
   """SumPool / GlobalSumPool (linear.py:1503, 1674) are epilogue scales of the fused kernels."""
   from oracle import ntk_oracle as O
