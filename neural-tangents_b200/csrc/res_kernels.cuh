@@ -205,13 +205,14 @@ k_res(const ResArgs<T> a) {
   const int nrows = ngroups * S;
   // compact tensor geometry: [p][kh][h][w][kw]
   const long long in_pair = (long long)ncw * S * S * ncw;
-  auto row_off = [&](int r, int& h, int& ch) -> long long {
+  // offsets inside one pair's tensor fit 32 bits (<= S^4 elements): int index arithmetic, one 64-bit add per access
+  auto row_off = [&](int r, int& h, int& ch) -> int {
     // marched row r -> (column group, h); this thread's column index kh and ch
     const int cg = r / S;
     h = r % S;
     const int kh = cg * cws + chs;
     ch = kh * cws;
-    return ((long long)kh * S + h) * S * ncw;
+    return (kh * S + h) * S * ncw;
   };
   const T* inK = IN == IN_LOAD ? a.inK + p * in_pair : nullptr;
   const T* inT = (IN == IN_LOAD && NTK) ? a.inT + p * in_pair : nullptr;
@@ -224,11 +225,11 @@ k_res(const ResArgs<T> a) {
   auto load_row = [&](const T* bk, const T* bt, int r, T* dk, T* dt) {
     int h, ch;
     const int rc = r < 0 ? 0 : (r > nrows - 1 ? nrows - 1 : r);
-    const long long ro = row_off(rc, h, ch) + (long long)w0 * ncw + kw;
+    const int ro = row_off(rc, h, ch) + w0 * ncw + kw;
 #pragma unroll
     for (int i = 0; i < WPT; ++i) {
-      dk[i] = __ldg(bk + ro + (long long)i * ncw);
-      dt[i] = NTK ? __ldg(bt + ro + (long long)i * ncw) : (T)0;
+      dk[i] = __ldg(bk + (ro + i * ncw));
+      dt[i] = NTK ? __ldg(bt + (ro + i * ncw)) : (T)0;
     }
   };
 
@@ -240,11 +241,11 @@ k_res(const ResArgs<T> a) {
     if (IN == IN_LOAD) {
       int h, ch;
       const int rc = r < 0 ? 0 : (r > nrows - 1 ? nrows - 1 : r);
-      const long long ro = row_off(rc, h, ch) + (long long)w0 * ncw + kw;
+      const int ro = row_off(rc, h, ch) + w0 * ncw + kw;
 #pragma unroll
       for (int i = 0; i < WPT; ++i) {
-        res_cp_async<sizeof(T)>(ring_at(r, 0, i), inK + ro + (long long)i * ncw);
-        if (NTK) res_cp_async<sizeof(T)>(ring_at(r, 1, i), inT + ro + (long long)i * ncw);
+        res_cp_async<sizeof(T)>(ring_at(r, 0, i), inK + (ro + i * ncw));
+        if (NTK) res_cp_async<sizeof(T)>(ring_at(r, 1, i), inT + (ro + i * ncw));
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
@@ -421,13 +422,15 @@ k_res(const ResArgs<T> a) {
     // ---- epilogue on row r_out ----------------------------------------------------------------
     if (r_out >= 0 && r_out < nrows && live) {
       int h, ch;
-      const long long ro = row_off(r_out, h, ch);
+      const int ro = row_off(r_out, h, ch);
       if (a.epi == REPI_STORE) {
-        const long long base = p * in_pair + ro + (long long)w0 * ncw + kw;
+        T* oK = a.outK + p * in_pair;
+        T* oT = (NTK && a.outT) ? a.outT + p * in_pair : nullptr;  // outT == nullptr: the ntk equals the nngp (stem)
+        const int base = ro + w0 * ncw + kw;
 #pragma unroll
         for (int i = 0; i < WPT; ++i) {
-          a.outK[base + (long long)i * ncw] = YK[i];
-          if (NTK && a.outT) a.outT[base + (long long)i * ncw] = YT[i];  // outT == nullptr: the ntk equals the nngp (stem)
+          oK[base + i * ncw] = YK[i];
+          if (oT) oT[base + i * ncw] = YT[i];
         }
       } else if (a.epi == REPI_SUB) {
         // stride-2 SAME conv == stride-1 box filter sampled at odd (h, w); output at S/2 keeps the
