@@ -82,10 +82,14 @@ struct ResGeom {
 // form); pure-ABRelu networks run the ERF = false instantiation, which carries no Erf code.
 // fp32: 8 w per thread for ABRelu networks, 4 for networks with Erf (measured on B200 with the input ring, WideResNet
 // block 96 x 96: Relu 436.6 k entries/s at 8 w vs 376.1 k at 4 w; Erf 320.6 k at 8 w vs 349.3 k at 4 w -- the Erf rows carry
-// more live values per element, at 8 w the kernel sits at 255 registers).
+// more live values per element, at 8 w the kernel sits at 255 registers).  fp64: 4 w; 2 w (16 warps per SM, NTK_RES_WPT_F64=2) measured
+// slower for ABRelu (168.8 k vs 186.1 k) and equal for Erf (154.8 k vs 153.5 k).
 template <typename T, bool ERF>
 struct ResWpt {
-  static constexpr int value = sizeof(T) == 8 ? 4 : (ERF ? 4 : 8);
+#ifndef NTK_RES_WPT_F64
+#define NTK_RES_WPT_F64 4
+#endif
+  static constexpr int value = sizeof(T) == 8 ? NTK_RES_WPT_F64 : (ERF ? 4 : 8);
 };
 
 // Input rows of a LOADing kernel travel through a per-thread ring in shared memory, filled with cp.async one marched row

@@ -239,6 +239,14 @@ def test_fused_path_covers_grey_nonsquare_and_mnist_sizes(lib):
   erf5 = ('serial', [('erf', 1., 1., 0.) if l == cases.RELU else l for l in gap5[1]])
   assert path(erf5, 32, 32, 3) == 'fused' and path(erf5, 28, 28, 1) == 'generic'
   assert path(erf5, 32, 32, 1) == 'fused' and path(erf5, 32, 32, 5) == 'fused'   # shear sizes, any C: pre-pass + Erf family
+  # 3x3 / 1 / VALID convs: Flatten nets on the diagonal-column kernels, pooled / GAP nets on the stage kernels when every pool sits
+  # behind an even number of VALID convs (the box origin must be even), otherwise per op
+  V = lambda: cases.conv(pad='VALID')
+  assert path(('serial', [V(), cases.RELU] * 3 + [('flatten',), ('dense', 1., 0.)]), 12, 12, 3) == 'diag'
+  assert path(('serial', [V(), cases.RELU] * 2 + [cases.pool(), V(), cases.RELU, ('gap',)]), 28, 28, 1) == 'fused'
+  assert path(('serial', [V(), cases.RELU] * 3 + [cases.pool(), V(), cases.RELU, ('gap',)]), 16, 16, 3) == 'generic'
+  assert path(('serial', [V(), cases.RELU, cases.conv(), cases.RELU, ('gap',)]), 16, 16, 3) == 'generic'   # mixed paddings
+  assert path(('serial', [V(), cases.RELU] * 4 + [('gap',)]), 8, 8, 3) == 'generic'                         # 8 - 2 * 4: empty map
   # SumPool / GlobalSumPool ride the same kernels (epilogue scales)
   sp = ('serial', [cases.conv(), cases.RELU, ('sumpool', (2, 2), (2, 2), 'VALID'), cases.conv(), cases.RELU, ('gsp',)])
   assert path(sp, 32, 32, 3) == 'fused' and path(sp, 28, 28, 1) == 'fused'
