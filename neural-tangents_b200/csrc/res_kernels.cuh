@@ -510,7 +510,10 @@ k_res(const ResArgs<T> a) {
 // ---------------------------------------------------------------------------------------
 enum { Q_CONV = 0, Q_ACT = 1, Q_COPY = 2, Q_ADD = 3, Q_INPUT = 4 };
 constexpr int kQValid = 3;  // QOp::stride code of a VALID conv (linear.py:3341-3378 with no padding: every tap is inside)
-__host__ __device__ __forceinline__ int qconv_out_size(int S, int st) { return st == kQValid ? S - 2 : (S + st - 1) / st; }
+constexpr int kQCirc = 4;   // 3x3 / stride 1 / CIRCULAR (linear.py:3158-3165: wrap-pad by the SAME amounts, then VALID): taps mod S
+__host__ __device__ __forceinline__ int qconv_out_size(int S, int st) {
+  return st == kQValid ? S - 2 : (st == kQCirc ? S : (S + st - 1) / st);
+}
 // A 3x3 / stride-2 / SAME conv on a size-S axis (lax.padtype_to_pads): out = ceil(S/2), total padding
 // (out-1)*2 + 3 - S = 1 (S even: lo = 0, window centred at 2a+1) or 2 (S odd: lo = 1, centred at 2a).
 __host__ __device__ __forceinline__ int strided_center_offset(int S) { return (S & 1) ? 0 : 1; }
@@ -573,8 +576,10 @@ __global__ void k_qprog(const T* __restrict__ x, int S0, int C, T in_scale, cons
       const T* P = img + sidx * S0 * S0;
       for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
         const int h = e / S, w = e % S;
-        const T mL = w > 0 ? (T)1 : (T)0, mR = w < S - 1 ? (T)1 : (T)0;
-        scratch[e] = hsum3<T>(P[h * S + (w > 0 ? w - 1 : w)], P[e], P[h * S + (w < S - 1 ? w + 1 : w)], mL, mR);
+        const bool circ = prog.stride[op] == kQCirc;
+        const T mL = (circ || w > 0) ? (T)1 : (T)0, mR = (circ || w < S - 1) ? (T)1 : (T)0;
+        scratch[e] = hsum3<T>(P[h * S + (w > 0 ? w - 1 : (circ ? S - 1 : w))], P[e],
+                              P[h * S + (w < S - 1 ? w + 1 : (circ ? 0 : w))], mL, mR);
       }
       __syncthreads();
       const int st = prog.stride[op];
@@ -585,9 +590,10 @@ __global__ void k_qprog(const T* __restrict__ x, int S0, int C, T in_scale, cons
         const int a_ = e / So, b_ = e % So;
         const int h = st == 2 ? 2 * a_ + o2 : (st == kQValid ? a_ + 1 : a_);
         const int w = st == 2 ? 2 * b_ + o2 : (st == kQValid ? b_ + 1 : b_);
-        const T vU = h > 0 ? (T)1 : (T)0, vD = h < S - 1 ? (T)1 : (T)0;
-        const T box = fma_t(vD, scratch[(h < S - 1 ? h + 1 : h) * S + w],
-                            fma_t(vU, scratch[(h > 0 ? h - 1 : h) * S + w], scratch[h * S + w]));
+        const bool circ = st == kQCirc;
+        const T vU = (circ || h > 0) ? (T)1 : (T)0, vD = (circ || h < S - 1) ? (T)1 : (T)0;
+        const T box = fma_t(vD, scratch[(h < S - 1 ? h + 1 : (circ ? 0 : h)) * S + w],
+                            fma_t(vU, scratch[(h > 0 ? h - 1 : (circ ? S - 1 : h)) * S + w], scratch[h * S + w]));
         D[e] = fma_t(box, prog.alpha[op], prog.bias[op]);
       }
       __syncthreads();
@@ -1132,8 +1138,9 @@ k_diagnet(const T* __restrict__ x1, const T* __restrict__ x2, int S0, int C, T i
         const T* PT = imgT + sidx * SS;
         for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
           const int h = e / S, w = e % S;
-          const T mL = w > 0 ? (T)1 : (T)0, mR = w < S - 1 ? (T)1 : (T)0;
-          const int el = h * S + (w > 0 ? w - 1 : w), er = h * S + (w < S - 1 ? w + 1 : w);
+          const bool circ = prog.stride[op] == kQCirc;
+          const T mL = (circ || w > 0) ? (T)1 : (T)0, mR = (circ || w < S - 1) ? (T)1 : (T)0;
+          const int el = h * S + (w > 0 ? w - 1 : (circ ? S - 1 : w)), er = h * S + (w < S - 1 ? w + 1 : (circ ? 0 : w));
           scK[e] = hsum3<T>(PK[el], PK[e], PK[er], mL, mR);
           if (ht) scT[e] = hsum3<T>(PT[el], PT[e], PT[er], mL, mR);
         }
@@ -1145,8 +1152,9 @@ k_diagnet(const T* __restrict__ x1, const T* __restrict__ x2, int S0, int C, T i
           const int a_ = e / So, b_ = e % So;
           const int h = st == 2 ? 2 * a_ + o2 : (st == kQValid ? a_ + 1 : a_);
           const int w = st == 2 ? 2 * b_ + o2 : (st == kQValid ? b_ + 1 : b_);
-          const T vU = h > 0 ? (T)1 : (T)0, vD = h < S - 1 ? (T)1 : (T)0;
-          const int eu = (h > 0 ? h - 1 : h) * S + w, ed = (h < S - 1 ? h + 1 : h) * S + w;
+          const bool circ = st == kQCirc;
+          const T vU = (circ || h > 0) ? (T)1 : (T)0, vD = (circ || h < S - 1) ? (T)1 : (T)0;
+          const int eu = (h > 0 ? h - 1 : (circ ? S - 1 : h)) * S + w, ed = (h < S - 1 ? h + 1 : (circ ? 0 : h)) * S + w;
           const T k = fma_t(fma_t(vD, scK[ed], fma_t(vU, scK[eu], scK[h * S + w])), prog.alpha[op],
                             prog.bias[op]);
           DK[e] = k;
@@ -1272,10 +1280,12 @@ inline DiagPlan plan_diag(const std::vector<ntk_op_t>& ops, const std::vector<in
     if (o.kind == NTK_OP_CONV) {
       const bool same = o.i[4] == NTK_PAD_SAME && (o.i[2] == 1 || o.i[2] == 2);
       const bool valid = o.i[4] == NTK_PAD_VALID && o.i[2] == 1;  // round 2: VALID 3x3 / 1 on the diagonal column
-      if (!(o.i[0] == 3 && o.i[1] == 3 && o.i[2] == o.i[3] && (same || valid))) return DiagPlan();
+      const bool circ = o.i[4] == NTK_PAD_CIRCULAR && o.i[2] == 1;  // and CIRCULAR 3x3 / 1 (taps mod S)
+      if (!(o.i[0] == 3 && o.i[1] == 3 && o.i[2] == o.i[3] && (same || valid || circ))) return DiagPlan();
       const int b = dst_buf(o.src, src_dies);
       if (b < 0) return DiagPlan();
-      plan.ops.push_back(QOp{Q_CONV, b, b, valid ? kQValid : o.i[2], 0, o.f[0] / 9.0, o.i[5] ? o.f[1] : 0.0, 0.0});
+      plan.ops.push_back(
+          QOp{Q_CONV, b, b, valid ? kQValid : (circ ? kQCirc : o.i[2]), 0, o.f[0] / 9.0, o.i[5] ? o.f[1] : 0.0, 0.0});
       buf_of[o.dst] = b;
     } else if (o.kind == NTK_OP_ABRELU || o.kind == NTK_OP_ERF) {
       if (o.kind == NTK_OP_ABRELU && o.i[0]) return DiagPlan();

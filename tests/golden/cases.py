@@ -145,6 +145,10 @@ CASES = {
     'valid_pool_gap_mnist_sym': (('serial', [conv(pad='VALID'), RELU, conv(pad='VALID'), RELU, pool(),
                                              conv(pad='VALID'), RELU, conv(pad='VALID'), RELU, ('gap',), ('dense', SQ2, 0.)]),
                                  (3, 28, 28, 1), None, ('nngp', 'ntk')),
+    # 3x3 / 1 / CIRCULAR convs ending in Flatten (diagonal-column kernels, taps mod S), Relu and Erf
+    'circular_flatten': (('serial', [conv(pad='CIRCULAR', W=1.3, b=0.1), RELU, conv(pad='CIRCULAR'), ('erf', 1., 0.9, 0.1),
+                                     conv(pad='CIRCULAR', W=1.1, b=0.05), RELU, ('flatten',), ('dense', 1., 0.1)]),
+                         (3, 9, 9, 2), (2, 9, 9, 2), ('nngp', 'ntk')),
 }
 
 

@@ -243,6 +243,7 @@ def test_fused_path_covers_grey_nonsquare_and_mnist_sizes(lib):
   # behind an even number of VALID convs (the box origin must be even), otherwise per op
   V = lambda: cases.conv(pad='VALID')
   assert path(('serial', [V(), cases.RELU] * 3 + [('flatten',), ('dense', 1., 0.)]), 12, 12, 3) == 'diag'
+  assert path(cases.CASES['circular_flatten'][0], 9, 9, 2) == 'diag'                                        # CIRCULAR: taps mod S
   assert path(('serial', [V(), cases.RELU] * 2 + [cases.pool(), V(), cases.RELU, ('gap',)]), 28, 28, 1) == 'fused'
   assert path(('serial', [V(), cases.RELU] * 3 + [cases.pool(), V(), cases.RELU, ('gap',)]), 16, 16, 3) == 'generic'
   assert path(('serial', [V(), cases.RELU, cases.conv(), cases.RELU, ('gap',)]), 16, 16, 3) == 'generic'   # mixed paddings
