@@ -20,6 +20,8 @@ NTK_FUSED_ERF_INSTANCES(extern, float)
 NTK_FUSED_ERF_INSTANCES(extern, double)
 NTK_FUSED_EMB_INSTANCES(extern, float)
 NTK_FUSED_EMB_INSTANCES(extern, double)
+NTK_FUSED_EMB_GEN_INSTANCES(extern, float)
+NTK_FUSED_EMB_GEN_INSTANCES(extern, double)
 NTK_FUSED_GEN_INSTANCES(extern, float)
 NTK_FUSED_GEN_INSTANCES(extern, double)
 NTK_RES_ERF_INSTANCES(extern, float)

@@ -3,6 +3,7 @@
 namespace ntk {
 NTK_FUSED_ERF_INSTANCES(extern, float)
 NTK_FUSED_EMB_INSTANCES(extern, float)
+NTK_FUSED_EMB_GEN_INSTANCES(extern, float)
 NTK_FUSED_GEN_INSTANCES(extern, float)
 NTK_FUSED_INSTANCES(, float)
 }  // namespace ntk

@@ -3,6 +3,7 @@
 namespace ntk {
 NTK_FUSED_ERF_INSTANCES(extern, double)
 NTK_FUSED_EMB_INSTANCES(extern, double)
+NTK_FUSED_EMB_GEN_INSTANCES(extern, double)
 NTK_FUSED_GEN_INSTANCES(extern, double)
 NTK_FUSED_INSTANCES(, double)
 }  // namespace ntk

@@ -1241,9 +1241,6 @@ bool fused_supported(const FusedPlan& plan, int H, int W, int C) {
   if (!fused_walk_boxes(plan, H, W, &in_box, &last)) return false;
   for (size_t s = 0; s + 1 < plan.stages.size(); ++s) {
     const FusedStage& st = plan.stages[s];
-    if (emb)
-      for (int l = 0; l < st.L; ++l)
-        if (st.kind[l] != ACT_ABRELU) return false;  // the EMB family carries no Erf code
     if (st.epi == EPI_POOL) {
       if (S <= 8) return false;  // S = 4 stages are not instantiated
       // VALID drops an odd last row (floor); SAME pads it with zeros the garbage outside the image cannot provide
@@ -1330,24 +1327,25 @@ int launch_stage_L(cudaStream_t stream, int64_t* launches, int L, int epi, const
   }
 }
 
-// EMB family (pure ABRelu): images of any size RH x RW <= S x S with C in {1, 3}; instantiated in fused_*_emb.cu.
-template <typename T, bool NTK>
+// EMB family: images of any size RH x RW <= S x S (FROM_X: C in {1, 3}).  ERF = 0: pure ABRelu (fused_*_emb.cu); ERF = 2: the
+// general activation family (ABRelu / Erf / Gelu / Sin / Rbf, fused_*_emb_gen.cu) for MNIST-sized inputs and VALID stacks.
+template <typename T, bool NTK, int ERF = 0>
 int launch_stage_emb(cudaStream_t stream, int64_t* launches, int S, int L, int from_x, int C, int epi,
                      const StageArgs<T>& a) {
   if (from_x) {
     if (C == 1) {
-      if (S == 32) return launch_stage_L<T, 32, IN_FROM_X, NTK, 1, false, true>(stream, launches, L, epi, a);
-      if (S == 16) return launch_stage_L<T, 16, IN_FROM_X, NTK, 1, false, true>(stream, launches, L, epi, a);
-      return launch_stage_L<T, 8, IN_FROM_X, NTK, 1, false, true>(stream, launches, L, epi, a);
+      if (S == 32) return launch_stage_L<T, 32, IN_FROM_X, NTK, 1, ERF, true>(stream, launches, L, epi, a);
+      if (S == 16) return launch_stage_L<T, 16, IN_FROM_X, NTK, 1, ERF, true>(stream, launches, L, epi, a);
+      return launch_stage_L<T, 8, IN_FROM_X, NTK, 1, ERF, true>(stream, launches, L, epi, a);
     }
     if (C != 3) return fail(NTK_EUNSUPPORTED, "fused FROM_X stages are instantiated for C == 1 and C == 3");
-    if (S == 32) return launch_stage_L<T, 32, IN_FROM_X, NTK, 3, false, true>(stream, launches, L, epi, a);
-    if (S == 16) return launch_stage_L<T, 16, IN_FROM_X, NTK, 3, false, true>(stream, launches, L, epi, a);
-    return launch_stage_L<T, 8, IN_FROM_X, NTK, 3, false, true>(stream, launches, L, epi, a);
+    if (S == 32) return launch_stage_L<T, 32, IN_FROM_X, NTK, 3, ERF, true>(stream, launches, L, epi, a);
+    if (S == 16) return launch_stage_L<T, 16, IN_FROM_X, NTK, 3, ERF, true>(stream, launches, L, epi, a);
+    return launch_stage_L<T, 8, IN_FROM_X, NTK, 3, ERF, true>(stream, launches, L, epi, a);
   }
-  if (S == 32) return launch_stage_L<T, 32, IN_LOAD, NTK, 1, false, true>(stream, launches, L, epi, a);
-  if (S == 16) return launch_stage_L<T, 16, IN_LOAD, NTK, 1, false, true>(stream, launches, L, epi, a);
-  return launch_stage_L<T, 8, IN_LOAD, NTK, 1, false, true>(stream, launches, L, epi, a);
+  if (S == 32) return launch_stage_L<T, 32, IN_LOAD, NTK, 1, ERF, true>(stream, launches, L, epi, a);
+  if (S == 16) return launch_stage_L<T, 16, IN_LOAD, NTK, 1, ERF, true>(stream, launches, L, epi, a);
+  return launch_stage_L<T, 8, IN_LOAD, NTK, 1, ERF, true>(stream, launches, L, epi, a);
 }
 
 // Packed-FP32 (FFMA2) instance for fp32 at 32x32: stage_packed.cuh / stage_packed.cu.
@@ -1406,7 +1404,7 @@ int launch_stage(cudaStream_t stream, int64_t* launches, int S, int L, int from_
   }
   const bool any_erf = n_erf > 0;
   if (emb) {
-    if (any_erf || n_gen) return fail(NTK_EUNSUPPORTED, "the embedded-size stage kernels are ABRelu only");
+    if (any_erf || n_gen) return launch_stage_emb<T, NTK, 2>(stream, launches, S, L, from_x, C, epi, a);
     return launch_stage_emb<T, NTK>(stream, launches, S, L, from_x, C, epi, a);
   }
   if (n_gen) return launch_stage_k<T, NTK, 2>(stream, launches, S, L, from_x, C, epi, a);

@@ -24,10 +24,17 @@
 
 // launch_stage_emb<T, NTK> (embedded-size scalar stage kernels, C in {1, 3}) lives in fused_*_emb.cu
 #define NTK_FUSED_EMB_INSTANCES(KW, T)                                                                     \
-  KW template int launch_stage_emb<T, true>(cudaStream_t, int64_t*, int, int, int, int, int,               \
-                                            const StageArgs<T>&);                                          \
-  KW template int launch_stage_emb<T, false>(cudaStream_t, int64_t*, int, int, int, int, int,              \
-                                             const StageArgs<T>&);
+  KW template int launch_stage_emb<T, true, 0>(cudaStream_t, int64_t*, int, int, int, int, int,            \
+                                               const StageArgs<T>&);                                       \
+  KW template int launch_stage_emb<T, false, 0>(cudaStream_t, int64_t*, int, int, int, int, int,           \
+                                                const StageArgs<T>&);
+
+// launch_stage_emb<T, NTK, 2> (embedded sizes, general activation family) lives in fused_*_emb_gen.cu
+#define NTK_FUSED_EMB_GEN_INSTANCES(KW, T)                                                                 \
+  KW template int launch_stage_emb<T, true, 2>(cudaStream_t, int64_t*, int, int, int, int, int,            \
+                                               const StageArgs<T>&);                                       \
+  KW template int launch_stage_emb<T, false, 2>(cudaStream_t, int64_t*, int, int, int, int, int,           \
+                                                const StageArgs<T>&);
 
 #define NTK_FUSED_INSTANCES(KW, T)                                                                        \
   KW template int fused_gram<T>(const FusedPlan&, Arena&, cudaStream_t, int64_t*, StageProfile*, const T*, \

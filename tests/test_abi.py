@@ -237,7 +237,7 @@ def test_fused_path_covers_grey_nonsquare_and_mnist_sizes(lib):
   assert path(same_pool, 16, 16, 3) == 'fused'                # SAME == VALID on even sizes
   assert path(same_pool, 15, 15, 3) == 'generic'              # SAME pads an odd size with zeros
   erf5 = ('serial', [('erf', 1., 1., 0.) if l == cases.RELU else l for l in gap5[1]])
-  assert path(erf5, 32, 32, 3) == 'fused' and path(erf5, 28, 28, 1) == 'generic'
+  assert path(erf5, 32, 32, 3) == 'fused' and path(erf5, 28, 28, 1) == 'fused'      # EMB general-activation family
   assert path(erf5, 32, 32, 1) == 'fused' and path(erf5, 32, 32, 5) == 'fused'   # shear sizes, any C: pre-pass + Erf family
   # 3x3 / 1 / VALID convs: Flatten nets on the diagonal-column kernels, pooled / GAP nets on the stage kernels when every pool sits
   # behind an even number of VALID convs (the box origin must be even), otherwise per op
@@ -254,5 +254,5 @@ def test_fused_path_covers_grey_nonsquare_and_mnist_sizes(lib):
   # Gelu / Sin / Rbf stages: the general family of the fused stage kernels at the native sizes, per-op elsewhere
   assert path(cases.CASES['gelu_conv'][0], 32, 32, 3) == 'fused'
   assert path(cases.CASES['rbf_conv_pool'][0], 16, 16, 3) == 'fused'
-  assert path(cases.CASES['gelu_conv'][0], 28, 28, 1) == 'generic'
+  assert path(cases.CASES['gelu_conv'][0], 28, 28, 1) == 'fused'
   assert path(cases.CASES['layernorm_conv'][0], 32, 32, 3) == 'generic'

@@ -475,6 +475,35 @@ def test_grey_erf_network_runs_on_the_fused_path_through_the_prepass(nt):
   nt.config.update('enable_x64', False)
 
 
+def test_embedded_sizes_with_erf_gelu_sin_run_on_the_fused_path(nt):
+  """The EMB family with the general activation code (fused_*_emb_gen.cu): MNIST-sized / non-square inputs and VALID stacks
+  whose stages contain Erf / Gelu / Sin layers, against the oracle."""
+  from oracle import ntk_oracle as O
+  erf = ('erf', 1., 1.1, 0.1)
+  V = lambda **kw: cases.conv(pad='VALID', **kw)
+  nets = [
+      (('serial', [cases.conv(W=1.2, b=0.1), erf, cases.conv(), erf, cases.pool(), cases.conv(), cases.RELU, ('gap',),
+                   ('dense', 1., 0.1)]), [(28, 28, 1), (20, 24, 3)]),
+      (('serial', [cases.conv(W=1.2, b=0.1), ('gelu',), cases.conv(W=1.1, b=0.), ('sin', 1.1, 0.7, 0.2), ('gap',),
+                   ('dense', 1., 0.1)]), [(12, 12, 3), (28, 28, 1)]),
+      (('serial', [V(W=1.2, b=0.1), erf, V(), ('gelu',), ('gap',), ('dense', 1., 0.)]), [(16, 16, 3), (14, 10, 2)]),
+  ]
+  for spec, shapes in nets:
+    _, _, kernel_fn = cases.build(spec, nt.stax)
+    low = nt.stax._lowered(nt.stax._strip(kernel_fn._spec), False, False, True)
+    for shape in shapes:
+      assert low.program.path(*shape) == 'fused', shape
+      x1 = np.random.default_rng(81).standard_normal((3,) + shape).astype(np.float32)
+      x2 = np.random.default_rng(82).standard_normal((2,) + shape).astype(np.float32)
+      ref = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'))
+      for x64 in (False, True):
+        nt.config.update('enable_x64', x64)
+        out = kernel_fn(x1, x2, ('nngp', 'ntk'))
+        np.testing.assert_allclose(out.nngp, ref[0], rtol=RTOL[x64], err_msg=f'{shape}')
+        np.testing.assert_allclose(out.ntk, ref[1], rtol=RTOL[x64], err_msg=f'{shape}')
+  nt.config.update('enable_x64', False)
+
+
 def test_sum_pools_on_the_fused_kernels(nt):
   """SumPool / GlobalSumPool (linear.py:1503, 1674) are epilogue scales of the fused kernels."""
   from oracle import ntk_oracle as O
