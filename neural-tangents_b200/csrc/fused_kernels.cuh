@@ -1235,7 +1235,9 @@ bool fused_supported(const FusedPlan& plan, int H, int W, int C) {
   int S = fused_shear_size(H, W);
   if (S == 0) return false;
   if (C < 1) return false;  // C = 1, 3: FROM_X stages; any other C: k_input_shear + LOADing first stage
-  const bool emb = fused_route(plan, H, W, C).emb;
+  // the pre-pass stages two image rows per warp in shared memory (launch_input_shear); sized for float64 so that both dtypes
+  // of a program land on the same path
+  if (fused_route(plan, H, W, C).prepass && (size_t)2 * S * (C | 1) * sizeof(double) > (size_t)200 * 1024) return false;
   FusedBox last{0, H, W};
   std::vector<FusedBox> in_box;
   if (!fused_walk_boxes(plan, H, W, &in_box, &last)) return false;

@@ -232,6 +232,7 @@ def test_fused_path_covers_grey_nonsquare_and_mnist_sizes(lib):
   assert path(gap5, 24, 24, 3) == 'fused'
   assert path(gap5, 28, 28, 2) == 'fused'                     # other channel counts: k_input_shear + LOADing first stage
   assert path(gap5, 32, 32, 16) == 'fused' and path(cases.myrtle(10), 32, 32, 4, x64=True) == 'fused'
+  assert path(gap5, 32, 32, 128) == 'fused' and path(gap5, 32, 32, 512) == 'generic'   # pre-pass rows must fit shared memory
   assert path(gap5, 40, 40, 3) == 'generic'                   # larger than the largest shear
   same_pool = ('serial', [cases.conv(), cases.RELU, cases.pool(pad='SAME'), cases.conv(), cases.RELU, ('gap',)])
   assert path(same_pool, 16, 16, 3) == 'fused'                # SAME == VALID on even sizes
