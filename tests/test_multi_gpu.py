@@ -504,6 +504,39 @@ def test_embedded_sizes_with_erf_gelu_sin_run_on_the_fused_path(nt):
   nt.config.update('enable_x64', False)
 
 
+def test_edge_networks_on_the_fused_path(nt):
+  """Corners of the round-2 widening: a single-stage network behind the channel pre-pass (the boundary buffers exist only
+  for the pre-pass), a single VALID layer, pre-pass + VALID + embedded size, an Erf stage behind the pre-pass, four layers
+  (two chunks) at C = 5 -- cross, symmetric and nngp-only calls against the oracle."""
+  from oracle import ntk_oracle as O
+  V = lambda **kw: cases.conv(pad='VALID', **kw)
+  nets = [
+      (('serial', [cases.conv(W=1.2, b=0.1), cases.RELU, ('gap',), ('dense', 1., 0.1)]), (16, 16, 4)),
+      (('serial', [V(W=1.2, b=0.1), cases.RELU, ('gap',)]), (8, 8, 3)),
+      (('serial', [V(), cases.RELU, V(W=1.1, b=0.2), cases.RELU, ('gap',), ('dense', 1., 0.)]), (12, 12, 2)),
+      (('serial', [cases.conv(), ('erf', 1., 1., 0.), ('gap',)]), (32, 32, 2)),
+      (('serial', [cases.conv(), cases.RELU] * 4 + [('gap',)]), (16, 16, 5)),
+  ]
+  for spec, shape in nets:
+    _, _, kernel_fn = cases.build(spec, nt.stax)
+    low = nt.stax._lowered(nt.stax._strip(kernel_fn._spec), False, False, True)
+    assert low.program.path(*shape) == 'fused', shape
+    x1 = np.random.default_rng(5).standard_normal((3,) + shape).astype(np.float32)
+    x2 = np.random.default_rng(6).standard_normal((2,) + shape).astype(np.float32)
+    ref = O.kernel_fn(spec, x1, x2, ('nngp', 'ntk'))
+    sref = O.kernel_fn(spec, x1, None, ('nngp', 'ntk'))
+    for x64 in (False, True):
+      nt.config.update('enable_x64', x64)
+      out = kernel_fn(x1, x2, ('nngp', 'ntk'))
+      np.testing.assert_allclose(out.nngp, ref[0], rtol=RTOL[x64], err_msg=f'{shape}')
+      np.testing.assert_allclose(out.ntk, ref[1], rtol=RTOL[x64], err_msg=f'{shape}')
+      np.testing.assert_allclose(kernel_fn(x1, x2, 'nngp'), ref[0], rtol=RTOL[x64])
+      sym = kernel_fn(x1, None, ('nngp', 'ntk'))
+      _check_sym(sym.nngp, sref[0], x64)
+      _check_sym(sym.ntk, sref[1], x64)
+  nt.config.update('enable_x64', False)
+
+
 def test_sum_pools_on_the_fused_kernels(nt):
   """SumPool / GlobalSumPool (linear.py:1503, 1674) are epilogue scales of the fused kernels."""
   from oracle import ntk_oracle as O
